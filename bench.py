@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — rendered megapixels/s (fwd+bwd) of the RGCA shade+splat hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     CPU restatement of the same path on the host cores
+
+One "step" = one pass of the hot path over one view per rank of the BASELINE.json configs[1] workload
+(300k Gaussians, 1 view 1024x667, L=32 point lights): SG specular shade + colour compose -> EWA projection ->
+tile bin/sort -> alpha blend rgb -> alpha blend depth, forward AND backward (v_out = 1), through the
+reference-shaped Python surface (goliath_b200.sgutils.evaluate_gaussian, goliath_b200.render.render_views).
+`value` = views*H*W/1e6 / time with inputs resident in HBM; `e2e` = same through HOST buffers (H2D of the decoded
+Gaussians + D2H of images and gradients inside the timed region).  N>1: one view per rank (weak scaling), the
+frame owner (rank 0) broadcasts the decoded Gaussians and gradients are all-reduced, both inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, BW = 1024, 667, 16
+NCOL = 19  # packed decoded Gaussian: pos3 quat4 scale3 opacity1 diff3 lobe3 sigma1 specvis1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=300_000)
+    ap.add_argument("--lights", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def packed_scene(G):
+    """[G,19] fp32 decoded-Gaussian table (SURVEY.md §8d recipe) on the CPU."""
+    from goliath_b200 import synthetic
+
+    sc = synthetic.head_gaussians(G)
+    sh = synthetic.shade_inputs(G)
+    g = torch.Generator().manual_seed(synthetic.SEED + 3)
+    spec_vis = torch.sigmoid(torch.randn(G, 1, generator=g))
+    return torch.cat([sc["means3d"], sc["quats"], sc["scales"], sc["opacity"], sc["colors"], sh["lobe_dirs"][0],
+                      sh["lobe_sigmas"][0][:, None], spec_vis], 1).contiguous()
+
+
+def unpack(p):
+    return dict(primpos=p[:, 0:3], primqvec=p[:, 3:7], primscale=p[:, 7:10], opacity=p[:, 10:11],
+                diff_color=p[:, 11:14], lobe_dirs=p[:, 14:17], sigma=p[:, 17], spec_vis=p[:, 18:19])
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_step(packed, cam, li):
+    """forward + backward of shade + render for one view; returns (rgb, alpha, depth)."""
+    from goliath_b200.render import render_views
+    from goliath_b200.sgutils import evaluate_gaussian
+
+    u = unpack(packed)
+    spec = evaluate_gaussian(u["lobe_dirs"][None].contiguous(), u["sigma"][None].contiguous(), li["light_intensity"],
+                             li["light_pos"], u["primpos"][None].contiguous(), li["n_lights"], w_type=0)[0]
+    color = (u["diff_color"].clamp(min=0.0) + spec * u["spec_vis"]).clamp(min=0.0)
+    preds = dict(primpos=u["primpos"][None], primqvec=u["primqvec"][None], primscale=u["primscale"][None],
+                 opacity=u["opacity"][None], color=color[None])
+    rgb, alpha, depth = render_views(W, H, None, cam["Rt"], preds, intrinsics_host=[cam["intr"]])
+    (rgb.sum() + depth.sum()).backward()
+    return rgb, alpha, depth
+
+
+def sample_clocks_start(dev_index):
+    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(dev_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                              "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return p, f.name
+
+
+def sample_clocks_stop(p, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except Exception:
+            p.kill()
+    try:
+        rows = [r.strip().split(",") for r in open(path) if r.strip()]
+        sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any(r[3 + i].strip().lower() == "active" for r in rows if len(r) >= 7):
+                    out["reasons"].append(n)
+            out["samples"] = len(sm)
+    except Exception:
+        pass
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return out
+
+
+def kernel_roofline(dev, packed, cam, flush):
+    """Time the blend kernels alone through the C ABI (CUDA events on the launch stream, L2 flushed between
+    launches) and report achieved ALGORITHMIC bytes/s (SURVEY.md §8d formulas) against the measured HBM peak."""
+    from goliath_b200 import _lib
+    from goliath_b200.gsplat import project_gaussians
+    from goliath_b200.gsplat import utils as gu
+
+    u = unpack(packed.detach())
+    fx, fy, cx, cy = cam["intr"]
+    xys, depths, radii, conics, comp, nth, cov3d = project_gaussians(
+        u["primpos"].contiguous(), u["primscale"].contiguous(), 1.0, u["primqvec"].contiguous(), cam["Rt"][0], fx, fy,
+        cx, cy, H, W, BW, 0.1)
+    n, cum = gu.compute_cumulative_intersects(nth)
+    tb = gu._tile_bounds(H, W, BW)
+    _, _, _, gids, bins = gu.bin_and_sort_gaussians(xys.shape[0], n, xys, depths, radii, cum, tb, BW)
+    colors = u["diff_color"].contiguous()
+    opac = (u["opacity"] * comp[:, None]).contiguous()
+    bg = torch.zeros(3, device=dev)
+    out = torch.empty(H, W, 3, device=dev)
+    Ts = torch.empty(H, W, device=dev)
+    fi = torch.empty(H, W, device=dev, dtype=torch.int32)
+    G = xys.shape[0]
+    v_out = torch.ones(H, W, 3, device=dev)
+    v_a = torch.zeros(H, W, device=dev)
+    gx, gc, gcol, go = (torch.zeros(G, 2, device=dev), torch.zeros(G, 3, device=dev), torch.zeros(G, 3, device=dev),
+                        torch.zeros(G, 1, device=dev))
+    L = _lib.lib()
+    st = _lib.stream_ptr(dev)
+
+    def fwd():
+        _lib.check(L.gb_rasterize_fwd(H, W, BW, 3, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
+                                      colors.data_ptr(), opac.data_ptr(), bg.data_ptr(), out.data_ptr(), Ts.data_ptr(),
+                                      fi.data_ptr(), st), "fwd")
+
+    def bwd():
+        _lib.check(L.gb_rasterize_bwd(H, W, BW, 3, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
+                                      colors.data_ptr(), opac.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+                                      v_out.data_ptr(), v_a.data_ptr(), gx.data_ptr(), gc.data_ptr(), gcol.data_ptr(),
+                                      go.data_ptr(), st), "bwd")
+
+    def timeit(fn, reps=20):
+        ts = []
+        for _ in range(3):
+            fn()
+        for _ in range(reps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    t_f, t_b = timeit(fwd), timeit(bwd)
+    P, T, I = H * W, tb[0] * tb[1], n
+    bytes_f = I * (4 + 36) + P * (12 + 4 + 4) + T * 8
+    bytes_b = I * (4 + 36) + I * 36 + P * (8 + 12 + 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    which = "measured" if "hbm_gbs" in peaks else "fallback"
+    ks = {
+        "rasterize_fwd_kernel<3>": {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
+        "rasterize_bwd_kernel<3>": {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
+    }
+    dom = max(ks, key=lambda k: ks[k]["ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": ks[dom]["gbs"] / peak, "traffic": None, "peak_source": which, "intersections": int(I),
+            "kernels": ks}
+    return roof
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from goliath_b200 import _lib, synthetic
+
+    lib = _lib.lib()
+    G = args.gaussians
+    host_packed = packed_scene(G).pin_memory()
+    li_h = synthetic.lights(args.lights)
+    li = {k: v.to(dev) for k, v in li_h.items()}
+    c = synthetic.ring_camera(rank % 16, img_h=H, img_w=W)
+    cam = dict(Rt=c["viewmat"][None].to(dev), intr=(c["fx"], c["fy"], c["cx"], c["cy"]))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)  # > 126 MB L2
+
+    resident = host_packed.to(dev)
+
+    def one_step(e2e):
+        if e2e:
+            packed = host_packed.to(dev, non_blocking=True)
+        else:
+            packed = resident.clone() if world > 1 else resident
+        if world > 1:
+            dist.broadcast(packed, src=0)           # decoded Gaussians of the frame, owner = rank 0
+        packed = packed.detach().requires_grad_()
+        rgb, alpha, depth = gpu_step(packed, cam, li)
+        grad = packed.grad
+        if world > 1:
+            dist.all_reduce(grad)                   # dL/d(decoded) summed over the views
+        if e2e:
+            outs = [t.detach().to("cpu", non_blocking=True) for t in (rgb, alpha, depth, grad)]
+            return outs
+        return None
+
+    def timed(e2e, steps, warmup):
+        for _ in range(warmup):
+            one_step(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        lib.gb_launch_count_reset()
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            one_step(e2e)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        launches = int(lib.gb_launch_count())
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, wall
+
+    proc = path = None
+    if rank == 0:
+        proc, path = sample_clocks_start(local)
+    ms_total, launches, wall = timed(False, args.steps, args.warmup)
+    clocks = sample_clocks_stop(proc, path) if rank == 0 else None
+    ms_e2e, _, _ = timed(True, args.steps, max(3, args.warmup))
+
+    mp_per_step = world * H * W / 1e6
+    value = mp_per_step * args.steps / (ms_total / 1e3)
+    e2e_v = mp_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = host_packed.numel() * 4
+    d2h = (H * W * 3 + H * W + H * W) * 4 + host_packed.numel() * 4
+
+    roof = cpu = None
+    if rank == 0:
+        roof = kernel_roofline(dev, resident, cam, flush)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(args, steps=1, warmup=0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "rendered megapixels/sec (fwd+bwd) RGCA head 300k Gaussians", "value": value, "unit": "MP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "rgca_example.yml head: %d Gaussians, 1 view %dx%d per GPU, L=%d lights, shade+project+"
+                               "bin/sort+blend(rgb)+blend(depth) fwd+bwd" % (G, H, W, args.lights),
+                   "gaussians": G, "views_per_gpu": 1, "lights": args.lights, "block_width": BW,
+                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world},
+        "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_step(orc, P, cam, li):
+    u = {k: np.ascontiguousarray(v) for k, v in unpack(P).items()}
+    fx, fy, cx, cy = cam["intr"]
+    V = cam["Rt"]
+    nrm = u["lobe_dirs"] / np.linalg.norm(u["lobe_dirs"], axis=-1, keepdims=True)
+    spec = orc.sg_fwd(nrm[None], u["sigma"][None], li["light_intensity"], li["light_pos"], u["primpos"][None],
+                      li["n_lights"], 0)[0]
+    color = np.maximum(np.maximum(u["diff_color"], 0) + spec * u["spec_vis"], 0).astype(np.float32)
+    p = orc.project_fwd(u["primpos"], u["primscale"], 1.0, u["primqvec"], V, fx, fy, cx, cy, H, W, BW, 0.1)
+    b = orc.bin_and_sort(p["xys"], p["depths"], p["radii"], p["num_tiles_hit"], H, W, BW)
+    opac = (u["opacity"][:, 0] * p["compensation"]).astype(np.float32)
+    z3 = np.zeros(3, np.float32)
+    o1, T1, f1 = orc.rasterize_fwd(H, W, BW, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], color,
+                                   opac, z3)
+    dcol = np.repeat(p["depths"][:, None], 3, 1)
+    o2, T2, f2 = orc.rasterize_fwd(H, W, BW, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], dcol,
+                                   opac, z3)
+    ones = np.ones((H, W, 3), np.float32)
+    za = np.zeros((H, W), np.float32)
+    inv_a = (1.0 / np.clip(1 - T2, 0.05, 1.0)).astype(np.float32)
+    wd = np.zeros((H, W, 3), np.float32)
+    wd[..., 0] = inv_a
+    g1 = orc.rasterize_bwd(H, W, BW, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], color, opac, z3,
+                           T1, f1, ones, za)
+    g2 = orc.rasterize_bwd(H, W, BW, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], dcol, opac, z3,
+                           T2, f2, wd, za)
+    v_op = (g1[3] + g2[3])[:, 0]
+    orc.project_bwd(u["primpos"], u["primscale"], 1.0, u["primqvec"], V, fx, fy, p["cov3d"], p["radii"], p["conics"],
+                    p["compensation"], g1[0] + g2[0], g2[2].sum(1), g1[1] + g2[1], v_op * u["opacity"][:, 0])
+    orc.sg_bwd(nrm[None], u["sigma"][None], li["light_intensity"], li["light_pos"], u["primpos"][None], li["n_lights"],
+               (g1[2] * u["spec_vis"])[None], 0, want_light_grad=False)
+    return b["num_intersects"]
+
+
+def cpu_baseline(args, steps, warmup):
+    import oracle
+    from goliath_b200 import synthetic
+
+    oracle.lib()
+    cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    P = packed_scene(args.gaussians).numpy()
+    li = {k: v.numpy() for k, v in synthetic.lights(args.lights).items()}
+    c = synthetic.ring_camera(0, img_h=H, img_w=W)
+    cam = dict(Rt=c["viewmat"].numpy(), intr=(c["fx"], c["fy"], c["cx"], c["cy"]))
+    for _ in range(warmup):
+        cpu_step(oracle, P, cam, li)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(oracle, P, cam, li)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": H * W / 1e6 / dt, "unit": "MP/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d full step(s) of the same workload (1 view %dx%d, %d Gaussians, L=%d) through the C oracle "
+                      "(oracle/*.c, OpenMP)" % (steps, H, W, args.gaussians, args.lights),
+            "s_per_step": dt}
+
+
+def run_reference(args):
+    """Reference arm: the reference has no CPU rasteriser (gsplat is a CUDA-only third-party dependency, absent), so the
+    CPU implementation of the path is the oracle port, timed with all host threads.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warmup = 1 if args.warmup > 0 else 0
+    cpu = cpu_baseline(args, steps=steps, warmup=warmup)
+    line = {
+        "impl": "reference", "metric": "rendered megapixels/sec (fwd+bwd) RGCA head 300k Gaussians",
+        "value": cpu["value"], "unit": "MP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "rgca_example.yml head: %d Gaussians, 1 view %dx%d, L=%d lights, shade+project+bin/sort+"
+                               "blend(rgb)+blend(depth) fwd+bwd" % (args.gaussians, H, W, args.lights),
+                   "gaussians": args.gaussians, "lights": args.lights, "block_width": BW},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

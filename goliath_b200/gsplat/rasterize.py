@@ -1,0 +1,113 @@
+"""rasterize_gaussians — tile binning + per-tile alpha blending (gsplat 0.1.11 `rasterize.py` API).
+
+Call sites in the reference: ca_code/utils/render_gsplat.py:65-78 (rgb) and :90-104 (depth as colour).
+"""
+from typing import Optional
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from .. import _lib
+from .utils import _tile_bounds, bin_and_sort_gaussians, compute_cumulative_intersects
+
+
+def rasterize_gaussians(
+    xys: Tensor,
+    depths: Tensor,
+    radii: Tensor,
+    conics: Tensor,
+    num_tiles_hit: Tensor,
+    colors: Tensor,
+    opacity: Tensor,
+    img_height: int,
+    img_width: int,
+    block_width: int,
+    background: Optional[Tensor] = None,
+    return_alpha: Optional[bool] = False,
+):
+    assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
+    if colors.dtype == torch.uint8:
+        colors = colors.float() / 255
+    if background is not None:
+        assert background.shape[0] == colors.shape[-1], f"incorrect shape of background color tensor, expected shape {colors.shape[-1]}"
+    else:
+        background = torch.ones(colors.shape[-1], dtype=torch.float32, device=colors.device)
+    if xys.ndimension() != 2 or xys.size(1) != 2:
+        raise ValueError("xys must have dimensions (N, 2)")
+    if colors.ndimension() != 2:
+        raise ValueError("colors must have dimensions (N, D)")
+    if colors.shape[-1] not in (3, 4):
+        raise NotImplementedError("goliath_b200 rasterises 3 (reference) or 4 (fused rgb+depth) channels")
+    return _RasterizeGaussians.apply(
+        xys.contiguous(), depths.contiguous(), radii.contiguous(), conics.contiguous(), num_tiles_hit.contiguous(),
+        colors.contiguous(), opacity.contiguous(), img_height, img_width, block_width, background.contiguous(),
+        return_alpha,
+    )
+
+
+class _RasterizeGaussians(Function):
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width, block_width,
+                background, return_alpha):
+        for t, n in ((xys, "xys"), (depths, "depths"), (conics, "conics"), (colors, "colors"),
+                     (opacity, "opacity"), (background, "background")):
+            _lib.check_input(t, n)
+        _lib.check_input(radii, "radii", torch.int32)
+        _lib.check_input(num_tiles_hit, "num_tiles_hit", torch.int32)
+        num_points = xys.size(0)
+        C = colors.shape[-1]
+        dev = xys.device
+        tile_bounds = _tile_bounds(img_height, img_width, block_width)
+        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+
+        if num_intersects < 1:
+            out_img = torch.ones(img_height, img_width, C, device=dev) * background
+            gaussian_ids_sorted = torch.zeros(0, 1, device=dev)
+            tile_bins = torch.zeros(0, 2, device=dev)
+            final_Ts = torch.zeros(img_height, img_width, device=dev)
+            final_idx = torch.zeros(img_height, img_width, device=dev)
+        else:
+            (_, _, _, gaussian_ids_sorted, tile_bins) = bin_and_sort_gaussians(
+                num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
+            out_img = torch.empty(img_height, img_width, C, device=dev, dtype=torch.float32)
+            final_Ts = torch.empty(img_height, img_width, device=dev, dtype=torch.float32)
+            final_idx = torch.empty(img_height, img_width, device=dev, dtype=torch.int32)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().gb_rasterize_fwd(
+                    img_height, img_width, block_width, C, _lib.ptr(gaussian_ids_sorted), _lib.ptr(tile_bins),
+                    _lib.ptr(xys), _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity), _lib.ptr(background),
+                    _lib.ptr(out_img), _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.stream_ptr(dev)),
+                    "rasterize_forward")
+
+        ctx.img_width, ctx.img_height = img_width, img_height
+        ctx.num_intersects, ctx.block_width = num_intersects, block_width
+        ctx.save_for_backward(gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
+                              final_idx)
+        if return_alpha:
+            out_alpha = 1 - final_Ts
+            return out_img, out_alpha
+        return out_img
+
+    @staticmethod
+    def backward(ctx, v_out_img, v_out_alpha=None):
+        (gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
+         final_idx) = ctx.saved_tensors
+        if v_out_alpha is None:
+            v_out_alpha = torch.zeros_like(v_out_img[..., 0])
+        dev = xys.device
+        C = colors.shape[-1]
+        v_xy = torch.zeros_like(xys)
+        v_conic = torch.zeros_like(conics)
+        v_colors = torch.zeros_like(colors)
+        v_opacity = torch.zeros_like(opacity)
+        if ctx.num_intersects >= 1:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().gb_rasterize_bwd(
+                    ctx.img_height, ctx.img_width, ctx.block_width, C, _lib.ptr(gaussian_ids_sorted),
+                    _lib.ptr(tile_bins), _lib.ptr(xys), _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity),
+                    _lib.ptr(background), _lib.ptr(final_Ts), _lib.ptr(final_idx),
+                    _lib.ptr(v_out_img.contiguous()), _lib.ptr(v_out_alpha.contiguous()), _lib.ptr(v_xy),
+                    _lib.ptr(v_conic), _lib.ptr(v_colors), _lib.ptr(v_opacity), _lib.stream_ptr(dev)),
+                    "rasterize_backward")
+        return (v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None, None, None)

@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference's splat render wrapper ca_code/utils/render_gsplat.py:13-108
+(`render`) and of rgca.AutoEncoder.render's post-processing (ca_code/models/rgca.py:112-151).
+
+`render(...)` keeps the reference signature and call sequence (project, rasterise rgb, rasterise depth as
+colour) so that its results are comparable call-for-call; the kernels underneath are the sm_100a ones.
+"""
+from typing import Optional
+
+import torch as th
+
+from .gsplat import project_gaussians, rasterize_gaussians
+
+
+def render(
+    cam_img_w: int,
+    cam_img_h: int,
+    fx: float,
+    fy: float,
+    cx: float,
+    cy: float,
+    Rt: th.Tensor,
+    primpos: th.Tensor,
+    primqvec: th.Tensor,
+    primscale: th.Tensor,
+    opacity: th.Tensor,
+    colors: th.Tensor,
+    return_depth: bool = True,
+    bg_color: Optional[th.Tensor] = None,
+    block_width: int = 16,
+    global_scale: float = 1.0,
+    z_near: float = 0.1,
+):
+    means3D = primpos.view(-1, 3).contiguous()
+    scales = primscale.view(-1, 3).contiguous()
+    rotations = primqvec.view(-1, 4).contiguous()
+    opacity = opacity.view(-1, 1).contiguous()
+    colors = colors.view(-1, 3).contiguous()
+    if bg_color is None:
+        bg_color = th.zeros(3, device=Rt.device)
+
+    xys, depths, radii, conics, compensation, num_tiles_hit, cov3d = project_gaussians(
+        means3D, scales, global_scale, rotations, Rt, fx, fy, cx, cy, cam_img_h, cam_img_w, block_width, z_near)
+
+    out_img, alpha = rasterize_gaussians(
+        xys, depths, radii, conics, num_tiles_hit, colors, opacity * compensation[:, None], cam_img_h, cam_img_w,
+        block_width, bg_color, return_alpha=True)
+    assert alpha is not None
+    out_color = out_img[..., :3]
+    final_T = 1.0 - alpha
+    out = {"render": out_color.permute(2, 0, 1), "final_T": final_T[None], "alpha": alpha[None], "radii": radii}
+
+    if return_depth:
+        out_depth = rasterize_gaussians(
+            xys, depths, radii, conics, num_tiles_hit, depths[:, None].expand(-1, 3).contiguous(),
+            opacity * compensation[:, None], cam_img_h, cam_img_w, block_width, bg_color, return_alpha=True)[0]
+        out["depth"] = out_depth[..., 0][None]
+    return out
+
+
+def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None):
+    """rgca.AutoEncoder.render (rgca.py:112-151): loop over the batch, stack, alpha from the DETACHED final_T,
+    depth normalised by alpha.clamp(0.05, 1).  `intrinsics_host` (list of (fx,fy,cx,cy)) avoids the reference's
+    four `.item()` device syncs per view when the caller already has them on the host."""
+    B = K.shape[0]
+    rgbs, Ts, depths = [], [], []
+    for b in range(B):
+        if intrinsics_host is not None:
+            fx, fy, cx, cy = intrinsics_host[b]
+        else:
+            fx, fy, cx, cy = K[b, 0, 0].item(), K[b, 1, 1].item(), K[b, 0, 2].item(), K[b, 1, 2].item()
+        o = render(width, height, fx, fy, cx, cy, Rt[b], preds["primpos"][b], preds["primqvec"][b],
+                   preds["primscale"][b], preds["opacity"][b], preds["color"][b], return_depth=True)
+        rgbs.append(o["render"])
+        Ts.append(o["final_T"].detach())
+        depths.append(o["depth"])
+    rgb = th.stack(rgbs)
+    depth = th.stack(depths)
+    alpha = 1.0 - th.stack(Ts)
+    depth = depth / alpha.clamp(0.05, 1.0)
+    return rgb, alpha, depth

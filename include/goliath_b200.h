@@ -1,0 +1,108 @@
+/*
+ * include/goliath_b200.h — C ABI of libgoliath_b200.so (hand-written sm_100a kernels).
+ *
+ * The drop-in boundary of the goliath render hot path.  Every entry point
+ *   - takes raw DEVICE pointers (fp32 / int32 / int64, contiguous, layouts exactly as the reference's
+ *     tensors), plain sizes and a cudaStream_t passed as void*;
+ *   - runs on the CURRENT device of the calling thread and only on the given stream (the reference's
+ *     mvpraymarchlib/utilslib launch on stream 0 with no device guard, mvpraymarch.cpp:122,142,176 —
+ *     this ABI is the superset behaviour needed for one-process-per-GPU operation);
+ *   - never allocates or synchronises: the caller owns outputs, gradients and workspaces;
+ *   - returns 0, or the cudaError_t value of the failing launch / argument check.
+ * Each declaration names the reference binding it replaces.  The Python-side bindings that mirror the
+ * reference's pybind modules live in goliath_b200/{sgutilslib,mvpraymarchlib,utilslib}.py and
+ * goliath_b200/gsplat/; INTEGRATION.md shows the stub a goliath maintainer would add.
+ */
+#ifndef GOLIATH_B200_H_
+#define GOLIATH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* library/ABI version: major*1000 + minor */
+int gb_version(void);
+/* kernels launched by this library since load / last reset (host counter; bench.py gpu_launches) */
+unsigned long long gb_launch_count(void);
+void gb_launch_count_reset(void);
+
+/* ---------------------------------------------------------------- sgutilslib (extensions/sgutils/sg.cu) */
+
+/* replaces sgutilslib.evaluate_gaussian_fwd — sg.cu:177-224 (kernel :27-76).
+ * lobe_dirs [N,D,3] (already normalised by sgutils.py:75), lobe_sigmas [N,D], light_values [N,L,3],
+ * light_pts [N,L,3], prim_pts [N,D,3], n_lights [N] int32, integral [N,D,3] out. w_type in 0..3. */
+int gb_sg_evaluate_fwd(const float* lobe_dirs, const float* lobe_sigmas, const float* light_values,
+                       const float* light_pts, const float* prim_pts, const int32_t* n_lights, float* integral,
+                       int N, int D, int L, int w_type, void* stream);
+
+/* replaces sgutilslib.evaluate_gaussian_bwd — sg.cu:226-277 (kernel :78-175).
+ * grad_dirs [N,D,3], grad_sigmas [N,D] are overwritten; grad_light_values [N,L,3] may be NULL, otherwise it
+ * is accumulated into (the reference zero-fills it in sgutils.py:43-47). */
+int gb_sg_evaluate_bwd(const float* lobe_dirs, const float* lobe_sigmas, const float* light_values,
+                       const float* light_pts, const float* prim_pts, const int32_t* n_lights,
+                       const float* grad_integral, float* grad_dirs, float* grad_sigmas, float* grad_light_values,
+                       int N, int D, int L, int w_type, void* stream);
+
+/* ---------------------------------------------------------------- gsplat 0.1.11 (third-party; call sites
+ * ca_code/utils/render_gsplat.py:49-63, 65-78, 90-104) */
+
+/* replaces gsplat._C.project_gaussians_forward.  means3d [G,3], scales [G,3], quats [G,4] (w,x,y,z),
+ * viewmat: DEVICE pointer to >= 12 floats, row-major [R|t].  Outputs (all written for every Gaussian;
+ * culled ones get zeros): cov3d [G,6], xys [G,2], depths [G], radii [G] i32, conics [G,3],
+ * compensation [G], num_tiles_hit [G] i32. */
+int gb_project_gaussians_fwd(int G, const float* means3d, const float* scales, float glob_scale,
+                             const float* quats, const float* viewmat, float fx, float fy, float cx, float cy,
+                             int img_h, int img_w, int block_width, float clip_thresh, float* cov3d, float* xys,
+                             float* depths, int32_t* radii, float* conics, float* compensation,
+                             int32_t* num_tiles_hit, void* stream);
+
+/* replaces gsplat._C.project_gaussians_backward.  All five gradient outputs are overwritten. */
+int gb_project_gaussians_bwd(int G, const float* means3d, const float* scales, float glob_scale,
+                             const float* quats, const float* viewmat, float fx, float fy, const float* cov3d,
+                             const int32_t* radii, const float* conics, const float* compensation,
+                             const float* v_xy, const float* v_depth, const float* v_conic,
+                             const float* v_compensation, float* v_cov2d, float* v_cov3d, float* v_mean3d,
+                             float* v_scale, float* v_quat, void* stream);
+
+/* replaces gsplat.utils.compute_cumulative_intersects (torch.cumsum int32): inclusive scan. */
+size_t gb_cumsum_workspace_bytes(int n);
+int gb_cumsum_i32(int n, const int32_t* in, int32_t* out, void* workspace, void* stream);
+
+/* replaces gsplat._C.map_gaussian_to_intersects: isect_ids [I] int64 = (tile_id << 32) | bits(depth),
+ * gaussian_ids [I] int32, emitted per Gaussian in row-major tile order. */
+int gb_map_gaussian_to_intersects(int G, const float* xys, const float* depths, const int32_t* radii,
+                                  const int32_t* cum_tiles_hit, int img_h, int img_w, int block_width,
+                                  int64_t* isect_ids, int32_t* gaussian_ids, void* stream);
+
+/* replaces torch.sort(isect_ids) + gather in gsplat.utils.bin_and_sort_gaussians: stable ascending radix
+ * sort on the low key_bits bits (32 + ceil(log2(#tiles))). */
+size_t gb_sort_workspace_bytes(int64_t n);
+int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t* gaussian_ids, int64_t* isect_sorted,
+                       int32_t* gids_sorted, int key_bits, void* workspace, void* stream);
+
+/* replaces gsplat._C.get_tile_bin_edges: tile_bins [T,2] int32, zeroed by the caller. */
+int gb_get_tile_bin_edges(int64_t n, const int64_t* isect_sorted, int32_t* tile_bins, void* stream);
+
+/* replaces gsplat._C.rasterize_forward (channels == 3); channels == 4 is the fused rgb+depth pass.
+ * colors [G,C], opacities [G], background [C] (device).  out_img [H,W,C], final_Ts [H,W],
+ * final_idx [H,W] i32 are fully overwritten. */
+int gb_rasterize_fwd(int img_h, int img_w, int block_width, int channels, const int32_t* gids_sorted,
+                     const int32_t* tile_bins, const float* xys, const float* conics, const float* colors,
+                     const float* opacities, const float* background, float* out_img, float* final_Ts,
+                     int32_t* final_idx, void* stream);
+
+/* replaces gsplat._C.rasterize_backward.  v_xy [G,2], v_conic [G,3], v_colors [G,C], v_opacity [G] are
+ * accumulated into (caller zeroes them). */
+int gb_rasterize_bwd(int img_h, int img_w, int block_width, int channels, const int32_t* gids_sorted,
+                     const int32_t* tile_bins, const float* xys, const float* conics, const float* colors,
+                     const float* opacities, const float* background, const float* final_Ts,
+                     const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
+                     float* v_conic, float* v_colors, float* v_opacity, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLIATH_B200_H_ */

@@ -1,0 +1,273 @@
+"""GPU parity of the splat path (project -> bin/sort -> blend, fwd + bwd) against the CPU oracle, through the
+C ABI (ctypes) and through the gsplat-compatible Python surface.
+
+Bars: bit-exact for projection outputs that feed binning, for intersection keys, sorted ids and tile bins;
+1e-4 relative for pixels and gradients (the blend uses the hardware ex2 like the reference's __expf)."""
+import numpy as np
+import pytest
+import torch
+
+from util import assert_close, small_scene, t2n
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: (kwargs of small_scene, block_width, scale multiplier)
+    "dense96": (dict(G=3000, img_h=96, img_w=80), 16, 12.0),
+    "ragged": (dict(G=2500, img_h=70, img_w=93, seed=11, cam=3), 16, 15.0),
+    "bw8": (dict(G=1500, img_h=64, img_w=48, seed=5), 8, 10.0),
+    "ties": (dict(G=4000, img_h=96, img_w=80, depth_quant=True), 16, 8.0),
+    "tiny_prims": (dict(G=5000, img_h=128, img_w=96, seed=9), 16, 1.0),
+}
+
+
+def _dev(d, dev):
+    return {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+
+
+def _project_gpu(s, dev, bw, mult):
+    from goliath_b200.gsplat import project_gaussians
+
+    t = _dev(s, dev)
+    return project_gaussians(t["means3d"], t["scales"] * mult, 1.0, t["quats"], t["viewmat"], s["fx"], s["fy"],
+                             s["cx"], s["cy"], s["img_h"], s["img_w"], bw, 0.1)
+
+
+def _project_cpu(orc, s, bw, mult):
+    return orc.project_fwd(s["means3d"], s["scales"] * np.float32(mult), 1.0, s["quats"], s["viewmat"], s["fx"],
+                           s["fy"], s["cx"], s["cy"], s["img_h"], s["img_w"], bw, 0.1)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_project_forward_bit_exact(orc, cuda, case):
+    kw, bw, mult = CASES[case]
+    s = small_scene(**kw)
+    xys, depths, radii, conics, comp, nth, cov3d = _project_gpu(s, cuda, bw, mult)
+    ref = _project_cpu(orc, s, bw, mult)
+    assert (ref["radii"] > 0).sum() > 100
+    for name, got in (("xys", xys), ("depths", depths), ("radii", radii), ("conics", conics),
+                      ("compensation", comp), ("num_tiles_hit", nth), ("cov3d", cov3d)):
+        g = t2n(got)
+        r = ref[name]
+        assert g.dtype == r.dtype and g.shape == r.shape, name
+        assert np.array_equal(g.view(np.uint32) if g.dtype == np.float32 else g,
+                              r.view(np.uint32) if r.dtype == np.float32 else r), "%s not bit-exact" % name
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_binning_bit_exact(orc, cuda, case):
+    from goliath_b200.gsplat import utils as gu
+
+    kw, bw, mult = CASES[case]
+    s = small_scene(**kw)
+    ref_p = _project_cpu(orc, s, bw, mult)
+    ref = orc.bin_and_sort(ref_p["xys"], ref_p["depths"], ref_p["radii"], ref_p["num_tiles_hit"], s["img_h"],
+                           s["img_w"], bw)
+    d = lambda a: torch.from_numpy(a).to(cuda)
+    n, cum = gu.compute_cumulative_intersects(d(ref_p["num_tiles_hit"]))
+    assert n == ref["num_intersects"]
+    assert np.array_equal(t2n(cum), ref["cum_tiles_hit"])
+    tb = gu._tile_bounds(s["img_h"], s["img_w"], bw)
+    isect, gids, isect_s, gids_s, bins = gu.bin_and_sort_gaussians(
+        len(ref_p["radii"]), n, d(ref_p["xys"]), d(ref_p["depths"]), d(ref_p["radii"]), cum, tb, bw)
+    assert np.array_equal(t2n(isect), ref["isect_ids"])
+    assert np.array_equal(t2n(gids), ref["gaussian_ids"])
+    assert np.array_equal(t2n(isect_s), ref["isect_ids_sorted"])
+    assert np.array_equal(t2n(gids_s), ref["gaussian_ids_sorted"])
+    assert np.array_equal(t2n(bins), ref["tile_bins"])
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 4095, 4096, 4097, 100_003, 1_500_000])
+def test_radix_sort_sizes(cuda, n):
+    """Stable sort contract at block-boundary sizes, full 64-bit-wide tile ids, and uniform digits."""
+    from goliath_b200.gsplat import utils as gu
+
+    g = torch.Generator().manual_seed(n)
+    tiles = torch.randint(0, 2688, (n,), generator=g, dtype=torch.int64)
+    depth = (900.0 + 200.0 * torch.rand(n, generator=g)).to(torch.float32)
+    depth[::7] = 1000.0  # many exact ties
+    keys = (tiles << 32) | depth.view(torch.int32).to(torch.int64)
+    vals = torch.arange(n, dtype=torch.int32)
+    ks, vs = gu.sort_intersects(keys.to(cuda), vals.to(cuda), 2688)
+    order = np.argsort(keys.numpy(), kind="stable")
+    assert np.array_equal(t2n(ks), keys.numpy()[order])
+    assert np.array_equal(t2n(vs), vals.numpy()[order])
+
+
+@pytest.mark.parametrize("n", [1, 5, 2047, 2048, 2049, 300_000, 1_048_576])
+def test_cumsum(cuda, n):
+    from goliath_b200.gsplat import utils as gu
+
+    x = torch.randint(0, 9, (n,), generator=torch.Generator().manual_seed(n), dtype=torch.int32)
+    tot, cum = gu.compute_cumulative_intersects(x.to(cuda))
+    ref = np.cumsum(x.numpy(), dtype=np.int64)
+    assert tot == ref[-1] and np.array_equal(t2n(cum), ref.astype(np.int32))
+
+
+def _blend_inputs(orc, s, bw, mult, C, rng):
+    p = _project_cpu(orc, s, bw, mult)
+    b = orc.bin_and_sort(p["xys"], p["depths"], p["radii"], p["num_tiles_hit"], s["img_h"], s["img_w"], bw)
+    G = len(p["radii"])
+    colors = rng.random((G, C)).astype(np.float32)
+    if C == 4:
+        colors[:, 3] = p["depths"]
+    bg = rng.random(C).astype(np.float32)
+    opac = (s["opacity"][:, 0] * p["compensation"]).astype(np.float32)
+    return p, b, colors, bg, opac
+
+
+@pytest.mark.parametrize("C", [3, 4])
+@pytest.mark.parametrize("case", list(CASES))
+def test_blend_forward_backward(orc, cuda, case, C):
+    from goliath_b200 import _lib
+
+    kw, bw, mult = CASES[case]
+    s = small_scene(**kw)
+    H, W = s["img_h"], s["img_w"]
+    rng = np.random.default_rng(42)
+    p, b, colors, bg, opac = _blend_inputs(orc, s, bw, mult, C, rng)
+    out_r, Ts_r, fi_r = orc.rasterize_fwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"],
+                                          colors, opac, bg)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    gids, bins, xys, conics, col, op, bgd = (d(b["gaussian_ids_sorted"]), d(b["tile_bins"]), d(p["xys"]),
+                                             d(p["conics"]), d(colors), d(opac), d(bg))
+    out = torch.empty(H, W, C, device=cuda)
+    Ts = torch.empty(H, W, device=cuda)
+    fi = torch.empty(H, W, device=cuda, dtype=torch.int32)
+    L = _lib.lib()
+    st = _lib.stream_ptr(cuda)
+    _lib.check(L.gb_rasterize_fwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
+                                  col.data_ptr(), op.data_ptr(), bgd.data_ptr(), out.data_ptr(), Ts.data_ptr(),
+                                  fi.data_ptr(), st), "fwd")
+    torch.cuda.synchronize()
+    assert (Ts_r < 0.9).mean() > 0.02, "scene must cover pixels"
+    # a borderline alpha<1/255 or T<=1e-4 decision can flip on a handful of pixels (ex2 vs libm expf)
+    assert_close(t2n(out), out_r, rtol=1e-4, atol=2e-5, frac=0.9995, what="out_img")
+    assert_close(t2n(Ts), Ts_r, rtol=1e-4, atol=2e-6, frac=0.9995, what="final_Ts")
+    assert (t2n(fi) == fi_r).mean() >= 0.999
+
+    # backward on the ORACLE's forward state so both sides differentiate the same blend
+    v_out = rng.standard_normal((H, W, C)).astype(np.float32)
+    v_alpha = rng.standard_normal((H, W)).astype(np.float32)
+    ref = orc.rasterize_bwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], colors, opac,
+                            bg, Ts_r, fi_r, v_out, v_alpha)
+    G = len(opac)
+    v_xy, v_conic = torch.zeros(G, 2, device=cuda), torch.zeros(G, 3, device=cuda)
+    v_col, v_op = torch.zeros(G, C, device=cuda), torch.zeros(G, 1, device=cuda)
+    _lib.check(L.gb_rasterize_bwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
+                                  col.data_ptr(), op.data_ptr(), bgd.data_ptr(), d(Ts_r).data_ptr(),
+                                  d(fi_r).data_ptr(), d(v_out).data_ptr(), d(v_alpha).data_ptr(), v_xy.data_ptr(),
+                                  v_conic.data_ptr(), v_col.data_ptr(), v_op.data_ptr(), st), "bwd")
+    torch.cuda.synchronize()
+    for name, got, want in (("v_xy", v_xy, ref[0]), ("v_conic", v_conic, ref[1]), ("v_colors", v_col, ref[2]),
+                            ("v_opacity", v_op, ref[3])):
+        assert_close(t2n(got), want, rtol=1e-4, atol=1e-4 * np.abs(want).max() * 0.1, frac=0.999, what=name)
+
+
+@pytest.mark.parametrize("case", ["dense96", "ragged"])
+def test_project_backward(orc, cuda, case):
+    kw, bw, mult = CASES[case]
+    s = small_scene(**kw)
+    t = _dev(s, cuda)
+    from goliath_b200.gsplat import project_gaussians
+
+    means, scales, quats = (t["means3d"].requires_grad_(), (t["scales"] * mult).requires_grad_(),
+                            t["quats"].requires_grad_())
+    xys, depths, radii, conics, comp, nth, cov3d = project_gaussians(
+        means, scales, 1.0, quats, t["viewmat"], s["fx"], s["fy"], s["cx"], s["cy"], s["img_h"], s["img_w"], bw, 0.1)
+    G = means.shape[0]
+    rng = np.random.default_rng(3)
+    v = [rng.standard_normal(sh).astype(np.float32) for sh in ((G, 2), (G,), (G, 3), (G,))]
+    d = lambda a: torch.from_numpy(a).to(cuda)
+    torch.autograd.backward([xys, depths, conics, comp], [d(v[0]), d(v[1]), d(v[2]), d(v[3])])
+    p = _project_cpu(orc, s, bw, mult)
+    ref = orc.project_bwd(s["means3d"], s["scales"] * np.float32(mult), 1.0, s["quats"], s["viewmat"], s["fx"],
+                          s["fy"], p["cov3d"], p["radii"], p["conics"], p["compensation"], *v)
+    assert_close(t2n(means.grad), ref["v_mean3d"], rtol=1e-5, what="v_mean3d")
+    assert_close(t2n(scales.grad), ref["v_scale"], rtol=1e-5, what="v_scale")
+    assert_close(t2n(quats.grad), ref["v_quat"], rtol=1e-5, what="v_quat")
+
+
+def test_render_like_reference_wrapper(orc, cuda):
+    """The exact call sequence of ca_code/utils/render_gsplat.py:41-106 (project, rasterise rgb, rasterise depth),
+    forward + backward through autograd, against the oracle chain."""
+    from goliath_b200.gsplat import project_gaussians, rasterize_gaussians
+
+    kw, bw, mult = CASES["dense96"]
+    s = small_scene(**kw)
+    H, W = s["img_h"], s["img_w"]
+    t = _dev(s, cuda)
+    means, scales, quats = t["means3d"].requires_grad_(), (t["scales"] * mult).requires_grad_(), t["quats"].requires_grad_()
+    opacity, colors = t["opacity"].requires_grad_(), t["colors"].requires_grad_()
+    bg = torch.zeros(3, device=cuda)
+    xys, depths, radii, conics, comp, nth, cov3d = project_gaussians(
+        means, scales, 1.0, quats, t["viewmat"], s["fx"], s["fy"], s["cx"], s["cy"], H, W, bw, 0.1)
+    out_img, alpha = rasterize_gaussians(xys, depths, radii, conics, nth, colors, opacity * comp[:, None], H, W, bw, bg,
+                                         return_alpha=True)
+    out_depth = rasterize_gaussians(xys, depths, radii, conics, nth, depths[:, None].expand(-1, 3).contiguous(),
+                                    opacity * comp[:, None], H, W, bw, bg, return_alpha=True)[0]
+    rng = np.random.default_rng(5)
+    w_img = torch.from_numpy(rng.standard_normal((H, W, 3)).astype(np.float32)).to(cuda)
+    w_dep = torch.from_numpy((1e-3 * rng.standard_normal((H, W))).astype(np.float32)).to(cuda)
+    ((out_img * w_img).sum() + (out_depth[..., 0] * w_dep).sum()).backward()
+
+    # oracle chain
+    p = _project_cpu(orc, s, bw, mult)
+    b = orc.bin_and_sort(p["xys"], p["depths"], p["radii"], p["num_tiles_hit"], H, W, bw)
+    opac = (s["opacity"][:, 0] * p["compensation"]).astype(np.float32)
+    z3 = np.zeros(3, np.float32)
+    o1, T1, f1 = orc.rasterize_fwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"],
+                                   s["colors"], opac, z3)
+    dcol = np.repeat(p["depths"][:, None], 3, 1)
+    o2, T2, f2 = orc.rasterize_fwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], dcol,
+                                   opac, z3)
+    assert_close(t2n(out_img), o1, rtol=1e-4, atol=2e-5, frac=0.9995, what="rgb")
+    assert_close(t2n(alpha), 1 - T1, rtol=1e-4, atol=2e-5, frac=0.9995, what="alpha")
+    assert_close(t2n(out_depth), o2, rtol=1e-4, atol=2e-2, frac=0.9995, what="depth")
+    za = np.zeros((H, W), np.float32)
+    wd3 = np.zeros((H, W, 3), np.float32)
+    wd3[..., 0] = t2n(w_dep)
+    g1 = orc.rasterize_bwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], s["colors"],
+                           opac, z3, T1, f1, t2n(w_img), za)
+    g2 = orc.rasterize_bwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], dcol, opac, z3,
+                           T2, f2, wd3, za)
+    v_xy, v_conic = g1[0] + g2[0], g1[1] + g2[1]
+    v_opac_eff = (g1[3] + g2[3])[:, 0]
+    v_depth = g2[2].sum(1)
+    v_comp = v_opac_eff * s["opacity"][:, 0]
+    ref = orc.project_bwd(s["means3d"], s["scales"] * np.float32(mult), 1.0, s["quats"], s["viewmat"], s["fx"],
+                          s["fy"], p["cov3d"], p["radii"], p["conics"], p["compensation"], v_xy, v_depth, v_conic,
+                          v_comp)
+    tol = dict(rtol=2e-4, frac=0.999)
+    assert_close(t2n(colors.grad), g1[2], what="d colors", **tol)
+    assert_close(t2n(opacity.grad)[:, 0], v_opac_eff * p["compensation"], what="d opacity", **tol)
+    assert_close(t2n(means.grad), ref["v_mean3d"], what="d means", **tol)
+    assert_close(t2n(scales.grad), ref["v_scale"], what="d scales", **tol)
+    assert_close(t2n(quats.grad), ref["v_quat"], what="d quats", **tol)
+
+
+def test_empty_and_culled(cuda):
+    from goliath_b200.gsplat import project_gaussians, rasterize_gaussians
+
+    H, W = 48, 40
+    V = torch.eye(4, device=cuda)[:3].contiguous()
+    means = torch.tensor([[0.0, 0.0, -5.0], [0.0, 0.0, 0.01]], device=cuda)  # behind / inside near plane
+    scales = torch.full((2, 3), 0.1, device=cuda)
+    quats = torch.tensor([[1.0, 0, 0, 0]] * 2, device=cuda)
+    xys, depths, radii, conics, comp, nth, cov3d = project_gaussians(means, scales, 1.0, quats, V, 50.0, 50.0, 20.0,
+                                                                     24.0, H, W, 16, 0.1)
+    assert int(nth.sum()) == 0 and int(radii.sum()) == 0
+    bg = torch.tensor([0.25, 0.5, 0.75], device=cuda)
+    img, alpha = rasterize_gaussians(xys, depths, radii, conics, nth, torch.rand(2, 3, device=cuda),
+                                     torch.rand(2, 1, device=cuda), H, W, 16, bg, return_alpha=True)
+    assert torch.allclose(img, bg.expand(H, W, 3))
+    # reference quirk kept: with zero intersections final_Ts is zeros, so alpha == 1 (gsplat 0.1.11 rasterize.py)
+    assert torch.all(alpha == 1)
+
+
+def test_product_refuses_cpu_tensors(cuda):
+    from goliath_b200.gsplat import project_gaussians
+
+    with pytest.raises(RuntimeError):
+        project_gaussians(torch.zeros(4, 3), torch.ones(4, 3), 1.0, torch.tensor([[1.0, 0, 0, 0]] * 4),
+                          torch.eye(4)[:3].contiguous(), 10.0, 10.0, 8.0, 8.0, 16, 16, 16)
