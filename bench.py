@@ -132,30 +132,40 @@ def kernel_roofline(dev, packed, cam, flush):
     n, cum = gu.compute_cumulative_intersects(nth)
     tb = gu._tile_bounds(H, W, BW)
     _, _, _, gids, bins = gu.bin_and_sort_gaussians(xys.shape[0], n, xys, depths, radii, cum, tb, BW)
-    colors = u["diff_color"].contiguous()
+    C = 4  # the product path blends rgb + depth in one 4-channel pass (goliath_b200.render.render, fused=True)
+    colors = torch.cat([u["diff_color"], depths[:, None]], 1).contiguous()
     opac = (u["opacity"] * comp[:, None]).contiguous()
-    bg = torch.zeros(3, device=dev)
-    out = torch.empty(H, W, 3, device=dev)
+    bg = torch.zeros(C, device=dev)
+    out = torch.empty(H, W, C, device=dev)
     Ts = torch.empty(H, W, device=dev)
     fi = torch.empty(H, W, device=dev, dtype=torch.int32)
     G = xys.shape[0]
-    v_out = torch.ones(H, W, 3, device=dev)
+    v_out = torch.ones(H, W, C, device=dev)
     v_a = torch.zeros(H, W, device=dev)
-    gx, gc, gcol, go = (torch.zeros(G, 2, device=dev), torch.zeros(G, 3, device=dev), torch.zeros(G, 3, device=dev),
+    gx, gc, gcol, go = (torch.zeros(G, 2, device=dev), torch.zeros(G, 3, device=dev), torch.zeros(G, C, device=dev),
                         torch.zeros(G, 1, device=dev))
     L = _lib.lib()
     st = _lib.stream_ptr(dev)
+    T_ = tb[0] * tb[1]
+    rec = torch.empty(n, 12, device=dev)
+    order = torch.empty(T_, dtype=torch.int32, device=dev)
+    _lib.check(L.gb_tile_order(T_, bins.data_ptr(), order.data_ptr(), st), "order")
+
+    def pack():
+        _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), colors.data_ptr(),
+                                     opac.data_ptr(), rec.data_ptr(), st), "pack")
 
     def fwd():
-        _lib.check(L.gb_rasterize_fwd(H, W, BW, 3, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
-                                      colors.data_ptr(), opac.data_ptr(), bg.data_ptr(), out.data_ptr(), Ts.data_ptr(),
-                                      fi.data_ptr(), st), "fwd")
+        _lib.check(L.gb_rasterize_packed_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(),
+                                             out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "fwd")
 
     def bwd():
-        _lib.check(L.gb_rasterize_bwd(H, W, BW, 3, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
-                                      colors.data_ptr(), opac.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
-                                      v_out.data_ptr(), v_a.data_ptr(), gx.data_ptr(), gc.data_ptr(), gcol.data_ptr(),
-                                      go.data_ptr(), st), "bwd")
+        _lib.check(L.gb_rasterize_packed_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(),
+                                             rec.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+                                             v_out.data_ptr(), v_a.data_ptr(), gx.data_ptr(), gc.data_ptr(),
+                                             gcol.data_ptr(), go.data_ptr(), st), "bwd")
+
+    pack()
 
     def timeit(fn, reps=20):
         ts = []
@@ -171,10 +181,12 @@ def kernel_roofline(dev, packed, cam, flush):
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
 
-    t_f, t_b = timeit(fwd), timeit(bwd)
+    t_p, t_f, t_b = timeit(pack), timeit(fwd), timeit(bwd)
     P, T, I = H * W, tb[0] * tb[1], n
-    bytes_f = I * (4 + 36) + P * (12 + 4 + 4) + T * 8
-    bytes_b = I * (4 + 36) + I * 36 + P * (8 + 12 + 4)
+    # SURVEY.md §8d per-unit figures, with C = 4 colour channels (rgb + depth in one pass)
+    bytes_f = I * (4 + 24 + 4 * C) + P * (4 * C + 4 + 4) + T * 8
+    bytes_b = I * (4 + 24 + 4 * C) + I * (4 * (C + 6)) + P * (8 + 4 * C + 4)
+    bytes_p = I * (4 + 24 + 4 * C) + I * 48
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -183,8 +195,9 @@ def kernel_roofline(dev, packed, cam, flush):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured" if "hbm_gbs" in peaks else "fallback"
     ks = {
-        "rasterize_fwd_kernel<3>": {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
-        "rasterize_bwd_kernel<3>": {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
+        "blend_fwd_packed_kernel<4>": {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
+        "blend_bwd_packed_kernel<4>": {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
+        "pack_records_kernel<4>": {"ms": t_p, "alg_bytes": bytes_p, "gbs": bytes_p / t_p / 1e6},
     }
     dom = max(ks, key=lambda k: ks[k]["ms"])
     roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["gbs"], "peak": peak, "unit": "GB/s",

@@ -31,6 +31,10 @@ SIGNATURES = {
     "gb_get_tile_bin_edges": (_i, [_i64, _vp, _vp, _vp]),
     "gb_rasterize_fwd": (_i, [_i, _i, _i, _i] + [_vp] * 10 + [_vp]),
     "gb_rasterize_bwd": (_i, [_i, _i, _i, _i] + [_vp] * 15 + [_vp]),
+    "gb_pack_records": (_i, [_i64, _i] + [_vp] * 6 + [_vp]),
+    "gb_tile_order": (_i, [_i, _vp, _vp, _vp]),
+    "gb_rasterize_packed_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
+    "gb_rasterize_packed_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
 }
 
 

@@ -10,8 +10,11 @@
 // 12 B out per Gaussian).  grad_light_values (optional) is reduced warp -> CTA (shared) -> one RED per
 // (CTA, light, channel) instead of the reference's 3 global atomics per (Gaussian, light).
 //
-// Numerics follow the reference formulation (clamped cosine -> acosf -> __expf) so that results agree
-// with the reference kernels to fp32 round-off; the -20 clamp-edge derivative (sg.cu:129,139) is kept.
+// Numerics: this translation unit is compiled with -use_fast_math exactly like the reference's extension
+// (extensions/sgutils/setup.py:31) and evaluates each (Gaussian, light) pair with the reference's formula in
+// the reference's operation order (clamped cosine -> acosf -> __expf, divisions where sg.cu divides), and
+// accumulates over lights sequentially per thread, so forward values and grad_dirs / grad_sigmas agree with
+// the reference kernels to the last bits; the -20 clamp-edge derivative (sg.cu:129,139) is kept.
 #include "common.cuh"
 
 namespace {
@@ -46,12 +49,6 @@ __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict_
     pp = make_float3(prim_pts[3 * o], prim_pts[3 * o + 1], prim_pts[3 * o + 2]);
     sigma = lobe_sigmas[o];
   }
-  // per-Gaussian constants hoisted out of the light loop
-  const float inv_sigma = 1.f / sigma;
-  float norm = 1.f;
-  if (WT == 0) norm = 1.f / (sigma * SQRT2PI23);
-  if (WT == 2) norm = 1.f / (sigma * TWOPI);
-
   const int nL = min(n_lights[n], L);
   float3 sum = make_float3(0.f, 0.f, 0.f);
   for (int l0 = 0; l0 < nL; l0 += kLightChunk) {
@@ -65,15 +62,20 @@ __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict_
 #pragma unroll 4
     for (int l = 0; l < cnt; ++l) {
       float lx = s_lp[3 * l] - pp.x, ly = s_lp[3 * l + 1] - pp.y, lz = s_lp[3 * l + 2] - pp.z;
-      const float rl = rsqrtf(lx * lx + ly * ly + lz * lz);
-      lx *= rl; ly *= rl; lz *= rl;
+      const float len = sqrtf(lx * lx + ly * ly + lz * lz);
+      lx /= len; ly /= len; lz /= len;
       const float cos_dot = fminf(fmaxf(lx * dir.x + ly * dir.y + lz * dir.z, -1.f), 1.f);
       float w;
-      if (WT == 0 || WT == 1) {
+      if (WT == 0) {
         const float angle = acosf(cos_dot);
-        w = __expf(-0.5f * sq(angle * inv_sigma)) * norm;
+        w = __expf(-0.5f * sq(angle / sigma)) / (sigma * SQRT2PI23);
+      } else if (WT == 1) {
+        const float angle = acosf(cos_dot);
+        w = __expf(-0.5f * sq(angle / sigma));
+      } else if (WT == 2) {
+        w = __expf((cos_dot - 1.f) / sigma) / (sigma * TWOPI);
       } else {
-        w = __expf((cos_dot - 1.f) * inv_sigma) * norm;
+        w = __expf((cos_dot - 1.f) / sigma);
       }
       sum.x += s_lv[3 * l] * w; sum.y += s_lv[3 * l + 1] * w; sum.z += s_lv[3 * l + 2] * w;
     }
@@ -109,8 +111,6 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
     gi = make_float3(grad_integral[3 * o], grad_integral[3 * o + 1], grad_integral[3 * o + 2]);
     sigma = lobe_sigmas[o];
   }
-  const float inv_sigma = 1.f / sigma;
-  const float s2 = sigma * sigma;
   const int nL = min(n_lights[n], L);
   float3 gdir = make_float3(0.f, 0.f, 0.f);
   float gsig = 0.f;
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
 #pragma unroll 2
     for (int l = 0; l < cnt; ++l) {
       float lx = s_lp[3 * l] - pp.x, ly = s_lp[3 * l + 1] - pp.y, lz = s_lp[3 * l + 2] - pp.z;
-      const float rl = rsqrtf(lx * lx + ly * ly + lz * lz);
-      lx *= rl; ly *= rl; lz *= rl;
+      const float len = sqrtf(lx * lx + ly * ly + lz * lz);
+      lx /= len; ly /= len; lz /= len;
       const float e0 = s_lv[3 * l], e1 = s_lv[3 * l + 1], e2 = s_lv[3 * l + 2];
       const float cos_dot = lx * dir.x + ly * dir.y + lz * dir.z;
       const float cc = fminf(fmaxf(cos_dot, -1.f), 1.f);
@@ -135,28 +135,28 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
       float weight, dL_cos;
       if (WT == 0) {
         const float angle = acosf(cc);
-        const float ev = __expf(-0.5f * sq(angle * inv_sigma));
+        const float ev = __expf(-0.5f * sq(angle / sigma));
         weight = ev / (sigma * SQRT2PI23);
-        gsig += dLw * ((ev * INVSQRT2PI23 * (sq(angle) - s2)) / (s2 * s2));
-        const float dL_angle = dLw * -((INVSQRT2PI23 * angle * ev) / (s2 * sigma));
-        dL_cos = dL_angle * ((cos_dot > -1.f && cos_dot < 1.f) ? (-rsqrtf(1.f - sq(cos_dot))) : -20.f);
+        gsig += dLw * ((ev * INVSQRT2PI23 * (sq(angle) - sq(sigma))) / (sq(sigma) * sq(sigma)));
+        const float dL_angle = dLw * -((INVSQRT2PI23 * angle * ev) / (sq(sigma) * sigma));
+        dL_cos = dL_angle * ((cos_dot > -1.f && cos_dot < 1.f) ? (-1.f / sqrtf(1.f - sq(cos_dot))) : -20.f);
       } else if (WT == 1) {
         const float angle = acosf(cc);
-        const float ev = __expf(-0.5f * sq(angle * inv_sigma));
+        const float ev = __expf(-0.5f * sq(angle / sigma));
         weight = ev;
-        gsig += dLw * ((ev * sq(angle)) / (sigma * s2));
-        const float dL_angle = dLw * -((angle * ev) / s2);
-        dL_cos = dL_angle * ((cos_dot > -1.f && cos_dot < 1.f) ? (-rsqrtf(1.f - sq(cos_dot))) : -20.f);
+        gsig += dLw * ((ev * sq(angle)) / (sigma * sq(sigma)));
+        const float dL_angle = dLw * -((angle * ev) / sq(sigma));
+        dL_cos = dL_angle * ((cos_dot > -1.f && cos_dot < 1.f) ? (-1.f / sqrtf(1.f - sq(cos_dot))) : -20.f);
       } else if (WT == 2) {
-        const float ev = __expf((cc - 1.f) * inv_sigma);
+        const float ev = __expf((cc - 1.f) / sigma);
         weight = ev / (sigma * TWOPI);
-        gsig += dLw * ((ev * INV2PI * ((1.f - cc) - sigma)) / (sigma * s2));
-        dL_cos = dLw * INV2PI * ev / s2;
+        gsig += dLw * ((ev * INV2PI * ((1.f - cc) - sigma)) / (sigma * sq(sigma)));
+        dL_cos = dLw * INV2PI * ev / sq(sigma);
       } else {
-        const float ev = __expf((cc - 1.f) * inv_sigma);
+        const float ev = __expf((cc - 1.f) / sigma);
         weight = ev;
-        gsig += dLw * ((ev * (1.f - cc) / s2));
-        dL_cos = dLw * ev * inv_sigma;
+        gsig += dLw * ((ev * (1.f - cc) / sq(sigma)));
+        dL_cos = dLw * ev / sigma;
       }
       gdir.x += dL_cos * lx; gdir.y += dL_cos * ly; gdir.z += dL_cos * lz;
       if (LIGHT_GRAD) {

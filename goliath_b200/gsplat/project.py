@@ -67,6 +67,7 @@ class _ProjectGaussians(Function):
         ctx.glob_scale, ctx.fx, ctx.fy, ctx.cx, ctx.cy = glob_scale, fx, fy, cx, cy
         ctx.save_for_backward(means3d, scales, quats, viewmat, cov3d, radii, conics, compensation)
         ctx.mark_non_differentiable(radii, num_tiles_hit)
+        ctx.set_materialize_grads(False)
         return xys, depths, radii, conics, compensation, num_tiles_hit, cov3d
 
     @staticmethod
@@ -93,9 +94,7 @@ class _ProjectGaussians(Function):
                 _lib.ptr(compensation), _lib.ptr(v_xys), _lib.ptr(v_depths), _lib.ptr(v_conics),
                 _lib.ptr(v_compensation), _lib.ptr(g_cov2d), _lib.ptr(g_cov3d), _lib.ptr(g_mean3d),
                 _lib.ptr(g_scale), _lib.ptr(g_quat), _lib.stream_ptr(dev)), "project_gaussians_backward")
-        if v_cov3d is not None:
-            # cov3d is also an output; its direct gradient joins the chain (never used by the reference)
-            raise NotImplementedError("gradient through the returned cov3d is not supported (as in gsplat 0.1.11)")
+        # v_cov3d (gradient of the returned cov3d) is ignored, as in gsplat 0.1.11
         v_viewmat = None
         if ctx.needs_input_grad[4]:
             # gsplat 0.1.11 camera-pose approximation: d f/d t = sum_g v_mean_cam, d f/d R_ij ~= v_mean_cam_i * mean_j

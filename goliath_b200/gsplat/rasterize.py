@@ -1,6 +1,13 @@
 """rasterize_gaussians — tile binning + per-tile alpha blending (gsplat 0.1.11 `rasterize.py` API).
 
 Call sites in the reference: ca_code/utils/render_gsplat.py:65-78 (rgb) and :90-104 (depth as colour).
+
+Two things differ from a literal re-implementation, neither visible in the results:
+  * the reference calls this function twice per view with the SAME (xys, depths, radii, num_tiles_hit) and
+    re-bins / re-sorts each time; here the binning of the last call is kept per device and reused when the very
+    same tensors (same storage, same version counter) come back;
+  * with block_width == 16 the blend runs on packed per-intersection records streamed by bulk async copies
+    (csrc/splat_blend_packed.cu); other block widths use the generic kernel (csrc/splat_blend.cu).
 """
 from typing import Optional
 
@@ -10,6 +17,41 @@ from torch.autograd import Function
 
 from .. import _lib
 from .utils import _tile_bounds, bin_and_sort_gaussians, compute_cumulative_intersects
+
+_BIN_CACHE = {}
+
+
+def _bin_cached(xys, depths, radii, num_tiles_hit, img_height, img_width, block_width):
+    """(num_intersects, gaussian_ids_sorted, tile_bins, tile_order) — recomputed unless the inputs are the tensors
+    of the previous call on this device, unmodified."""
+    dev = xys.device
+    key = (dev.index, img_height, img_width, block_width,
+           tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (xys, depths, radii, num_tiles_hit)))
+    hit = _BIN_CACHE.get(dev.index)
+    if hit is not None and hit[0] == key:
+        return hit[2]
+    tile_bounds = _tile_bounds(img_height, img_width, block_width)
+    num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+    if num_intersects < 1:
+        res = (0, None, None, None)
+    else:
+        (_, _, _, gaussian_ids_sorted, tile_bins) = bin_and_sort_gaussians(
+            xys.size(0), num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
+        tile_order = None
+        if block_width == 16:
+            T = tile_bounds[0] * tile_bounds[1]
+            tile_order = torch.empty(T, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().gb_tile_order(T, _lib.ptr(tile_bins), _lib.ptr(tile_order),
+                                                    _lib.stream_ptr(dev)), "tile_order")
+        res = (num_intersects, gaussian_ids_sorted, tile_bins, tile_order)
+    # the strong references keep the storages alive, so an equal data_ptr really is the same allocation
+    _BIN_CACHE[dev.index] = (key, (xys, depths, radii, num_tiles_hit), res)
+    return res
+
+
+def clear_bin_cache():
+    _BIN_CACHE.clear()
 
 
 def rasterize_gaussians(
@@ -55,12 +97,12 @@ class _RasterizeGaussians(Function):
             _lib.check_input(t, n)
         _lib.check_input(radii, "radii", torch.int32)
         _lib.check_input(num_tiles_hit, "num_tiles_hit", torch.int32)
-        num_points = xys.size(0)
         C = colors.shape[-1]
         dev = xys.device
-        tile_bounds = _tile_bounds(img_height, img_width, block_width)
-        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
-
+        L = _lib.lib()
+        num_intersects, gaussian_ids_sorted, tile_bins, tile_order = _bin_cached(
+            xys, depths, radii, num_tiles_hit, img_height, img_width, block_width)
+        records = None
         if num_intersects < 1:
             out_img = torch.ones(img_height, img_width, C, device=dev) * background
             gaussian_ids_sorted = torch.zeros(0, 1, device=dev)
@@ -68,22 +110,33 @@ class _RasterizeGaussians(Function):
             final_Ts = torch.zeros(img_height, img_width, device=dev)
             final_idx = torch.zeros(img_height, img_width, device=dev)
         else:
-            (_, _, _, gaussian_ids_sorted, tile_bins) = bin_and_sort_gaussians(
-                num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds, block_width)
             out_img = torch.empty(img_height, img_width, C, device=dev, dtype=torch.float32)
             final_Ts = torch.empty(img_height, img_width, device=dev, dtype=torch.float32)
             final_idx = torch.empty(img_height, img_width, device=dev, dtype=torch.int32)
             with torch.cuda.device(dev):
-                _lib.check(_lib.lib().gb_rasterize_fwd(
-                    img_height, img_width, block_width, C, _lib.ptr(gaussian_ids_sorted), _lib.ptr(tile_bins),
-                    _lib.ptr(xys), _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity), _lib.ptr(background),
-                    _lib.ptr(out_img), _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.stream_ptr(dev)),
-                    "rasterize_forward")
+                st = _lib.stream_ptr(dev)
+                if block_width == 16:
+                    records = torch.empty(num_intersects, 12, device=dev, dtype=torch.float32)
+                    _lib.check(L.gb_pack_records(num_intersects, C, _lib.ptr(gaussian_ids_sorted), _lib.ptr(xys),
+                                                 _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity),
+                                                 _lib.ptr(records), st), "pack_records")
+                    _lib.check(L.gb_rasterize_packed_fwd(img_height, img_width, C, _lib.ptr(tile_bins),
+                                                         _lib.ptr(tile_order), _lib.ptr(records), _lib.ptr(background),
+                                                         _lib.ptr(out_img), _lib.ptr(final_Ts), _lib.ptr(final_idx),
+                                                         st), "rasterize_packed_forward")
+                else:
+                    _lib.check(L.gb_rasterize_fwd(
+                        img_height, img_width, block_width, C, _lib.ptr(gaussian_ids_sorted), _lib.ptr(tile_bins),
+                        _lib.ptr(xys), _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity), _lib.ptr(background),
+                        _lib.ptr(out_img), _lib.ptr(final_Ts), _lib.ptr(final_idx), st), "rasterize_forward")
 
         ctx.img_width, ctx.img_height = img_width, img_height
         ctx.num_intersects, ctx.block_width = num_intersects, block_width
-        ctx.save_for_backward(gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
-                              final_idx)
+        ctx.packed = records is not None
+        saved = [gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts, final_idx]
+        if ctx.packed:
+            saved += [records, tile_order]
+        ctx.save_for_backward(*saved)
         if return_alpha:
             out_alpha = 1 - final_Ts
             return out_img, out_alpha
@@ -91,8 +144,8 @@ class _RasterizeGaussians(Function):
 
     @staticmethod
     def backward(ctx, v_out_img, v_out_alpha=None):
-        (gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts,
-         final_idx) = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        (gaussian_ids_sorted, tile_bins, xys, conics, colors, opacity, background, final_Ts, final_idx) = saved[:9]
         if v_out_alpha is None:
             v_out_alpha = torch.zeros_like(v_out_img[..., 0])
         dev = xys.device
@@ -102,12 +155,23 @@ class _RasterizeGaussians(Function):
         v_colors = torch.zeros_like(colors)
         v_opacity = torch.zeros_like(opacity)
         if ctx.num_intersects >= 1:
+            L = _lib.lib()
+            v_out_img = v_out_img.contiguous()
+            v_out_alpha = v_out_alpha.contiguous()
             with torch.cuda.device(dev):
-                _lib.check(_lib.lib().gb_rasterize_bwd(
-                    ctx.img_height, ctx.img_width, ctx.block_width, C, _lib.ptr(gaussian_ids_sorted),
-                    _lib.ptr(tile_bins), _lib.ptr(xys), _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity),
-                    _lib.ptr(background), _lib.ptr(final_Ts), _lib.ptr(final_idx),
-                    _lib.ptr(v_out_img.contiguous()), _lib.ptr(v_out_alpha.contiguous()), _lib.ptr(v_xy),
-                    _lib.ptr(v_conic), _lib.ptr(v_colors), _lib.ptr(v_opacity), _lib.stream_ptr(dev)),
-                    "rasterize_backward")
+                st = _lib.stream_ptr(dev)
+                if ctx.packed:
+                    records, tile_order = saved[9], saved[10]
+                    _lib.check(L.gb_rasterize_packed_bwd(
+                        ctx.img_height, ctx.img_width, C, _lib.ptr(gaussian_ids_sorted), _lib.ptr(tile_bins),
+                        _lib.ptr(tile_order), _lib.ptr(records), _lib.ptr(background), _lib.ptr(final_Ts),
+                        _lib.ptr(final_idx), _lib.ptr(v_out_img), _lib.ptr(v_out_alpha), _lib.ptr(v_xy),
+                        _lib.ptr(v_conic), _lib.ptr(v_colors), _lib.ptr(v_opacity), st), "rasterize_packed_backward")
+                else:
+                    _lib.check(L.gb_rasterize_bwd(
+                        ctx.img_height, ctx.img_width, ctx.block_width, C, _lib.ptr(gaussian_ids_sorted),
+                        _lib.ptr(tile_bins), _lib.ptr(xys), _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity),
+                        _lib.ptr(background), _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out_img),
+                        _lib.ptr(v_out_alpha), _lib.ptr(v_xy), _lib.ptr(v_conic), _lib.ptr(v_colors),
+                        _lib.ptr(v_opacity), st), "rasterize_backward")
         return (v_xy, None, None, v_conic, None, v_colors, v_opacity, None, None, None, None, None)

@@ -29,6 +29,7 @@ def render(
     block_width: int = 16,
     global_scale: float = 1.0,
     z_near: float = 0.1,
+    fused: bool = True,
 ):
     means3D = primpos.view(-1, 3).contiguous()
     scales = primscale.view(-1, 3).contiguous()
@@ -40,6 +41,16 @@ def render(
 
     xys, depths, radii, conics, compensation, num_tiles_hit, cov3d = project_gaussians(
         means3D, scales, global_scale, rotations, Rt, fx, fy, cx, cy, cam_img_h, cam_img_w, block_width, z_near)
+
+    if fused and return_depth:
+        # rgb and depth share the alphas, so one 4-channel pass gives the same pixels as the
+        # reference's two 3-channel passes (render_gsplat.py:65-78 + :90-104) with half the blend work
+        bg4 = th.cat([bg_color, bg_color[:1]])
+        out4, alpha = rasterize_gaussians(
+            xys, depths, radii, conics, num_tiles_hit, th.cat([colors, depths[:, None]], 1),
+            opacity * compensation[:, None], cam_img_h, cam_img_w, block_width, bg4, return_alpha=True)
+        return {"render": out4[..., :3].permute(2, 0, 1), "final_T": (1.0 - alpha)[None], "alpha": alpha[None],
+                "radii": radii, "depth": out4[..., 3][None]}
 
     out_img, alpha = rasterize_gaussians(
         xys, depths, radii, conics, num_tiles_hit, colors, opacity * compensation[:, None], cam_img_h, cam_img_w,
@@ -57,11 +68,11 @@ def render(
     return out
 
 
-def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None):
+def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None, fused=True):
     """rgca.AutoEncoder.render (rgca.py:112-151): loop over the batch, stack, alpha from the DETACHED final_T,
     depth normalised by alpha.clamp(0.05, 1).  `intrinsics_host` (list of (fx,fy,cx,cy)) avoids the reference's
     four `.item()` device syncs per view when the caller already has them on the host."""
-    B = K.shape[0]
+    B = Rt.shape[0]
     rgbs, Ts, depths = [], [], []
     for b in range(B):
         if intrinsics_host is not None:
@@ -69,7 +80,7 @@ def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, in
         else:
             fx, fy, cx, cy = K[b, 0, 0].item(), K[b, 1, 1].item(), K[b, 0, 2].item(), K[b, 1, 2].item()
         o = render(width, height, fx, fy, cx, cy, Rt[b], preds["primpos"][b], preds["primqvec"][b],
-                   preds["primscale"][b], preds["opacity"][b], preds["color"][b], return_depth=True)
+                   preds["primscale"][b], preds["opacity"][b], preds["color"][b], return_depth=True, fused=fused)
         rgbs.append(o["render"])
         Ts.append(o["final_T"].detach())
         depths.append(o["depth"])

@@ -102,6 +102,29 @@ int gb_rasterize_bwd(int img_h, int img_w, int block_width, int channels, const 
                      const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
                      float* v_conic, float* v_colors, float* v_opacity, void* stream);
 
+/* ---- B200 blend path (block_width == 16): same results as gb_rasterize_fwd/bwd, different work distribution.
+ * These have no counterpart in gsplat's binding; they sit behind the same rasterize_gaussians call
+ * (ca_code/utils/render_gsplat.py:65-78,90-104). */
+
+/* gather (xy, conic, opacity, colours, cull box) of every intersection in sorted order: records [n,12] fp32 */
+int gb_pack_records(int64_t n, int channels, const int32_t* gids_sorted, const float* xys, const float* conics,
+                    const float* colors, const float* opacities, float* records, void* stream);
+
+/* launch order of the tiles, longest list first: order [T] int32 */
+int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
+
+/* blend forward over packed records streamed with cp.async.bulk; tile_order may be NULL */
+int gb_rasterize_packed_fwd(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+                            const float* records, const float* background, float* out_img, float* final_Ts,
+                            int32_t* final_idx, void* stream);
+
+/* blend backward over packed records; gradients are accumulated into (caller zeroes them) */
+int gb_rasterize_packed_bwd(int img_h, int img_w, int channels, const int32_t* gids_sorted,
+                            const int32_t* tile_bins, const int32_t* tile_order, const float* records,
+                            const float* background, const float* final_Ts, const int32_t* final_idx,
+                            const float* v_output, const float* v_output_alpha, float* v_xy, float* v_conic,
+                            float* v_colors, float* v_opacity, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

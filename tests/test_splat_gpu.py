@@ -154,9 +154,10 @@ def test_blend_forward_backward(orc, cuda, case, C):
     G = len(opac)
     v_xy, v_conic = torch.zeros(G, 2, device=cuda), torch.zeros(G, 3, device=cuda)
     v_col, v_op = torch.zeros(G, C, device=cuda), torch.zeros(G, 1, device=cuda)
+    Ts_d, fi_d, vo_d, va_d = d(Ts_r), d(fi_r), d(v_out), d(v_alpha)  # keep alive: raw pointers cross the C ABI
     _lib.check(L.gb_rasterize_bwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(), conics.data_ptr(),
-                                  col.data_ptr(), op.data_ptr(), bgd.data_ptr(), d(Ts_r).data_ptr(),
-                                  d(fi_r).data_ptr(), d(v_out).data_ptr(), d(v_alpha).data_ptr(), v_xy.data_ptr(),
+                                  col.data_ptr(), op.data_ptr(), bgd.data_ptr(), Ts_d.data_ptr(),
+                                  fi_d.data_ptr(), vo_d.data_ptr(), va_d.data_ptr(), v_xy.data_ptr(),
                                   v_conic.data_ptr(), v_col.data_ptr(), v_op.data_ptr(), st), "bwd")
     torch.cuda.synchronize()
     for name, got, want in (("v_xy", v_xy, ref[0]), ("v_conic", v_conic, ref[1]), ("v_colors", v_col, ref[2]),
@@ -271,3 +272,119 @@ def test_product_refuses_cpu_tensors(cuda):
     with pytest.raises(RuntimeError):
         project_gaussians(torch.zeros(4, 3), torch.ones(4, 3), 1.0, torch.tensor([[1.0, 0, 0, 0]] * 4),
                           torch.eye(4)[:3].contiguous(), 10.0, 10.0, 8.0, 8.0, 16, 16, 16)
+
+
+@pytest.mark.parametrize("C", [3, 4])
+@pytest.mark.parametrize("case", ["dense96", "ragged", "ties", "tiny_prims", "big"])
+def test_packed_blend_matches_generic_kernel(orc, cuda, case, C):
+    """The bulk-copy/culling blend (csrc/splat_blend_packed.cu) must give the generic kernel's pixels BIT-exactly
+    (same per-pair arithmetic, culled pairs are exactly the alpha<1/255 ones) and its gradients to atomics order."""
+    from goliath_b200 import _lib
+
+    if case == "big":
+        kw, bw, mult = dict(G=60000, img_h=300, img_w=260, seed=21), 16, 3.0
+    else:
+        kw, bw, mult = CASES[case]
+    s = small_scene(**kw)
+    H, W = s["img_h"], s["img_w"]
+    rng = np.random.default_rng(7)
+    p, b, colors, bg, opac = _blend_inputs(orc, s, bw, mult, C, rng)
+    opac[::97] = 0.001   # below 1/255: culled everywhere
+    opac[::89] = 1.0     # exercises the 0.99 / 0.999 clamps
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    gids, bins, xys, conics, col, op, bgd = (d(b["gaussian_ids_sorted"]), d(b["tile_bins"]), d(p["xys"]),
+                                             d(p["conics"]), d(colors), d(opac), d(bg))
+    n = len(b["gaussian_ids_sorted"])
+    T = bins.shape[0]
+    L = _lib.lib()
+    st = _lib.stream_ptr(cuda)
+    outs = []
+    rec = torch.empty(n, 12, device=cuda)
+    order = torch.empty(T, dtype=torch.int32, device=cuda)
+    _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), col.data_ptr(),
+                                 op.data_ptr(), rec.data_ptr(), st), "pack")
+    _lib.check(L.gb_tile_order(T, bins.data_ptr(), order.data_ptr(), st), "order")
+    torch.cuda.synchronize()
+    o = t2n(order)
+    assert np.array_equal(np.sort(o), np.arange(T)), "tile order must be a permutation"
+    lens = (b["tile_bins"][:, 1] - b["tile_bins"][:, 0])[o]
+    assert np.all(np.diff(lens >> 3) <= 0), "longest lists first"
+    for packed in (False, True):
+        out = torch.empty(H, W, C, device=cuda)
+        Ts = torch.empty(H, W, device=cuda)
+        fi = torch.empty(H, W, device=cuda, dtype=torch.int32)
+        if packed:
+            _lib.check(L.gb_rasterize_packed_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(),
+                                                 bgd.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "pf")
+        else:
+            _lib.check(L.gb_rasterize_fwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(),
+                                          conics.data_ptr(), col.data_ptr(), op.data_ptr(), bgd.data_ptr(),
+                                          out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "gf")
+        torch.cuda.synchronize()
+        outs.append((out, Ts, fi))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    v_out = d(rng.standard_normal((H, W, C)).astype(np.float32))
+    v_alpha = d(rng.standard_normal((H, W)).astype(np.float32))
+    G = len(opac)
+    grads = []
+    for packed in (False, True):
+        g = [torch.zeros(G, 2, device=cuda), torch.zeros(G, 3, device=cuda), torch.zeros(G, C, device=cuda),
+             torch.zeros(G, 1, device=cuda)]
+        Ts, fi = outs[0][1], outs[0][2]
+        if packed:
+            _lib.check(L.gb_rasterize_packed_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(),
+                                                 rec.data_ptr(), bgd.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+                                                 v_out.data_ptr(), v_alpha.data_ptr(), g[0].data_ptr(), g[1].data_ptr(),
+                                                 g[2].data_ptr(), g[3].data_ptr(), st), "pb")
+        else:
+            _lib.check(L.gb_rasterize_bwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(),
+                                          conics.data_ptr(), col.data_ptr(), op.data_ptr(), bgd.data_ptr(),
+                                          Ts.data_ptr(), fi.data_ptr(), v_out.data_ptr(), v_alpha.data_ptr(),
+                                          g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), st), "gb")
+        torch.cuda.synchronize()
+        grads.append([t2n(x) for x in g])
+    for name, x, y in zip(("v_xy", "v_conic", "v_colors", "v_opacity"), grads[1], grads[0]):
+        assert_close(x, y, rtol=2e-5, atol=2e-5 * np.abs(y).max(), what=name + " packed vs generic")
+    # and against the oracle
+    ref = orc.rasterize_bwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], colors, opac,
+                            bg, t2n(outs[0][1]), t2n(outs[0][2]), t2n(v_out), t2n(v_alpha))
+    for name, x, y in zip(("v_xy", "v_conic", "v_colors", "v_opacity"), grads[1], ref):
+        assert_close(x, y, rtol=1e-4, atol=1e-5 * np.abs(y).max(), frac=0.999, what=name + " packed vs oracle")
+
+
+def test_fused_render_equals_two_pass_and_bin_cache(cuda):
+    """goliath_b200.render.render: the fused 4-channel pass gives the two-pass pixels exactly; the second
+    rasterisation of the two-pass form reuses the binning (no cumsum/sort launches) unless an input changed."""
+    from goliath_b200 import _lib
+    from goliath_b200.gsplat import rasterize as R
+    from goliath_b200.render import render
+
+    kw, bw, mult = CASES["dense96"]
+    s = small_scene(**kw)
+    t = _dev(s, cuda)
+    args = (s["img_w"], s["img_h"], s["fx"], s["fy"], s["cx"], s["cy"], t["viewmat"], t["means3d"],
+            t["quats"], t["scales"] * mult, t["opacity"], t["colors"])
+    R.clear_bin_cache()
+    L = _lib.lib()
+    L.gb_launch_count_reset()
+    a = render(*args, fused=False)
+    two_pass_launches = L.gb_launch_count()
+    R.clear_bin_cache()
+    L.gb_launch_count_reset()
+    b = render(*args, fused=True)
+    fused_launches = L.gb_launch_count()
+    for k in ("render", "alpha", "depth"):
+        assert torch.equal(a[k], b[k]), k
+    # one binning serves both passes of the two-pass form: only pack + blend are extra
+    assert two_pass_launches - fused_launches == 2, (two_pass_launches, fused_launches)
+    # cache must miss after an in-place change of an input
+    from goliath_b200.gsplat import project_gaussians, rasterize_gaussians
+    xys, depths, radii, conics, comp, nth, cov3d = project_gaussians(
+        t["means3d"], t["scales"] * mult, 1.0, t["quats"], t["viewmat"], s["fx"], s["fy"], s["cx"], s["cy"],
+        s["img_h"], s["img_w"], bw, 0.1)
+    bg = torch.zeros(3, device=cuda)
+    i1 = rasterize_gaussians(xys, depths, radii, conics, nth, t["colors"], t["opacity"], s["img_h"], s["img_w"], bw, bg)
+    depths.add_(5.0)  # bumps the version counter
+    L.gb_launch_count_reset()
+    i2 = rasterize_gaussians(xys, depths, radii, conics, nth, t["colors"], t["opacity"], s["img_h"], s["img_w"], bw, bg)
+    assert L.gb_launch_count() > 6, "binning must be recomputed when depths changed"
