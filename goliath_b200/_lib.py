@@ -35,6 +35,14 @@ SIGNATURES = {
     "gb_tile_order": (_i, [_i, _vp, _vp, _vp]),
     "gb_rasterize_packed_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_packed_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
+    "gb_compute_raydirs_fwd": (_i, [_i, _i, _i] + [_vp] * 5 + [_f] + [_vp] * 3 + [_vp]),
+    "gb_compute_raydirs_bwd": (_i, []),
+    "gb_mvp_aabb_workspace_bytes": (_sz, [_i, _i]),
+    "gb_mvp_compute_aabb": (_i, [_i, _i] + [_vp] * 8 + [_vp]),
+    "gb_mvp_raymarch_fwd": (_i, [_i] * 4 + [_vp, _vp, _f] + [_vp] * 5 + [_i] * 3 + [_vp] + [_i] * 3 + [_vp] * 4
+                            + [_i, _f, _f, _i, _i, _vp]),
+    "gb_mvp_raymarch_bwd": (_i, [_i] * 4 + [_vp, _vp, _f] + [_vp] * 5 + [_i] * 3 + [_vp] + [_i] * 3 + [_vp] * 8
+                            + [_i, _f, _f, _i, _i, _vp]),
 }
 
 

@@ -17,7 +17,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 # per-file extra flags.  splat_project.cu carries the bit-exact binning contract: no FMA contraction.
 # sg_shade.cu mirrors the reference extension's own flag (extensions/sgutils/setup.py:31) for last-bit parity.
-EXTRA = {"splat_project.cu": ["-fmad=false"], "sg_shade.cu": ["-use_fast_math"]}
+EXTRA = {"splat_project.cu": ["-fmad=false"], "sg_shade.cu": ["-use_fast_math"],
+         "mvp_raymarch.cu": ["-use_fast_math"]}  # extensions/mvpraymarch/setup.py:31
 
 
 def sources():

@@ -62,3 +62,54 @@ def shade_inputs(G: int, seed: int = SEED + 2) -> Dict[str, torch.Tensor]:
     lobe_dirs = torch.randn(1, G, 3, generator=g).contiguous()
     sigma = (0.1 * torch.exp(0.5 * torch.randn(1, G, generator=g))).clamp(min=0.01).contiguous()
     return dict(lobe_dirs=lobe_dirs, lobe_sigmas=sigma)
+
+
+def mvp_scene(N: int = 2, side: int = 8, T=(4, 8, 8), img_h: int = 64, img_w: int = 48, seed: int = SEED + 7,
+              density: float = 40.0, with_warp: bool = False) -> Dict:
+    """Hand-MVP-like synthetic scene (SURVEY.md §8d config 4 recipe, scaled): K = side*side primitives on a UV grid
+    wrapped on a cylinder (normalised unit-cube coordinates, volradius = 1), small random rotations, template =
+    softplus(1.5 N(0,1)) with the alpha channel shifted, N ring cameras.  Returns CPU tensors + camera parameters."""
+    g = torch.Generator().manual_seed(seed)
+    K = side * side
+    u = (torch.arange(side, dtype=torch.float32) + 0.5) / side
+    uu, vv = torch.meshgrid(u, u, indexing="ij")          # uu: around the axis, vv: along it
+    ang = 2 * math.pi * uu.reshape(-1)
+    rad, height = 0.28, 0.9
+    pos = torch.stack([rad * torch.cos(ang), (vv.reshape(-1) - 0.5) * height, rad * torch.sin(ang)], -1)
+    pos = pos + 0.01 * torch.randn(K, 3, generator=g)
+    normal = torch.stack([torch.cos(ang), torch.zeros(K), torch.sin(ang)], -1)
+    tangent = torch.stack([-torch.sin(ang), torch.zeros(K), torch.cos(ang)], -1)
+    up = torch.tensor([0.0, 1.0, 0.0]).expand(K, 3)
+    R = torch.stack([tangent, up, normal], -1)            # columns = local axes in world space
+    # small random rotation
+    w = 0.15 * torch.randn(K, 3, generator=g)
+    th = w.norm(dim=-1, keepdim=True).clamp(min=1e-8)
+    kx = w / th
+    Kx = torch.zeros(K, 3, 3)
+    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0] = -kx[:, 2], kx[:, 1], kx[:, 2]
+    Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -kx[:, 0], -kx[:, 1], kx[:, 0]
+    Rr = torch.eye(3) + torch.sin(th)[..., None] * Kx + (1 - torch.cos(th))[..., None] * (Kx @ Kx)
+    R = Rr @ R
+    half = torch.tensor([1.3 * math.pi * rad / side, 0.65 * height / side, 0.04])
+    primscale = (1.0 / half).expand(K, 3)
+    TD, TH, TW = T
+    tpl = torch.nn.functional.softplus(1.5 * torch.randn(N, K, TD, TH, TW, 4, generator=g))
+    tpl[..., 3] = torch.nn.functional.softplus(1.5 * torch.randn(N, K, TD, TH, TW, generator=g) - 1.0) * density
+    out = dict(primpos=pos[None].repeat(N, 1, 1).contiguous(), primrot=R[None].repeat(N, 1, 1, 1).contiguous(),
+               primscale=primscale[None].repeat(N, 1, 1).contiguous(), template=tpl.contiguous())
+    if with_warp:
+        lin = [torch.linspace(-1, 1, s) for s in (TD, TH, TW)]
+        zz, yy, xx = torch.meshgrid(*lin, indexing="ij")
+        grid = torch.stack([xx, yy, zz], -1)               # channels-last identity warp, (x, y, z)
+        out["warp"] = (grid[None, None] + 0.05 * torch.randn(N, K, TD, TH, TW, 3, generator=g)).contiguous()
+    # cameras on a ring of radius 2.5 (normalised units) looking at the origin
+    viewpos, viewrot = [], []
+    for n in range(N):
+        c = ring_camera(n * 3 + 1, radius=2.5, img_h=img_h, img_w=img_w)
+        viewpos.append(c["campos"])
+        viewrot.append(c["viewmat"][:, :3])                # rows = camera axes in world space
+    f = 1.6 * min(img_h, img_w)
+    out.update(viewpos=torch.stack(viewpos).contiguous(), viewrot=torch.stack(viewrot).contiguous(),
+               focal=torch.full((N, 2), f), princpt=torch.tensor([[img_w / 2.0, img_h / 2.0]] * N),
+               img_h=img_h, img_w=img_w, volradius=1.0)
+    return out

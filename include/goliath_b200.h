@@ -125,6 +125,47 @@ int gb_rasterize_packed_bwd(int img_h, int img_w, int channels, const int32_t* g
                             const float* v_output, const float* v_output_alpha, float* v_xy, float* v_conic,
                             float* v_colors, float* v_opacity, void* stream);
 
+/* ---------------------------------------------------------------- utilslib (extensions/utils) */
+
+/* replaces utilslib.compute_raydirs_forward — utils.cpp:46-82 (kernel utils_kernel.cu:11-51).
+ * viewpos [N,3], viewrot [N,3,3], focal [N,2], princpt [N,2], pixelcoords [N,H,W,2] or NULL (integer grid),
+ * outputs raypos/raydir [N,H,W,3], tminmax [N,H,W,2]. */
+int gb_compute_raydirs_fwd(int N, int H, int W, const float* viewpos, const float* viewrot, const float* focal,
+                           const float* princpt, const float* pixelcoords, float volradius, float* raypos,
+                           float* raydir, float* tminmax, void* stream);
+/* replaces utilslib.compute_raydirs_backward — utils.cpp:84-132: the reference kernel is an empty stub. */
+int gb_compute_raydirs_bwd(void);
+
+/* ---------------------------------------------------------------- mvpraymarchlib (extensions/mvpraymarch) */
+
+/* replaces mvpraymarchlib.compute_aabb — mvpraymarch.cpp (compute_aabb) -> bvh.cu:157-201,249-294.
+ * Tree arrays as built by mvpraymarch.py:44-82; nodeaabb [N,2K-1,2,3] out; workspace of
+ * gb_mvp_aabb_workspace_bytes(N,K) bytes replaces the reference's per-call cudaMalloc. */
+size_t gb_mvp_aabb_workspace_bytes(int N, int K);
+int gb_mvp_compute_aabb(int N, int K, const float* primpos, const float* primrot, const float* primscale,
+                        const int32_t* sortedobjid, const int32_t* nodechildren, const int32_t* nodeparent,
+                        float* nodeaabb, void* workspace, void* stream);
+
+/* replaces mvpraymarchlib.raymarch_forward — mvpraymarch.cpp:179-283 -> mvpraymarch_kernel.cu:41-130.
+ * template [N,K,TD,TH,TW,4] channels-last; warp [N,K,WD,WH,WW,3] or NULL (algo 0); rayrgba [N,H,W,4] out;
+ * raysat [N,H,W,3] out or NULL; shadow [N,K,TD,TH,TW,2] accumulated or NULL.  The arguments the reference
+ * accepts and ignores (sortboxes, maxhitboxes, synchitboxes, chlast, accum, termthresh, griddim)
+ * are handled by the Python binding and are not part of the ABI. */
+int gb_mvp_raymarch_fwd(int N, int H, int W, int K, const float* raypos, const float* raydir, float stepsize,
+                        const float* tminmax, const float* nodeaabb, const float* primpos, const float* primrot,
+                        const float* primscale, int TD, int TH, int TW, const float* tplate, int WD, int WH, int WW,
+                        const float* warp, float* rayrgba, float* raysat, float* shadow, int algo, float fadescale,
+                        float fadeexp, int blocksizex, int blocksizey, void* stream);
+
+/* replaces mvpraymarchlib.raymarch_backward — mvpraymarch.cpp:285-399 -> mvpraymarch_kernel.cu:132-221.
+ * Gradient buffers are accumulated into (the caller zero-fills them, mvpraymarch.py:256-263). */
+int gb_mvp_raymarch_bwd(int N, int H, int W, int K, const float* raypos, const float* raydir, float stepsize,
+                        const float* tminmax, const float* nodeaabb, const float* primpos, const float* primrot,
+                        const float* primscale, int TD, int TH, int TW, const float* tplate, int WD, int WH, int WW,
+                        const float* warp, const float* raysat, const float* grad_rayrgba, float* grad_primpos,
+                        float* grad_primrot, float* grad_primscale, float* grad_tplate, float* grad_warp, int algo,
+                        float fadescale, float fadeexp, int blocksizex, int blocksizey, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

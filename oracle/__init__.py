@@ -190,3 +190,79 @@ def sg_bwd(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, n_lights, 
     lib().orc_sg_bwd(ctypes.c_int(N), ctypes.c_int(D), ctypes.c_int(L), *[_p(x) for x in a], _p(gd), _p(gs), _p(gl),
                      ctypes.c_int(w_type))
     return gd, gs, gl
+
+
+# ----------------------------------------------------------------------------------------- MVP raymarch path
+
+
+def raydirs_fwd(viewpos, viewrot, focal, princpt, pixelcoords, volradius, H=None, W=None):
+    """compute_raydirs (extensions/utils/utils_kernel.cu:11-51). pixelcoords [N,H,W,2] or None (then H, W given)."""
+    viewpos, viewrot, focal, princpt = _f32(viewpos), _f32(viewrot), _f32(focal), _f32(princpt)
+    N = viewpos.shape[0]
+    if pixelcoords is not None:
+        pixelcoords = _f32(pixelcoords)
+        H, W = pixelcoords.shape[1:3]
+    raypos = np.zeros((N, H, W, 3), np.float32)
+    raydir = np.zeros((N, H, W, 3), np.float32)
+    tminmax = np.zeros((N, H, W, 2), np.float32)
+    lib().orc_raydirs_fwd(ctypes.c_int(N), ctypes.c_int(H), ctypes.c_int(W), _p(viewpos), _p(viewrot), _p(focal),
+                          _p(princpt), _p(pixelcoords), ctypes.c_float(volradius), _p(raypos), _p(raydir), _p(tminmax))
+    return raypos, raydir, tminmax
+
+
+def compute_aabb_fixedorder(primpos, primrot, primscale):
+    primpos, primrot, primscale = _f32(primpos), _f32(primrot), _f32(primscale)
+    N, K = primpos.shape[:2]
+    aabb = np.zeros((N, 2 * K - 1, 2, 3), np.float32)
+    lib().orc_compute_aabb_fixedorder(ctypes.c_int(N), ctypes.c_int(K), _p(primpos), _p(primrot), _p(primscale), _p(aabb))
+    return aabb
+
+
+def _rm_common(raypos, raydir, tminmax, primpos, primrot, primscale, template, warp):
+    raypos, raydir, tminmax = _f32(raypos), _f32(raydir), _f32(tminmax)
+    primpos, primrot, primscale, template = _f32(primpos), _f32(primrot), _f32(primscale), _f32(template)
+    N, H, W = raypos.shape[:3]
+    K = primpos.shape[1]
+    TD, TH, TW = template.shape[2:5]
+    assert template.shape[-1] == 4, "channels-last template [N,K,TD,TH,TW,4]"
+    if warp is not None:
+        warp = _f32(warp)
+        WD, WH, WW = warp.shape[2:5]
+    else:
+        WD = WH = WW = 0
+    aabb = compute_aabb_fixedorder(primpos, primrot, primscale)
+    return raypos, raydir, tminmax, primpos, primrot, primscale, template, warp, aabb, (N, H, W, K, TD, TH, TW, WD, WH, WW)
+
+
+def raymarch_fwd(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp=None, algo=0,
+                 fadescale=8.0, fadeexp=8.0, blocksize=(8, 16), with_shadow=False):
+    """mvpraymarch forward, usebvh='fixedorder' (extensions/mvpraymarch/mvpraymarch.py:91-220)."""
+    (raypos, raydir, tminmax, primpos, primrot, primscale, template, warp, aabb,
+     (N, H, W, K, TD, TH, TW, WD, WH, WW)) = _rm_common(raypos, raydir, tminmax, primpos, primrot, primscale, template, warp)
+    rayrgba = np.zeros((N, H, W, 4), np.float32)
+    raysat = np.full((N, H, W, 3), -1, np.float32)
+    shadow = np.zeros((N, K, TD, TH, TW, 2), np.float32) if with_shadow else None
+    c = ctypes
+    lib().orc_raymarch_fwd(
+        c.c_int(N), c.c_int(H), c.c_int(W), c.c_int(K), _p(raypos), _p(raydir), c.c_float(stepsize), _p(tminmax),
+        _p(aabb), _p(primpos), _p(primrot), _p(primscale), c.c_int(TD), c.c_int(TH), c.c_int(TW), _p(template),
+        c.c_int(WD), c.c_int(WH), c.c_int(WW), _p(warp), _p(rayrgba), _p(raysat), _p(shadow), c.c_int(algo),
+        c.c_float(fadescale), c.c_float(fadeexp), c.c_int(blocksize[0]), c.c_int(blocksize[1]))
+    return rayrgba, raysat, shadow
+
+
+def raymarch_bwd(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, raysat, grad_rayrgba,
+                 algo=0, fadescale=8.0, fadeexp=8.0, blocksize=(8, 16)):
+    (raypos, raydir, tminmax, primpos, primrot, primscale, template, warp, aabb,
+     (N, H, W, K, TD, TH, TW, WD, WH, WW)) = _rm_common(raypos, raydir, tminmax, primpos, primrot, primscale, template, warp)
+    g_pos, g_rot, g_scale = np.zeros_like(primpos), np.zeros_like(primrot), np.zeros_like(primscale)
+    g_t = np.zeros_like(template)
+    g_w = np.zeros_like(warp) if warp is not None else None
+    c = ctypes
+    lib().orc_raymarch_bwd(
+        c.c_int(N), c.c_int(H), c.c_int(W), c.c_int(K), _p(raypos), _p(raydir), c.c_float(stepsize), _p(tminmax),
+        _p(aabb), _p(primpos), _p(primrot), _p(primscale), c.c_int(TD), c.c_int(TH), c.c_int(TW), _p(template),
+        c.c_int(WD), c.c_int(WH), c.c_int(WW), _p(warp), _p(_f32(raysat)), _p(_f32(grad_rayrgba)), _p(g_pos), _p(g_rot),
+        _p(g_scale), _p(g_t), _p(g_w), c.c_int(algo), c.c_float(fadescale), c.c_float(fadeexp), c.c_int(blocksize[0]),
+        c.c_int(blocksize[1]))
+    return g_pos, g_rot, g_scale, g_t, g_w
