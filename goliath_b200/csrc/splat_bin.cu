@@ -155,75 +155,39 @@ __global__ void __launch_bounds__(kSortBlock) sort_hist_kernel(long long n, cons
   hist[(size_t)threadIdx.x * num_tiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// single CTA: exclusive scan over the digit-major table (length 256*num_tiles), in place.
-// Also reports whether the whole pass is a no-op (one digit holds every key) via *uniform.
-__global__ void __launch_bounds__(1024) sort_scan_kernel(int len, unsigned* __restrict__ hist, int num_tiles,
-                                                         long long n, int* __restrict__ uniform) {
-  __shared__ unsigned s_warp[33];
-  __shared__ unsigned s_carry;
-  __shared__ int s_uniform;
-  if (threadIdx.x == 0) { s_carry = 0; s_uniform = 0; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // each thread handles 4 consecutive entries per sweep
-  for (int base = 0; base < len; base += 4096) {
-    const int i0 = base + threadIdx.x * 4;
-    unsigned v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < len) ? hist[i0 + k] : 0u;
-    const unsigned s = v[0] + v[1] + v[2] + v[3];
-    unsigned inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned w = s_warp[lane], winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
-        if (lane >= o) winc += t;
-      }
-      s_warp[lane] = winc - w;
-      if (lane == 31) s_warp[32] = winc;
-    }
-    __syncthreads();
-    unsigned run = s_carry + s_warp[warp] + inc - s;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i0 + k < len) {
-        hist[i0 + k] = run;
-        // digit boundary: entry index (i0+k) % num_tiles == 0 starts a digit; detect "all keys in one digit"
-      }
-      run += v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += s_warp[32];
-    __syncthreads();
+// one CTA per digit: exclusive scan of that digit's per-tile counts (in place) + the digit's total.
+// 256 small independent scans run in parallel instead of one serial sweep over the 256*num_tiles table.
+__global__ void __launch_bounds__(kScanBlock) sort_scan_kernel(unsigned* __restrict__ hist, int num_tiles,
+                                                               unsigned* __restrict__ totals) {
+  __shared__ int s_warp[33];
+  unsigned* row = hist + (size_t)blockIdx.x * num_tiles;
+  int carry = 0;
+  for (int base = 0; base < num_tiles; base += kScanBlock) {
+    const int i = base + threadIdx.x;
+    const int v = (i < num_tiles) ? (int)row[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, s_warp, total);
+    if (i < num_tiles) row[i] = (unsigned)(carry + ex);
+    carry += total;
   }
-  // uniform pass test: some digit's range [start_d, start_{d+1}) covers all n keys.
-  // start_d = hist[d*num_tiles]; after the scan, a digit holds everything iff start_d == 0 and start_{d+1} == n
-  // (or d == 255 with start_d == 0).  Equivalent: the number of digits with start == 0 ... simpler: check directly.
-  for (int d = threadIdx.x; d < kRadix; d += blockDim.x) {
-    const unsigned start = hist[(size_t)d * num_tiles];
-    const unsigned end = (d == kRadix - 1) ? (unsigned)n : hist[(size_t)(d + 1) * num_tiles];
-    if (start == 0u && end == (unsigned)n && n > 0) s_uniform = 1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *uniform = s_uniform;
+  if (threadIdx.x == 0) totals[blockIdx.x] = (unsigned)carry;
 }
 
 __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(
     long long n, const unsigned long long* __restrict__ keys_in, const int* __restrict__ vals_in,
     unsigned long long* __restrict__ keys_out, int* __restrict__ vals_out, int shift, int num_tiles,
-    const unsigned* __restrict__ offsets /* scanned [256][num_tiles] */, const int* __restrict__ uniform) {
+    const unsigned* __restrict__ offsets /* per-digit scanned [256][num_tiles] */,
+    const unsigned* __restrict__ totals /* [256] keys per digit */) {
   constexpr int kWarps = kSortBlock / 32;
   __shared__ unsigned s_whist[kWarps][kRadix];  // per-warp digit counts -> per-warp running offsets (8 KB)
+  __shared__ int s_scan[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool copy_only = (*uniform != 0);
+  // digit bases = exclusive scan of the 256 digit totals (every CTA recomputes it: 256 loads from L2);
+  // a digit holding every key makes the pass a no-op (typical for the top depth byte)
+  const unsigned my_total = totals[threadIdx.x];
+  const bool copy_only = __syncthreads_or(my_total == (unsigned)n) != 0;
+  int tot_unused;
+  const unsigned digit_base = (unsigned)block_exclusive_scan((int)my_total, s_scan, tot_unused);
   const long long tile_base = (long long)blockIdx.x * kSortTile;
   const long long warp_base = tile_base + (long long)warp * (32 * kSortItems);
 
@@ -265,7 +229,7 @@ __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(
   // exclusive scan across warps per digit + global base for (digit, tile)
   {
     const int d = threadIdx.x;  // 256 threads == 256 digits
-    unsigned run = offsets[(size_t)d * num_tiles + blockIdx.x];
+    unsigned run = digit_base + offsets[(size_t)d * num_tiles + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       const unsigned c = s_whist[w][d];
@@ -343,7 +307,7 @@ GB_API size_t gb_sort_workspace_bytes(int64_t n) {
   b += (size_t)nn * 4;                 // alt vals
   b = (b + 255) & ~(size_t)255;
   b += (size_t)kRadix * tiles * 4;     // histogram table
-  b += 256;                            // uniform flag
+  b += kRadix * 4;                     // digit totals
   return b;
 }
 
@@ -361,7 +325,7 @@ GB_API int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t
   int* alt_v = (int*)(ws + (size_t)n * 8);
   size_t off = ((size_t)n * 12 + 255) & ~(size_t)255;
   unsigned* hist = (unsigned*)(ws + off);
-  int* uniform = (int*)(ws + off + (size_t)kRadix * tiles * 4);
+  unsigned* totals = (unsigned*)(ws + off + (size_t)kRadix * tiles * 4);
 
   const int passes = (key_bits + 7) / 8;
   // ping-pong so that the LAST pass lands in the caller's output buffers
@@ -373,8 +337,8 @@ GB_API int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t
     int* dst_v = to_out ? gids_sorted : alt_v;
     const int shift = 8 * p;
     sort_hist_kernel<<<tiles, kSortBlock, 0, s>>>(n, src_k, shift, tiles, hist);
-    sort_scan_kernel<<<1, 1024, 0, s>>>(kRadix * tiles, hist, tiles, n, uniform);
-    sort_scatter_kernel<<<tiles, kSortBlock, 0, s>>>(n, src_k, src_v, dst_k, dst_v, shift, tiles, hist, uniform);
+    sort_scan_kernel<<<kRadix, kScanBlock, 0, s>>>(hist, tiles, totals);
+    sort_scatter_kernel<<<tiles, kSortBlock, 0, s>>>(n, src_k, src_v, dst_k, dst_v, shift, tiles, hist, totals);
     src_k = dst_k;
     src_v = dst_v;
   }

@@ -1,0 +1,77 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of the view-sharded path — the frame owner broadcasts
+the packed decoded-Gaussian table, every rank renders its own view, gradients w.r.t. the table are all-reduced.
+The per-view render is replaced by the CPU oracle here (tests may use it); the collectives and the sharding are the
+code under test (bench.py uses the same pattern with NCCL)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from goliath_b200 import synthetic
+    from goliath_b200.dist import owner_broadcast, reduce_grads, views_of_rank
+
+    G, H, W = 800, 48, 40
+    table = torch.zeros(G, 14)
+    if rank == 0:  # only the owner holds the decoded Gaussians
+        sc = synthetic.head_gaussians(G, seed=3)
+        table = torch.cat([sc["means3d"], sc["quats"], sc["scales"] * 12, sc["opacity"], sc["colors"]], 1).contiguous()
+    table = owner_broadcast(table, src=0)
+    views = views_of_rank(rank, world, 4)
+    assert views == [rank, rank + 2]
+    grad = torch.zeros_like(table)
+    checksum = 0.0
+    for v in views:
+        c = synthetic.ring_camera(v, img_h=H, img_w=W)
+        f = 300.0
+        t = table.numpy()
+        p = oracle.project_fwd(t[:, 0:3], t[:, 7:10], 1.0, t[:, 3:7], c["viewmat"].numpy(), f, f, W / 2, H / 2, H, W, 16, 0.1)
+        b = oracle.bin_and_sort(p["xys"], p["depths"], p["radii"], p["num_tiles_hit"], H, W, 16)
+        opac = t[:, 10] * p["compensation"]
+        img, Ts, fi = oracle.rasterize_fwd(H, W, 16, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"],
+                                           t[:, 11:14], opac, np.zeros(3, np.float32))
+        g = oracle.rasterize_bwd(H, W, 16, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], t[:, 11:14],
+                                 opac, np.zeros(3, np.float32), Ts, fi, np.ones((H, W, 3), np.float32),
+                                 np.zeros((H, W), np.float32))
+        grad[:, 11:14] += torch.from_numpy(g[2])
+        checksum += float(img.sum())
+    local = float(grad.sum())
+    total = reduce_grads(grad)  # in place
+    q.put((rank, float(table.sum()), checksum, float(total.sum()), local))
+    dist.destroy_process_group()
+
+
+def test_view_shard_broadcast_and_grad_allreduce():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    (_, t0, c0, tot0, g0), (_, t1, c1, tot1, g1) = res
+    assert t0 == t1 and t0 != 0.0, "both ranks must hold the owner's table after the broadcast"
+    assert c0 != c1, "ranks render different views"
+    assert abs(tot0 - tot1) < 1e-3 * abs(tot0) and abs(tot0 - (g0 + g1)) < 1e-3 * abs(tot0), "all-reduce(sum) of grads"
