@@ -1,0 +1,131 @@
+"""Decoder building blocks with the reference's names, parameter names and shapes (ca_code/nn/layers.py), so its
+checkpoints load (`weight_v`, `weight_g`, `bias`): `ConvTranspose2dWNUB`, `LinearWN`, `make_conv_trans`,
+`make_linear`.  Weight norm is the reference's non-standard one: g per output channel, norm of v over the WHOLE tensor
+(layers.py:200-204,468-480):  w = g * v / ||v||_F.
+
+The stride-2 4x4 transposed convolution + untied bias + LeakyReLU runs as ONE hand-written sm_100a kernel in the
+forward (csrc/deconv_wnub.cu).  Round-1 status: its backward and LinearWN still go through PyTorch library calls
+(cuDNN / cuBLAS) — listed as next in DESIGN.md §7, not claimed as hand-written."""
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib
+
+
+class _Deconv4x4s2WNUB(Function):
+    @staticmethod
+    def forward(ctx, x, weight_v, weight_g, bias, slope):
+        x, weight_v = x.contiguous(), weight_v.contiguous()
+        _lib.check_input(x, "input")
+        _lib.check_input(weight_v, "weight_v")
+        B, Cin, Hi, Wi = x.shape
+        Cout = weight_v.shape[1]
+        if weight_v.shape != (Cin, Cout, 4, 4):
+            raise RuntimeError("weight_v must be [Cin, Cout, 4, 4]")
+        vnorm = weight_v.norm()
+        scale = (weight_g.reshape(-1) / vnorm).contiguous()
+        b = None if bias is None else bias.contiguous()
+        if b is not None and b.shape != (Cout, 2 * Hi, 2 * Wi):
+            raise RuntimeError("untied bias must be [Cout, 2*Hi, 2*Wi]")
+        out = torch.empty(B, Cout, 2 * Hi, 2 * Wi, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().gb_deconv4x4s2_wnub_fwd(
+                B, Cin, Cout, Hi, Wi, _lib.ptr(x), _lib.ptr(weight_v), _lib.ptr(scale), _lib.ptr(b),
+                float(slope if slope is not None else 1.0), int(slope is not None), _lib.ptr(out),
+                _lib.stream_ptr(x.device)), "deconv4x4s2_wnub_fwd")
+        ctx.save_for_backward(x, weight_v, weight_g, out)
+        ctx.slope = slope
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        # library backward (cuDNN) — see module docstring
+        x, v, g, out = ctx.saved_tensors
+        gz = gout if ctx.slope is None else gout * torch.where(out > 0, 1.0, float(ctx.slope))
+        vnorm = v.norm()
+        w = g * v / vnorm
+        gx = F.conv2d(gz, w, stride=2, padding=1) if ctx.needs_input_grad[0] else None
+        gw = torch.nn.grad.conv2d_weight(gz, w.shape, x, stride=2, padding=1)
+        # w = g * v / n, n = ||v||_F :  dL/dg_co = <gw_co, v_co> / n ;  dL/dv = g * gw / n - <gw, w> * v / n^2
+        gg = (gw * v).sum(dim=(0, 2, 3), keepdim=True) / vnorm
+        gv = g * gw / vnorm - (gw * w).sum() * v / (vnorm * vnorm)
+        gb = gz.sum(0) if ctx.has_bias else None
+        return gx, gv, gg.view_as(g), gb, None
+
+
+class ConvTranspose2dWNUB(nn.Module):
+    """ConvTranspose2d(k=4, s=2, p=1) with weight norm and untied bias (layers.py:331-397,478-480)."""
+
+    def __init__(self, in_channels, out_channels, height, width, kernel_size=4, stride=2, padding=1, bias=True):
+        super().__init__()
+        if (kernel_size, stride, padding) != (4, 2, 1):
+            raise NotImplementedError("the fused kernel covers the decoder towers' k=4, s=2, p=1 layers")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight_v = nn.Parameter(torch.empty(in_channels, out_channels, 4, 4))
+        self.weight_g = nn.Parameter(torch.ones(1, out_channels, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(out_channels, height, width)) if bias else None
+        self.fused_slope: Optional[float] = None  # set by make_conv_trans when a LeakyReLU follows the layer
+        nn.init.kaiming_uniform_(self.weight_v, a=math.sqrt(5))
+        with torch.no_grad():
+            self.weight_g.fill_(float(self.weight_v.norm()))  # weight == weight_v at init (layers.py:236-242)
+
+    @property
+    def weight(self):
+        return self.weight_g * self.weight_v / self.weight_v.norm()
+
+    def forward(self, input, slope: Optional[float] = None):
+        """`slope` (or `fused_slope`) fuses the LeakyReLU that follows the layer into the same kernel."""
+        slope = self.fused_slope if slope is None else slope
+        return _Deconv4x4s2WNUB.apply(input, self.weight_v, self.weight_g, self.bias, slope)
+
+
+class LinearWN(nn.Module):
+    """nn.Linear with the reference's weight norm (layers.py:468): weight_g [out,1], weight_v [out,in]."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.weight_v = nn.Parameter(torch.empty(out_features, in_features))
+        self.weight_g = nn.Parameter(torch.ones(out_features, 1))
+        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+        nn.init.kaiming_uniform_(self.weight_v, a=math.sqrt(5))
+        with torch.no_grad():
+            self.weight_g.fill_(float(self.weight_v.norm()))
+
+    @property
+    def weight(self):
+        return self.weight_g * self.weight_v / self.weight_v.norm()
+
+    def forward(self, input):
+        return F.linear(input, self.weight, self.bias)  # plain library GEMM (cuBLAS)
+
+
+class FusedLeakyReLU(nn.Identity):
+    """Placeholder for the LeakyReLU that the preceding ConvTranspose2dWNUB already applied in its epilogue; it keeps
+    the Sequential indices (and therefore the checkpoint key names) identical to the reference's [layer, act] lists."""
+
+
+def make_conv_trans(n_in, n_out, fs, stride, pad, mode, act=None, ub=None, bias=True):
+    """layers.py:27-47 with trans=True, ub=(H,W).  Returns [layer] or [layer, act] like the reference; a LeakyReLU is
+    executed inside the layer's kernel and replaced by a parameter-free placeholder at the same list position."""
+    assert mode == "wn" and ub is not None
+    layer = ConvTranspose2dWNUB(n_in, n_out, ub[0], ub[1], fs, stride, pad, bias=bias)
+    if act is None:
+        return [layer]
+    if isinstance(act, nn.LeakyReLU):
+        layer.fused_slope = float(act.negative_slope)
+        return [layer, FusedLeakyReLU()]
+    return [layer, act]
+
+
+def make_linear(n_in, n_out, mode, act=None, bias=True):
+    assert mode == "wn"
+    layers = [LinearWN(n_in, n_out, bias=bias)]
+    if act is not None:
+        layers.append(act)
+    return layers

@@ -166,6 +166,38 @@ int gb_mvp_raymarch_bwd(int N, int H, int W, int K, const float* raypos, const f
                         float* grad_primrot, float* grad_primscale, float* grad_tplate, float* grad_warp, int algo,
                         float fadescale, float fadeexp, int blocksizex, int blocksizey, void* stream);
 
+/* ---------------------------------------------------------------- RGCA decoder heads (row R2) */
+
+/* replaces the eager PyTorch block ca_code/models/rgca.py:506-546 (Gaussian heads, SH diffuse, reflection
+ * direction); there is no native boundary in the reference, the Python mirror is goliath_b200.rgca_heads.
+ * f_vnocond [B,125,G], f_vcond [B,4,G], postex / tn [B,3,G] planes (G = H*W), albedo [G,3], light_sh [B,3,81],
+ * campos [B,3].  Outputs [B,G,3] except primqvec [B,G,4] and opacity / sigma / spec_vis [B,G]; shsum [B,G,3] is
+ * saved for the backward. */
+int gb_rgca_heads_fwd(int B, int G, const float* f_vnocond, const float* f_vcond, const float* postex, const float* tn,
+                      const float* albedo, const float* light_sh, const float* campos, float scale_lo, float scale_hi,
+                      float* primpos, float* primqvec, float* primscale, float* primscale_preclip, float* opacity,
+                      float* sigma, float* spec_vis, float* spec_dnml, float* spec_nml, float* diff_color,
+                      float* ref_dirs, float* primnmlbase, float* shsum, void* stream);
+
+/* backward of the above; upstream gradients may be NULL; g_albedo is [B,G,3] (summed over B by the caller). */
+int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* f_vcond, const float* postex, const float* tn,
+                      const float* albedo, const float* light_sh, const float* campos, float scale_lo, float scale_hi,
+                      const float* shsum, const float* g_primpos, const float* g_primqvec, const float* g_primscale,
+                      const float* g_primscale_preclip, const float* g_opacity, const float* g_sigma,
+                      const float* g_spec_vis, const float* g_spec_dnml, const float* g_spec_nml,
+                      const float* g_diff_color, const float* g_ref_dirs, const float* g_primnmlbase, float* g_f_vnocond,
+                      float* g_f_vcond, float* g_postex, float* g_tn, float* g_albedo, void* stream);
+
+/* ---------------------------------------------------------------- decoder layers (rows R1 / R8) */
+
+/* replaces conv_transpose2d + untied-bias add (ca_code/nn/layers.py:380-396) + the LeakyReLU that follows it in
+ * make_conv_trans (layers.py:27-47) for k=4, s=2, p=1, with the weight-norm scale folded in:
+ * out = act(scale[co] * convT(x, v) + bias).  x [B,Cin,Hi,Wi], v [Cin,Cout,4,4], scale [Cout] = g / ||v||_F,
+ * bias [Cout,2Hi,2Wi] or NULL, out [B,Cout,2Hi,2Wi]; apply_act != 0 applies LeakyReLU(slope). */
+int gb_deconv4x4s2_wnub_fwd(int B, int Cin, int Cout, int Hi, int Wi, const float* x, const float* v,
+                            const float* scale, const float* bias, float slope, int apply_act, float* out,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
