@@ -124,3 +124,197 @@ GB_API int gb_deconv4x4s2_wnub_fwd(int B, int Cin, int Cout, int Hi, int Wi, con
   GB_CHECK_LAUNCH();
   return 0;
 }
+
+// =====================================================================================================
+// Backward (training): three kernels, all hand-written (no cuDNN):
+//   1. deconv_act_bwd_kernel : gz = gout * act'(out)  and  g_bias = sum_b gz      (element-wise, HBM)
+//   2. deconv4x4s2_bwd_data_kernel   : gx[ci,y,x] = sum_co scale[co] sum_{ky,kx} gz[co,2y-1+ky,2x-1+kx] v[ci,co,ky,kx]
+//   3. deconv4x4s2_bwd_weight_kernel : gw[ci,co,ky,kx] = sum_{b,y,x} x[ci,y,x] gz[co,2y-1+ky,2x-1+kx]
+// (gw is the gradient of the EFFECTIVE weight divided by nothing: the weight-norm chain rule on the tiny
+//  [Cin,Cout,4,4] tensors is finished by the caller.)
+namespace {
+
+__global__ void __launch_bounds__(256) deconv_act_bwd_kernel(int B, long long per_item /* Cout*Ho*Wo */,
+                                                             const float* __restrict__ gout,
+                                                             const float* __restrict__ out, float slope, int apply_act,
+                                                             float* __restrict__ gz, float* __restrict__ gbias) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_item) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t o = (size_t)b * per_item + i;
+    float g = gout[o];
+    if (apply_act) g = out[o] > 0.f ? g : g * slope;
+    gz[o] = g;
+    acc += g;
+  }
+  if (gbias) gbias[i] = acc;
+}
+
+constexpr int BD_T = 16;          // input pixels per CTA edge
+constexpr int BD_CO = 8;          // output channels staged per step
+constexpr int BD_CI = 8;          // input channels per CTA
+constexpr int BD_G = 2 * BD_T + 2;  // gz tile edge (34)
+
+__global__ void __launch_bounds__(BD_T* BD_T) deconv4x4s2_bwd_data_kernel(
+    int Cin, int Cout, int Hi, int Wi, const float* __restrict__ gz /* [B,Cout,2Hi,2Wi] */,
+    const float* __restrict__ v, const float* __restrict__ scale, float* __restrict__ gx /* [B,Cin,Hi,Wi] */) {
+  __shared__ float s_g[BD_CO][BD_G][BD_G + 1];
+  __shared__ __align__(16) float s_w[BD_CO][BD_CI][16];
+  const int tiles_x = (Wi + BD_T - 1) / BD_T;
+  const int ty0 = (blockIdx.x / tiles_x) * BD_T, tx0 = (blockIdx.x % tiles_x) * BD_T;
+  const int ci0 = blockIdx.y * BD_CI;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x, py = tid / BD_T, px = tid % BD_T;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const float* gzb = gz + (size_t)b * Cout * Ho * Wo;
+  float acc[BD_CI];
+#pragma unroll
+  for (int c = 0; c < BD_CI; ++c) acc[c] = 0.f;
+  for (int co0 = 0; co0 < Cout; co0 += BD_CO) {
+    __syncthreads();
+    // gz tile: rows 2*ty0-1 .. 2*ty0+2*BD_T, i.e. BD_G rows
+    for (int i = tid; i < BD_CO * BD_G * BD_G; i += BD_T * BD_T) {
+      const int co = i / (BD_G * BD_G), r = (i / BD_G) % BD_G, c = i % BD_G;
+      const int Y = 2 * ty0 - 1 + r, X = 2 * tx0 - 1 + c;
+      float val = 0.f;
+      if (co0 + co < Cout && Y >= 0 && Y < Ho && X >= 0 && X < Wo) val = gzb[((size_t)(co0 + co) * Ho + Y) * Wo + X];
+      s_g[co][r][c] = val;
+    }
+    for (int i = tid; i < BD_CO * BD_CI * 16; i += BD_T * BD_T) {
+      const int co = i / (BD_CI * 16), ci = (i / 16) % BD_CI, k = i % 16;
+      float val = 0.f;
+      if (co0 + co < Cout && ci0 + ci < Cin) val = v[((size_t)(ci0 + ci) * Cout + (co0 + co)) * 16 + k] * scale[co0 + co];
+      s_w[co][ci][k] = val;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int co = 0; co < BD_CO; ++co) {
+      float g[16];  // 4x4 window: rows 2*py .. 2*py+3 of the tile (= 2y-1 .. 2y+2), cols 2*px .. 2*px+3
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) g[ky * 4 + kx] = s_g[co][2 * py + ky][2 * px + kx];
+#pragma unroll
+      for (int ci = 0; ci < BD_CI; ++ci) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[co][ci][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[co][ci][4]);
+        const float4 w2 = *reinterpret_cast<const float4*>(&s_w[co][ci][8]);
+        const float4 w3 = *reinterpret_cast<const float4*>(&s_w[co][ci][12]);
+        acc[ci] += g[0] * w0.x + g[1] * w0.y + g[2] * w0.z + g[3] * w0.w + g[4] * w1.x + g[5] * w1.y + g[6] * w1.z +
+                   g[7] * w1.w + g[8] * w2.x + g[9] * w2.y + g[10] * w2.z + g[11] * w2.w + g[12] * w3.x + g[13] * w3.y +
+                   g[14] * w3.z + g[15] * w3.w;
+      }
+    }
+  }
+  const int y = ty0 + py, x = tx0 + px;
+  if (y >= Hi || x >= Wi) return;
+#pragma unroll
+  for (int ci = 0; ci < BD_CI; ++ci)
+    if (ci0 + ci < Cin) gx[(((size_t)b * Cin + ci0 + ci) * Hi + y) * Wi + x] = acc[ci];
+}
+
+// weight gradient: warp tile = 16 ci x 8 co (lane: cig = lane>>3 -> 4 ci, co = lane&7 -> 16 taps), 8 warps split the
+// pixels of each staged 16x16 input tile; every CTA walks many tiles and flushes its sums once.
+constexpr int BW_TX = 16, BW_TY = 8;            // input tile staged per step: 8 rows x 16 columns = 128 pixels
+constexpr int BW_CI = 16;
+constexpr int BW_CO = 8;
+constexpr int BW_GX = 2 * BW_TX + 2, BW_GY = 2 * BW_TY + 2;
+
+__global__ void __launch_bounds__(256) deconv4x4s2_bwd_weight_kernel(
+    int B, int Cin, int Cout, int Hi, int Wi, const float* __restrict__ x, const float* __restrict__ gz,
+    float* __restrict__ gw /* [Cin,Cout,4,4], accumulated */) {
+  __shared__ float s_x[BW_CI][BW_TX * BW_TY];
+  __shared__ float s_g[BW_CO][BW_GY][BW_GX + 1];
+  const int ci0 = blockIdx.y * BW_CI, co0 = blockIdx.z * BW_CO;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cig = lane >> 3, col = lane & 7;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const int tiles_x = (Wi + BW_TX - 1) / BW_TX, tiles_y = (Hi + BW_TY - 1) / BW_TY;
+  const int total = B * tiles_x * tiles_y;
+  float acc[4][16];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[a][k] = 0.f;
+
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int b = t / (tiles_x * tiles_y), tt = t % (tiles_x * tiles_y);
+    const int ty0 = (tt / tiles_x) * BW_TY, tx0 = (tt % tiles_x) * BW_TX;
+    __syncthreads();
+    for (int i = tid; i < BW_CI * BW_TX * BW_TY; i += 256) {
+      const int ci = i / (BW_TX * BW_TY), p = i % (BW_TX * BW_TY);
+      const int yy = ty0 + p / BW_TX, xx = tx0 + p % BW_TX;
+      float val = 0.f;
+      if (ci0 + ci < Cin && yy < Hi && xx < Wi) val = x[(((size_t)b * Cin + ci0 + ci) * Hi + yy) * Wi + xx];
+      s_x[ci][p] = val;
+    }
+    for (int i = tid; i < BW_CO * BW_GY * BW_GX; i += 256) {
+      const int co = i / (BW_GY * BW_GX), r = (i / BW_GX) % BW_GY, c = i % BW_GX;
+      const int Y = 2 * ty0 - 1 + r, X = 2 * tx0 - 1 + c;
+      float val = 0.f;
+      if (co0 + co < Cout && Y >= 0 && Y < Ho && X >= 0 && X < Wo) val = gz[(((size_t)b * Cout + co0 + co) * Ho + Y) * Wo + X];
+      s_g[co][r][c] = val;
+    }
+    __syncthreads();
+    // this warp's 16 pixels of the tile (one row)
+    for (int pp = 0; pp < (BW_TX * BW_TY) / 8; ++pp) {
+      const int p = warp * ((BW_TX * BW_TY) / 8) + pp, py = p / BW_TX, px = p % BW_TX;
+      float xv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xv[a] = s_x[cig * 4 + a][p];
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          const float g = s_g[col][2 * py + ky][2 * px + kx];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[a][ky * 4 + kx] += xv[a] * g;
+        }
+    }
+  }
+  // flush: one RED per (ci, co, tap) per warp
+  const int co = co0 + col;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int ci = ci0 + cig * 4 + a;
+    if (ci < Cin && co < Cout) {
+#pragma unroll
+      for (int k = 0; k < 16; k += 4)
+        gb::red_add_v4(gw + ((size_t)ci * Cout + co) * 16 + k, acc[a][k], acc[a][k + 1], acc[a][k + 2], acc[a][k + 3]);
+    }
+  }
+}
+
+}  // namespace
+
+// Backward of gb_deconv4x4s2_wnub_fwd.  gz [B,Cout,2Hi,2Wi] is scratch (pre-activation gradient), g_bias
+// [Cout,2Hi,2Wi] or NULL, gx [B,Cin,Hi,Wi] or NULL, gw [Cin,Cout,4,4] is ACCUMULATED into (caller zeroes it) and is the
+// gradient w.r.t. the un-normalised direction tensor v at unit scale (d out / d (scale*v) contracted with v's slot):
+// gw[ci,co,k] = sum x * gz; the caller applies the weight-norm chain rule.
+GB_API int gb_deconv4x4s2_wnub_bwd(int B, int Cin, int Cout, int Hi, int Wi, const float* x, const float* v,
+                                   const float* scale, const float* out, const float* gout, float slope, int apply_act,
+                                   float* gz, float* g_bias, float* gx, float* gw, void* stream) {
+  if (B <= 0 || Cin <= 0 || Cout <= 0 || Hi <= 0 || Wi <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long per_item = (long long)Cout * 4 * Hi * Wi;
+  deconv_act_bwd_kernel<<<(unsigned)gb::cdiv64(per_item, 256), 256, 0, s>>>(B, per_item, gout, out, slope, apply_act, gz, g_bias);
+  int launches = 1;
+  if (gx) {
+    dim3 grid(gb::cdiv(Hi, BD_T) * gb::cdiv(Wi, BD_T), gb::cdiv(Cin, BD_CI), B);
+    deconv4x4s2_bwd_data_kernel<<<grid, BD_T * BD_T, 0, s>>>(Cin, Cout, Hi, Wi, gz, v, scale, gx);
+    ++launches;
+  }
+  if (gw) {
+    const int total = B * gb::cdiv(Hi, BW_TY) * gb::cdiv(Wi, BW_TX);
+    const int pairs = gb::cdiv(Cin, BW_CI) * gb::cdiv(Cout, BW_CO);
+    int split = gb::cdiv(gb::kNumSMs * 3, pairs);  // ~3 CTAs per SM in total
+    split = max(1, min(split, total));
+    dim3 grid(split, gb::cdiv(Cin, BW_CI), gb::cdiv(Cout, BW_CO));
+    deconv4x4s2_bwd_weight_kernel<<<grid, 256, 0, s>>>(B, Cin, Cout, Hi, Wi, x, gz, gw);
+    ++launches;
+  }
+  gb::count_launches(launches);
+  GB_CHECK_LAUNCH();
+  return 0;
+}

@@ -4,8 +4,8 @@ checkpoints load (`weight_v`, `weight_g`, `bias`): `ConvTranspose2dWNUB`, `Linea
 (layers.py:200-204,468-480):  w = g * v / ||v||_F.
 
 The stride-2 4x4 transposed convolution + untied bias + LeakyReLU runs as ONE hand-written sm_100a kernel in the
-forward (csrc/deconv_wnub.cu).  Round-1 status: its backward and LinearWN still go through PyTorch library calls
-(cuDNN / cuBLAS) — listed as next in DESIGN.md §7, not claimed as hand-written."""
+forward, and its backward as three more (activation/bias gradient, data gradient, weight gradient) — no cuDNN
+(csrc/deconv_wnub.cu).  Round-1 status: fp32 SIMT kernels; LinearWN is a plain library GEMM (cuBLAS via F.linear)."""
 import math
 from typing import Optional
 
@@ -45,17 +45,26 @@ class _Deconv4x4s2WNUB(Function):
 
     @staticmethod
     def backward(ctx, gout):
-        # library backward (cuDNN) — see module docstring
         x, v, g, out = ctx.saved_tensors
-        gz = gout if ctx.slope is None else gout * torch.where(out > 0, 1.0, float(ctx.slope))
+        B, Cin, Hi, Wi = x.shape
+        Cout = v.shape[1]
+        dev = x.device
+        gout = gout.contiguous()
         vnorm = v.norm()
+        scale = (g.reshape(-1) / vnorm).contiguous()
+        gz = torch.empty_like(out)                       # scratch: gradient w.r.t. the pre-activation
+        gb = torch.empty(Cout, 2 * Hi, 2 * Wi, device=dev, dtype=torch.float32) if ctx.has_bias else None
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.zeros_like(v)                         # d L / d (effective weight), accumulated by the kernel
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gb_deconv4x4s2_wnub_bwd(
+                B, Cin, Cout, Hi, Wi, _lib.ptr(x), _lib.ptr(v), _lib.ptr(scale), _lib.ptr(out), _lib.ptr(gout),
+                float(ctx.slope if ctx.slope is not None else 1.0), int(ctx.slope is not None), _lib.ptr(gz), _lib.ptr(gb),
+                _lib.ptr(gx), _lib.ptr(gw), _lib.stream_ptr(dev)), "deconv4x4s2_wnub_bwd")
+        # weight-norm chain rule on the small [Cin,Cout,4,4] tensors:  w = g * v / n,  n = ||v||_F
         w = g * v / vnorm
-        gx = F.conv2d(gz, w, stride=2, padding=1) if ctx.needs_input_grad[0] else None
-        gw = torch.nn.grad.conv2d_weight(gz, w.shape, x, stride=2, padding=1)
-        # w = g * v / n, n = ||v||_F :  dL/dg_co = <gw_co, v_co> / n ;  dL/dv = g * gw / n - <gw, w> * v / n^2
         gg = (gw * v).sum(dim=(0, 2, 3), keepdim=True) / vnorm
         gv = g * gw / vnorm - (gw * w).sum() * v / (vnorm * vnorm)
-        gb = gz.sum(0) if ctx.has_bias else None
         return gx, gv, gg.view_as(g), gb, None
 
 

@@ -198,6 +198,13 @@ int gb_deconv4x4s2_wnub_fwd(int B, int Cin, int Cout, int Hi, int Wi, const floa
                             const float* scale, const float* bias, float slope, int apply_act, float* out,
                             void* stream);
 
+/* backward of the above (replaces the cuDNN backward-data / backward-filter calls autograd makes for
+ * layers.py:380-396).  gz [B,Cout,2Hi,2Wi] scratch; g_bias [Cout,2Hi,2Wi] or NULL; gx [B,Cin,Hi,Wi] or NULL;
+ * gw [Cin,Cout,4,4] = dL/d(effective weight), ACCUMULATED (caller zeroes it and applies the weight-norm chain rule). */
+int gb_deconv4x4s2_wnub_bwd(int B, int Cin, int Cout, int Hi, int Wi, const float* x, const float* v,
+                            const float* scale, const float* out, const float* gout, float slope, int apply_act,
+                            float* gz, float* g_bias, float* gx, float* gw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
