@@ -39,6 +39,10 @@ def parse():
     ap.add_argument("--gaussians", type=int, default=300_000)
     ap.add_argument("--lights", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mvp-density", type=float, default=2000.0, help="template alpha scale of the --ext-compare MVP scene")
+    ap.add_argument("--ext-compare", action="store_true",
+                    help="time the reference's own extensions rebuilt for sm_100a (oracle/_ref) against ours: SG shade, "
+                         "raydirs, MVP raymarch (BASELINE config 4 shape); prints its own JSON line")
     return ap.parse_args()
 
 
@@ -397,9 +401,110 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ extension-level comparison
+def run_ext_compare(args):
+    """Reference arm at the EXTENSION level: the reference's sgutilslib / utilslib / mvpraymarchlib
+    rebuilt for sm_100a by oracle/build_ref.py versus ours, same tensors, CUDA-event timing, L2 flushed between reps.
+    gsplat cannot be compared: it is absent from the reference tree and from this image."""
+    import importlib.util
+
+    from goliath_b200 import mvpraymarchlib, sgutilslib, synthetic, utilslib
+    from goliath_b200.mvpraymarch import _fixedorder_topology
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def ref_mod(name):
+        so = os.path.join(ROOT, "oracle", "_ref", name + ".so")
+        if not os.path.exists(so):
+            return None
+        spec = importlib.util.spec_from_file_location(name, so)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    def timeit(fn, reps=10, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush_buf.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    res = {}
+    # --- SG shade, G = 300k, L = 32
+    G, L = args.gaussians, args.lights
+    sh = synthetic.shade_inputs(G)
+    li = synthetic.lights(L)
+    sc = synthetic.head_gaussians(G)
+    a = [torch.nn.functional.normalize(sh["lobe_dirs"], dim=-1).to(dev).contiguous(), sh["lobe_sigmas"].to(dev),
+         li["light_intensity"].to(dev), li["light_pos"].to(dev), sc["means3d"][None].to(dev).contiguous(), li["n_lights"].to(dev)]
+    out = torch.empty(1, G, 3, device=dev)
+    g = torch.ones(1, G, 3, device=dev)
+    gd, gs = torch.zeros(1, G, 3, device=dev), torch.zeros(1, G, device=dev)
+    for tag, lib in (("ours", sgutilslib), ("reference", ref_mod("sgutilslib"))):
+        if lib is None:
+            continue
+        res["sg_fwd_ms_" + tag] = timeit(lambda: lib.evaluate_gaussian_fwd(*a, out, 0))
+        res["sg_bwd_ms_" + tag] = timeit(lambda: lib.evaluate_gaussian_bwd(*a, g, gd, gs, None, 0))
+    # --- MVP: BASELINE config 4 shape (4096 primitives of 8x16x16 voxels, 1024x667 rays, dt = 1/2000), N views
+    N = 2
+    s = synthetic.mvp_scene(N=N, side=64, T=(8, 16, 16), img_h=H, img_w=W, density=args.mvp_density)
+    t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s.items()}
+    raypos, raydir, tmm = (torch.empty(N, H, W, 3, device=dev), torch.empty(N, H, W, 3, device=dev),
+                           torch.empty(N, H, W, 2, device=dev))
+    for tag, lib in (("ours", utilslib), ("reference", ref_mod("utilslib"))):
+        if lib is None:
+            continue
+        res["raydirs_ms_" + tag] = timeit(lambda: lib.compute_raydirs_forward(t["viewpos"], t["viewrot"], t["focal"], t["princpt"],
+                                                                               None, W, H, 1.0, raypos, raydir, tmm))
+    K = t["primpos"].shape[1]
+    sid, ch, par = _fixedorder_topology(N, K, dev)
+    aabb = torch.empty(N, 2 * K - 1, 2, 3, device=dev)
+    step = 1.0 / 2000.0
+    rgba = torch.empty(N, H, W, 4, device=dev)
+    sat = torch.empty(N, H, W, 3, device=dev)
+    grgba = torch.ones(N, H, W, 4, device=dev)
+    gp, gr, gsc = torch.zeros_like(t["primpos"]), torch.zeros_like(t["primrot"]), torch.zeros_like(t["primscale"])
+    gt = torch.zeros_like(t["template"])
+    for tag, lib in (("ours", mvpraymarchlib), ("reference", ref_mod("mvpraymarchlib"))):
+        if lib is None:
+            continue
+        res["aabb_ms_" + tag] = timeit(lambda: lib.compute_aabb(t["primpos"], t["primrot"], t["primscale"], sid, ch, par, aabb, 0))
+
+        def fwd():
+            sat.fill_(-1.0)
+            lib.raymarch_forward(raypos, raydir, step, tmm, sid, ch, aabb, t["primpos"], t["primrot"], t["primscale"],
+                                 t["template"], None, rgba, sat, None, None, 0, False, 512, True, True, 8.0, 8.0, 0, 0.99, 3, 8, 16)
+
+        def bwd():
+            lib.raymarch_backward(raypos, raydir, step, tmm, sid, ch, aabb, t["primpos"], gp, t["primrot"], gr,
+                                  t["primscale"], gsc, t["template"], gt, None, None, rgba, grgba, sat, None, 0, False, 512,
+                                  True, True, 8.0, 8.0, 0, 0.99, 3, 8, 16)
+
+        res["raymarch_fwd_ms_" + tag] = timeit(fwd, reps=5, warm=1)
+        res["raymarch_bwd_ms_" + tag] = timeit(bwd, reps=5, warm=1)
+        res["raymarch_alpha_mean_" + tag] = float(rgba[..., 3].mean())
+    mp = N * H * W / 1e6
+    for tag in ("ours", "reference"):
+        if "raymarch_fwd_ms_" + tag in res:
+            res["raymarch_mp_per_s_fwd_bwd_" + tag] = mp / ((res["raymarch_fwd_ms_" + tag] + res["raymarch_bwd_ms_" + tag]) / 1e3)
+    print(json.dumps({"ext_compare": res, "config": {"sg": {"G": G, "L": L}, "mvp": {"N": N, "K": K, "template": [8, 16, 16],
+                      "rays": [H, W], "stepsize": step, "algo": 0, "density": args.mvp_density}}}))
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.ext_compare:
+        run_ext_compare(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "gb_rasterize_bwd": (_i, [_i, _i, _i, _i] + [_vp] * 15 + [_vp]),
     "gb_pack_records": (_i, [_i64, _i] + [_vp] * 6 + [_vp]),
     "gb_tile_order": (_i, [_i, _vp, _vp, _vp]),
+    "gb_pack_records_fused": (_i, [_i64] + [_vp] * 8 + [_vp]),
+    "gb_splat_grad_unpack": (_i, [_i] + [_vp] * 8 + [_vp]),
     "gb_rasterize_packed_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_packed_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
     "gb_compute_raydirs_fwd": (_i, [_i, _i, _i] + [_vp] * 5 + [_f] + [_vp] * 3 + [_vp]),

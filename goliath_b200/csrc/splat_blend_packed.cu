@@ -99,6 +99,58 @@ __global__ void __launch_bounds__(256) pack_records_kernel(long long n, const in
   rec[3 * i + 2] = make_float4(c0, c1, c2, c3);
 }
 
+// Fused-render variant of the packing: the record's opacity is opacity * compensation and its 4th colour channel is
+// the view-space depth, i.e. exactly what ca_code/utils/render_gsplat.py:72 and :97 feed to the two rasterise calls,
+// without materialising those tensors.
+__global__ void __launch_bounds__(256) pack_records_fused_kernel(long long n, const int* __restrict__ gids_sorted,
+                                                                 const float2* __restrict__ xys,
+                                                                 const float* __restrict__ conics,
+                                                                 const float* __restrict__ colors3,
+                                                                 const float* __restrict__ depths,
+                                                                 const float* __restrict__ opacity,
+                                                                 const float* __restrict__ comp, float4* __restrict__ rec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = gids_sorted[i];
+  const float2 xy = xys[g];
+  const float A = conics[3 * g], B = conics[3 * g + 1], Cc = conics[3 * g + 2];
+  const float o = opacity[g] * comp[g];
+  float ex, ey;
+  const float bb = B * B;
+  const float det = fmaf(A, Cc, -bb) + fmaf(-B, B, bb);
+  const float s = __logf(255.f * o) + 1e-3f;
+  if (!(o >= 0.f) || !(det > 0.f) || !(A > 0.f) || !(Cc > 0.f)) {
+    ex = ey = 3.0e38f;
+  } else if (s <= 0.f) {
+    ex = ey = -1.f;
+  } else {
+    const float inv = 1.f / det;
+    ex = sqrtf(2.f * s * Cc * inv) * 1.0005f + 1e-3f;
+    ey = sqrtf(2.f * s * A * inv) * 1.0005f + 1e-3f;
+  }
+  rec[3 * i + 0] = make_float4(xy.x, xy.y, ex, ey);
+  rec[3 * i + 1] = make_float4(A, B, Cc, o);
+  rec[3 * i + 2] = make_float4(colors3[3 * g], colors3[3 * g + 1], colors3[3 * g + 2], depths[g]);
+}
+
+// Backward glue of the fused render: split the blend's per-Gaussian gradients back into the tensors the projection
+// backward and the caller expect (product rule of opacity * compensation, depth = 4th colour channel).
+__global__ void __launch_bounds__(256) splat_grad_unpack_kernel(int G, const float4* __restrict__ v_colors4,
+                                                                const float* __restrict__ v_opac_eff,
+                                                                const float* __restrict__ opacity,
+                                                                const float* __restrict__ comp, float* __restrict__ v_colors3,
+                                                                float* __restrict__ v_opacity, float* __restrict__ v_comp,
+                                                                float* __restrict__ v_depth) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float4 c = v_colors4[g];
+  const float e = v_opac_eff[g];
+  v_colors3[3 * g] = c.x; v_colors3[3 * g + 1] = c.y; v_colors3[3 * g + 2] = c.z;
+  v_depth[g] = c.w;
+  v_opacity[g] = e * comp[g];
+  v_comp[g] = e * opacity[g];
+}
+
 // ------------------------------------------------------------------ LPT tile order (single CTA)
 // order[] = tile ids sorted by descending list length (bucketed, stable); any tile count.
 __global__ void __launch_bounds__(1024) tile_order_kernel(int T, const int2* __restrict__ tile_bins,
@@ -469,6 +521,30 @@ GB_API int gb_pack_records(int64_t n, int channels, const int32_t* gids_sorted, 
     pack_records_kernel<3><<<blocks, 256, 0, s>>>(n, gids_sorted, (const float2*)xys, conics, colors, opacities, (float4*)records);
   else
     pack_records_kernel<4><<<blocks, 256, 0, s>>>(n, gids_sorted, (const float2*)xys, conics, colors, opacities, (float4*)records);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Fused-render packing: records carry opacity*compensation and (rgb, depth); see pack_records_fused_kernel.
+GB_API int gb_pack_records_fused(int64_t n, const int32_t* gids_sorted, const float* xys, const float* conics,
+                                 const float* colors3, const float* depths, const float* opacity,
+                                 const float* compensation, float* records, void* stream) {
+  if (n <= 0) return 0;
+  pack_records_fused_kernel<<<(unsigned)gb::cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, gids_sorted, (const float2*)xys, conics, colors3, depths, opacity, compensation, (float4*)records);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Backward glue of the fused render (all outputs overwritten): v_colors3 [G,3], v_opacity [G], v_comp [G], v_depth [G].
+GB_API int gb_splat_grad_unpack(int G, const float* v_colors4, const float* v_opac_eff, const float* opacity,
+                                const float* compensation, float* v_colors3, float* v_opacity, float* v_comp,
+                                float* v_depth, void* stream) {
+  if (G <= 0) return 0;
+  splat_grad_unpack_kernel<<<gb::cdiv(G, 256), 256, 0, (cudaStream_t)stream>>>(
+      G, (const float4*)v_colors4, v_opac_eff, opacity, compensation, v_colors3, v_opacity, v_comp, v_depth);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;

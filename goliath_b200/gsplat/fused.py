@@ -1,0 +1,107 @@
+"""render_fused — project -> bin/sort -> pack -> one 4-channel blend, as a single autograd node.
+
+Equivalent, output for output, to the reference's call sequence in ca_code/utils/render_gsplat.py:41-106
+(project_gaussians, rasterize rgb with opacity * compensation, rasterize depth-as-colour) — same kernels, same
+arithmetic — but without the tensors that sequence materialises between the calls (`opacity * compensation[:, None]`,
+`depths[:, None].expand(-1, 3)`, the second binning) and without their autograd glue in the backward."""
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from .utils import _tile_bounds, bin_and_sort_gaussians, compute_cumulative_intersects
+
+
+class _RenderFused(Function):
+    @staticmethod
+    def forward(ctx, means3d, scales, quats, opacity, colors, viewmat, background, glob_scale, fx, fy, cx, cy, img_height,
+                img_width, clip_thresh):
+        ins = [t.contiguous() for t in (means3d, scales, quats, opacity, colors, viewmat, background)]
+        for t, n in zip(ins, ("means3d", "scales", "quats", "opacity", "colors", "viewmat", "background")):
+            _lib.check_input(t, n)
+        means3d, scales, quats, opacity, colors, viewmat, background = ins
+        G = means3d.size(0)
+        dev = means3d.device
+        L = _lib.lib()
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        cov3d, xys, depths = torch.empty(G, 6, **f32), torch.empty(G, 2, **f32), torch.empty(G, **f32)
+        radii, conics, comp = torch.empty(G, **i32), torch.empty(G, 3, **f32), torch.empty(G, **f32)
+        num_tiles_hit = torch.empty(G, **i32)
+        H, W, BW = int(img_height), int(img_width), 16
+        out4 = torch.empty(H, W, 4, **f32)
+        final_Ts = torch.empty(H, W, **f32)
+        final_idx = torch.empty(H, W, **i32)
+        bg4 = torch.cat([background, background[:1]])
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(L.gb_project_gaussians_fwd(
+                G, _lib.ptr(means3d), _lib.ptr(scales), float(glob_scale), _lib.ptr(quats), _lib.ptr(viewmat), float(fx),
+                float(fy), float(cx), float(cy), H, W, BW, float(clip_thresh), _lib.ptr(cov3d), _lib.ptr(xys),
+                _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics), _lib.ptr(comp), _lib.ptr(num_tiles_hit), st),
+                "project_gaussians_forward")
+            num_intersects, cum = compute_cumulative_intersects(num_tiles_hit)
+            tb = _tile_bounds(H, W, BW)
+            if num_intersects < 1:
+                # reference behaviour with nothing to draw (gsplat 0.1.11 rasterize.py): background, final_Ts = 0
+                out4.copy_(bg4.expand(H, W, 4))
+                final_Ts.zero_()
+                final_idx.zero_()
+                gids = bins = order = records = torch.empty(0, **i32)
+            else:
+                _, _, _, gids, bins = bin_and_sort_gaussians(G, num_intersects, xys, depths, radii, cum, tb, BW)
+                T = tb[0] * tb[1]
+                order = torch.empty(T, **i32)
+                records = torch.empty(num_intersects, 12, **f32)
+                _lib.check(L.gb_tile_order(T, _lib.ptr(bins), _lib.ptr(order), st), "tile_order")
+                _lib.check(L.gb_pack_records_fused(num_intersects, _lib.ptr(gids), _lib.ptr(xys), _lib.ptr(conics),
+                                                   _lib.ptr(colors), _lib.ptr(depths), _lib.ptr(opacity), _lib.ptr(comp),
+                                                   _lib.ptr(records), st), "pack_records_fused")
+                _lib.check(L.gb_rasterize_packed_fwd(H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records),
+                                                     _lib.ptr(bg4), _lib.ptr(out4), _lib.ptr(final_Ts),
+                                                     _lib.ptr(final_idx), st), "rasterize_packed_forward")
+        ctx.save_for_backward(means3d, scales, quats, opacity, viewmat, bg4, cov3d, radii, conics, comp, gids, bins, order,
+                              records, final_Ts, final_idx)
+        ctx.meta = (G, H, W, num_intersects, float(glob_scale), float(fx), float(fy))
+        ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)
+        return out4, 1 - final_Ts, radii
+
+    @staticmethod
+    def backward(ctx, v_out4, v_alpha, _v_radii):
+        (means3d, scales, quats, opacity, viewmat, bg4, cov3d, radii, conics, comp, gids, bins, order, records, final_Ts,
+         final_idx) = ctx.saved_tensors
+        G, H, W, num_intersects, glob_scale, fx, fy = ctx.meta
+        dev = means3d.device
+        L = _lib.lib()
+        f32 = dict(device=dev, dtype=torch.float32)
+        v_out4 = torch.zeros(H, W, 4, **f32) if v_out4 is None else v_out4.contiguous()
+        v_alpha = torch.zeros(H, W, **f32) if v_alpha is None else v_alpha.contiguous()
+        v_xy, v_conic = torch.zeros(G, 2, **f32), torch.zeros(G, 3, **f32)
+        v_col4, v_opeff = torch.zeros(G, 4, **f32), torch.zeros(G, **f32)
+        v_colors, v_opacity = torch.empty(G, 3, **f32), torch.empty(G, 1, **f32)
+        v_comp, v_depth = torch.empty(G, **f32), torch.empty(G, **f32)
+        g_cov2d, g_cov3d = torch.empty(G, 3, **f32), torch.empty(G, 6, **f32)
+        g_mean, g_scale, g_quat = torch.empty(G, 3, **f32), torch.empty(G, 3, **f32), torch.empty(G, 4, **f32)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            if num_intersects >= 1:
+                _lib.check(L.gb_rasterize_packed_bwd(
+                    H, W, 4, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4),
+                    _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out4), _lib.ptr(v_alpha), _lib.ptr(v_xy),
+                    _lib.ptr(v_conic), _lib.ptr(v_col4), _lib.ptr(v_opeff), st), "rasterize_packed_backward")
+            _lib.check(L.gb_splat_grad_unpack(G, _lib.ptr(v_col4), _lib.ptr(v_opeff), _lib.ptr(opacity), _lib.ptr(comp),
+                                              _lib.ptr(v_colors), _lib.ptr(v_opacity), _lib.ptr(v_comp), _lib.ptr(v_depth),
+                                              st), "splat_grad_unpack")
+            _lib.check(L.gb_project_gaussians_bwd(
+                G, _lib.ptr(means3d), _lib.ptr(scales), glob_scale, _lib.ptr(quats), _lib.ptr(viewmat), fx, fy,
+                _lib.ptr(cov3d), _lib.ptr(radii), _lib.ptr(conics), _lib.ptr(comp), _lib.ptr(v_xy), _lib.ptr(v_depth),
+                _lib.ptr(v_conic), _lib.ptr(v_comp), _lib.ptr(g_cov2d), _lib.ptr(g_cov3d), _lib.ptr(g_mean),
+                _lib.ptr(g_scale), _lib.ptr(g_quat), st), "project_gaussians_backward")
+        return (g_mean, g_scale, g_quat, v_opacity, v_colors, None, None, None, None, None, None, None, None, None, None)
+
+
+def render_fused(means3d, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, img_height, img_width, opacity, colors,
+                 background, clip_thresh=0.01):
+    """Returns (out4 [H,W,4] = rgb + depth, alpha [H,W], radii [G] i32).  block_width is 16."""
+    return _RenderFused.apply(means3d, scales, quats, opacity, colors, viewmat, background, glob_scale, fx, fy, cx, cy,
+                              img_height, img_width, clip_thresh)

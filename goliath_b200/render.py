@@ -39,6 +39,16 @@ def render(
     if bg_color is None:
         bg_color = th.zeros(3, device=Rt.device)
 
+    if fused and return_depth and block_width == 16:
+        # one autograd node for project + bin/sort + pack + 4-channel blend (gsplat/fused.py): same kernels and
+        # arithmetic as the branch below, minus the intermediate tensors and their autograd glue
+        from .gsplat.fused import render_fused
+
+        out4, alpha, radii = render_fused(means3D, scales, global_scale, rotations, Rt, fx, fy, cx, cy, cam_img_h,
+                                          cam_img_w, opacity, colors, bg_color, z_near)
+        return {"render": out4[..., :3].permute(2, 0, 1), "final_T": (1.0 - alpha)[None], "alpha": alpha[None],
+                "radii": radii, "depth": out4[..., 3][None]}
+
     xys, depths, radii, conics, compensation, num_tiles_hit, cov3d = project_gaussians(
         means3D, scales, global_scale, rotations, Rt, fx, fy, cx, cy, cam_img_h, cam_img_w, block_width, z_near)
 

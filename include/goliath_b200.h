@@ -110,6 +110,16 @@ int gb_rasterize_bwd(int img_h, int img_w, int block_width, int channels, const 
 int gb_pack_records(int64_t n, int channels, const int32_t* gids_sorted, const float* xys, const float* conics,
                     const float* colors, const float* opacities, float* records, void* stream);
 
+/* fused-render variant: record opacity = opacity*compensation (render_gsplat.py:72), 4th colour = depth (:97) */
+int gb_pack_records_fused(int64_t n, const int32_t* gids_sorted, const float* xys, const float* conics,
+                          const float* colors3, const float* depths, const float* opacity, const float* compensation,
+                          float* records, void* stream);
+
+/* backward glue of the fused render: split v_colors4 / v_opacity_eff into v_colors3, v_opacity, v_comp, v_depth */
+int gb_splat_grad_unpack(int G, const float* v_colors4, const float* v_opac_eff, const float* opacity,
+                         const float* compensation, float* v_colors3, float* v_opacity, float* v_comp, float* v_depth,
+                         void* stream);
+
 /* launch order of the tiles, longest list first: order [T] int32 */
 int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
 

@@ -377,6 +377,18 @@ def test_fused_render_equals_two_pass_and_bin_cache(cuda):
         assert torch.equal(a[k], b[k]), k
     # one binning serves both passes of the two-pass form: only pack + blend are extra
     assert two_pass_launches - fused_launches == 2, (two_pass_launches, fused_launches)
+    # gradients of the single-node fused render == gradients of the two-pass autograd chain (atomics order apart)
+    grads = []
+    for fused in (False, True):
+        leaves = [t[k].clone().requires_grad_() for k in ("means3d", "quats", "scales", "opacity", "colors")]
+        leaves[2] = (t["scales"] * mult).clone().requires_grad_()
+        o = render(s["img_w"], s["img_h"], s["fx"], s["fy"], s["cx"], s["cy"], t["viewmat"], leaves[0], leaves[1],
+                   leaves[2], leaves[3], leaves[4], fused=fused)
+        w = torch.linspace(0.5, 1.5, s["img_h"] * s["img_w"], device=cuda).view(s["img_h"], s["img_w"])
+        ((o["render"] * w).sum() + (o["depth"] * w * 1e-3).sum() + (o["alpha"] * w).sum()).backward()
+        grads.append([t2n(x.grad) for x in leaves])
+    for name, a_, b_ in zip(("means3d", "quats", "scales", "opacity", "colors"), grads[0], grads[1]):
+        assert_close(b_, a_, rtol=1e-4, atol=2e-5 * np.abs(a_).max(), frac=0.999, what="fused vs two-pass grad " + name)
     # cache must miss after an in-place change of an input
     from goliath_b200.gsplat import project_gaussians, rasterize_gaussians
     xys, depths, radii, conics, comp, nth, cov3d = project_gaussians(
