@@ -46,21 +46,34 @@ def parse():
     return ap.parse_args()
 
 
+FIELDS = (("primpos", 3), ("primqvec", 4), ("primscale", 3), ("opacity", 1), ("diff_color", 3), ("lobe_dirs", 3),
+          ("sigma", 0), ("spec_vis", 1))  # width 0 = [G] vector
+
+
 def packed_scene(G):
-    """[G,19] fp32 decoded-Gaussian table (SURVEY.md §8d recipe) on the CPU."""
+    """Flat fp32 buffer of G*19 floats holding the decoded Gaussians FIELD-MAJOR (each field contiguous, as the decoder
+    heads kernel emits them), SURVEY.md §8d recipe, on the CPU.  One buffer = one H2D copy / one broadcast."""
     from goliath_b200 import synthetic
 
     sc = synthetic.head_gaussians(G)
     sh = synthetic.shade_inputs(G)
     g = torch.Generator().manual_seed(synthetic.SEED + 3)
     spec_vis = torch.sigmoid(torch.randn(G, 1, generator=g))
-    return torch.cat([sc["means3d"], sc["quats"], sc["scales"], sc["opacity"], sc["colors"], sh["lobe_dirs"][0],
-                      sh["lobe_sigmas"][0][:, None], spec_vis], 1).contiguous()
+    parts = [sc["means3d"], sc["quats"], sc["scales"], sc["opacity"], sc["colors"], sh["lobe_dirs"][0],
+             sh["lobe_sigmas"][0], spec_vis]
+    return torch.cat([p.reshape(-1) for p in parts]).contiguous()
 
 
-def unpack(p):
-    return dict(primpos=p[:, 0:3], primqvec=p[:, 3:7], primscale=p[:, 7:10], opacity=p[:, 10:11],
-                diff_color=p[:, 11:14], lobe_dirs=p[:, 14:17], sigma=p[:, 17], spec_vis=p[:, 18:19])
+def unpack(flat, G=None):
+    """Contiguous views (no copies) of the field-major buffer; works for torch tensors and numpy arrays."""
+    G = flat.shape[0] // NCOL if G is None else G
+    out, off = {}, 0
+    for name, w in FIELDS:
+        n = G * max(w, 1)
+        v = flat[off:off + n]
+        out[name] = v.reshape(G, w) if w else v
+        off += n
+    return out
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -69,9 +82,9 @@ def gpu_step(packed, cam, li):
     from goliath_b200.render import render_views
     from goliath_b200.sgutils import evaluate_gaussian
 
-    u = unpack(packed)
-    spec = evaluate_gaussian(u["lobe_dirs"][None].contiguous(), u["sigma"][None].contiguous(), li["light_intensity"],
-                             li["light_pos"], u["primpos"][None].contiguous(), li["n_lights"], w_type=0)[0]
+    u = packed  # dict of leaf tensors (contiguous views of the flat buffer)
+    spec = evaluate_gaussian(u["lobe_dirs"][None], u["sigma"][None], li["light_intensity"],
+                             li["light_pos"], u["primpos"][None], li["n_lights"], w_type=0)[0]
     color = (u["diff_color"].clamp(min=0.0) + spec * u["spec_vis"]).clamp(min=0.0)
     preds = dict(primpos=u["primpos"][None], primqvec=u["primqvec"][None], primscale=u["primscale"][None],
                  opacity=u["opacity"][None], color=color[None])
@@ -243,9 +256,9 @@ def run_ours(args):
             packed = resident.clone() if world > 1 else resident
         if world > 1:
             dist.broadcast(packed, src=0)           # decoded Gaussians of the frame, owner = rank 0
-        packed = packed.detach().requires_grad_()
-        rgb, alpha, depth = gpu_step(packed, cam, li)
-        grad = packed.grad
+        leaves = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
+        rgb, alpha, depth = gpu_step(leaves, cam, li)
+        grad = torch.cat([leaves[k].grad.reshape(-1) for k, _ in FIELDS])  # flat dL/d(decoded), same layout
         if world > 1:
             dist.all_reduce(grad)                   # dL/d(decoded) summed over the views
         if e2e:

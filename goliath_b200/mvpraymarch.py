@@ -48,94 +48,72 @@ def build_accel(primtransfin, algo, fixedorder=False):
     return sortedobjid, nodechildren, nodeaabb
 
 
+def _block(opt):
+    return opt if isinstance(opt, tuple) else (opt, 1)
+
+
+def _check_march_inputs(raypos, raydir, tminmax, primpos, primrot, primscale, template, warp, chlast):
+    for name, t, last in (("raypos", raypos, 3), ("raydir", raydir, 3), ("tminmax", tminmax, 2)):
+        assert t.is_contiguous() and t.size(3) == last, "%s must be contiguous [N,H,W,%d]" % (name, last)
+    for name, t in (("primpos", primpos), ("primrot", primrot), ("primscale", primscale)):
+        assert t is None or (t.is_contiguous() and t.size(2) == 3), name
+    assert template.is_contiguous() and template.dim() == 6
+    ch = -1 if chlast else 2
+    assert template.size(ch) == 4
+    assert warp is None or (warp.is_contiguous() and warp.size(ch) == 3)
+
+
 class MVPRaymarch(Function):
-    """Custom Function for raymarching Mixture of Volumetric Primitives."""
+    """autograd node around mvpraymarchlib.raymarch_forward / raymarch_backward (mvpraymarch.py:87-311 upstream)."""
 
     @staticmethod
     def forward(self, raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm, gradmode,
                 options):
-        algo = options["algo"]
-        usebvh = options["usebvh"]
-        chlast = options["chlast"]
-        with_shadow = options["with_shadow"]
-        if isinstance(options["blocksize"], tuple):
-            blocksizex, blocksizey = options["blocksize"]
-        else:
-            blocksizex, blocksizey = options["blocksize"], 1
+        o = options
+        _check_march_inputs(raypos, raydir, tminmax, primpos, primrot, primscale, template, warp, o["chlast"])
+        transf = (primpos, primrot, primscale)
+        tree = (None, None, None)
+        if o["usebvh"] is not False:
+            tree = build_accel(transf, o["algo"], fixedorder=o["usebvh"] == "fixedorder")
+        sortedobjid, nodechildren, nodeaabb = tree
 
-        assert raypos.is_contiguous() and raypos.size(3) == 3
-        assert raydir.is_contiguous() and raydir.size(3) == 3
-        assert tminmax.is_contiguous() and tminmax.size(3) == 2
-        assert primpos is None or primpos.is_contiguous() and primpos.size(2) == 3
-        assert primrot is None or primrot.is_contiguous() and primrot.size(2) == 3
-        assert primscale is None or primscale.is_contiguous() and primscale.size(2) == 3
-        if chlast:
-            assert template.is_contiguous()
-            assert len(template.size()) == 6
-            assert template.size(-1) == 4
-            assert warp is None or (warp.is_contiguous() and warp.size(-1) == 3)
-        else:
-            assert template.is_contiguous() and len(template.size()) == 6 and template.size(2) == 4
-            assert warp is None or (warp.is_contiguous() and warp.size(2) == 3)
-
-        primtransfin = (primpos, primrot, primscale)
-        if usebvh is not False:
-            sortedobjid, nodechildren, nodeaabb = build_accel(primtransfin, algo, fixedorder=usebvh == "fixedorder")
-        else:
-            sortedobjid, nodechildren, nodeaabb = None, None, None
-
-        N, H, W = raypos.size(0), raypos.size(1), raypos.size(2)
-        rayrgba = torch.empty((N, H, W, 4), device=raypos.device)
-        # the kernel writes raysat for every ray, so no fill(-1) pass is needed (reference: mvpraymarch.py:150)
-        raysat = torch.empty((N, H, W, 3), dtype=torch.float32, device=raypos.device) if gradmode else None
-        rayterm = None
-
+        N, H, W = raypos.shape[:3]
+        dev = raypos.device
+        rayrgba = torch.empty((N, H, W, 4), device=dev)
+        # written for every ray by the kernel, so no fill(-1) pass (the reference pre-fills it, mvpraymarch.py:150)
+        raysat = torch.empty((N, H, W, 3), device=dev) if gradmode else None
         shadow = None
-        if with_shadow:
-            if chlast:
-                Ns, P, D, Hs, Ws, C = template.shape
-                shadow = torch.zeros((Ns, P, D, Hs, Ws, 2), device=template.device, dtype=torch.float32)
-            else:
-                Ns, P, C, D, Hs, Ws = template.shape
-                shadow = torch.zeros((Ns, P, 2, D, Hs, Ws), device=template.device, dtype=torch.float32)
+        if o["with_shadow"]:
+            vol = template.shape[:-1] + (2,) if o["chlast"] else template.shape[:2] + (2,) + template.shape[3:]
+            shadow = torch.zeros(vol, device=template.device, dtype=torch.float32)
 
+        bx, by = _block(o["blocksize"])
         mvpraymarchlib.raymarch_forward(
-            raypos, raydir, stepsize, tminmax, sortedobjid, nodechildren, nodeaabb, *primtransfin, template, warp, rayrgba,
-            raysat, rayterm, shadow, algo, options["sortprims"], options["maxhitboxes"], options["synchitboxes"], chlast,
-            options["fadescale"], options["fadeexp"], options["accum"], options["termthresh"], options["griddim"],
-            blocksizex, blocksizey)
+            raypos, raydir, stepsize, tminmax, sortedobjid, nodechildren, nodeaabb, *transf, template, warp, rayrgba,
+            raysat, None, shadow, o["algo"], o["sortprims"], o["maxhitboxes"], o["synchitboxes"], o["chlast"],
+            o["fadescale"], o["fadeexp"], o["accum"], o["termthresh"], o["griddim"], bx, by)
 
         self.save_for_backward(raypos, raydir, tminmax, sortedobjid, nodechildren, nodeaabb, primpos, primrot, primscale,
-                               template, warp, rayrgba, raysat, rayterm)
-        self.options = options
-        self.stepsize = stepsize
+                               template, warp, rayrgba, raysat)
+        self.options, self.stepsize = o, stepsize
         return rayrgba, shadow
 
     @staticmethod
     def backward(self, grad_rayrgba, grad_shadow):
         (raypos, raydir, tminmax, sortedobjid, nodechildren, nodeaabb, primpos, primrot, primscale, template, warp, rayrgba,
-         raysat, rayterm) = self.saved_tensors
+         raysat) = self.saved_tensors
         o = self.options
-        if isinstance(o["bwdblocksize"], tuple):
-            blocksizex, blocksizey = o["bwdblocksize"]
-        else:
-            blocksizex, blocksizey = o["bwdblocksize"], 1
-
-        grad_primpos = torch.zeros_like(primpos)
-        grad_primrot = torch.zeros_like(primrot)
-        grad_primscale = torch.zeros_like(primscale)
-        primtransfin = (primpos, grad_primpos, primrot, grad_primrot, primscale, grad_primscale)
-        grad_template = torch.zeros_like(template)
-        grad_warp = torch.zeros_like(warp) if warp is not None else None
-
+        # accumulated into by the kernel (REDs), hence zero-filled
+        g_pos, g_rot, g_scale = (torch.zeros_like(t) for t in (primpos, primrot, primscale))
+        g_template = torch.zeros_like(template)
+        g_warp = None if warp is None else torch.zeros_like(warp)
+        bx, by = _block(o["bwdblocksize"])
         mvpraymarchlib.raymarch_backward(
-            raypos, raydir, self.stepsize, tminmax, sortedobjid, nodechildren, nodeaabb, *primtransfin, template,
-            grad_template, warp, grad_warp, rayrgba, grad_rayrgba.contiguous(), raysat, rayterm, o["algo"], o["sortprims"],
-            o["maxhitboxes"], o["synchitboxes"], o["chlast"], o["fadescale"], o["fadeexp"], o["accum"], o["termthresh"],
-            o["griddim"], blocksizex, blocksizey)
-
-        return (None, None, None, None, grad_primpos, grad_primrot, grad_primscale, grad_template, grad_warp, None, None,
-                None)
+            raypos, raydir, self.stepsize, tminmax, sortedobjid, nodechildren, nodeaabb, primpos, g_pos, primrot, g_rot,
+            primscale, g_scale, template, g_template, warp, g_warp, rayrgba, grad_rayrgba.contiguous(), raysat, None,
+            o["algo"], o["sortprims"], o["maxhitboxes"], o["synchitboxes"], o["chlast"], o["fadescale"], o["fadeexp"],
+            o["accum"], o["termthresh"], o["griddim"], bx, by)
+        return (None, None, None, None, g_pos, g_rot, g_scale, g_template, g_warp, None, None, None)
 
 
 def mvpraymarch(

@@ -70,3 +70,59 @@ def test_linear_wn_vs_reference(cuda):
     assert_close(t2n(x.grad), g["li_gx"], rtol=2e-4, atol=1e-5, what="LinearWN grad x")
     assert_close(t2n(lin.weight_v.grad), g["li_gv"], rtol=5e-4, atol=1e-5, what="LinearWN grad v")
     assert_close(t2n(lin.weight_g.grad), g["li_gg"], rtol=5e-4, atol=1e-5, what="LinearWN grad g")
+
+
+def test_prim_decoder_end_to_end_small(cuda):
+    """goliath_b200.rgca.PrimDecoder at slabsize 128 against the same computation done with torch fp64 ops on the
+    CPU from the same parameters (towers = conv_transpose2d + untied bias + LeakyReLU, heads = pinned torch oracle)."""
+    from goliath_b200.rgca import PrimDecoder
+    from oracle import heads_oracle as ho
+
+    class Geo:  # stand-in for ca_code.utils.geom.GeometryModule: UV position / normal maps
+        def __init__(self, pos, nml): self.pos, self.nml = pos, nml
+        def to_uv(self, x): return x
+        def vn(self, g): return self.nml
+
+    th = torch
+    gen = th.Generator().manual_seed(9)
+    S, B = 128, 1
+    pos = 100 * th.randn(B, 3, S, S, generator=gen)
+    nml = th.randn(B, 3, S, S, generator=gen)
+    dec = PrimDecoder(16, Geo(pos.to(cuda), nml.to(cuda)), 255 * th.rand(3, S, S, generator=gen), slabsize=S).to(cuda)
+    with th.no_grad():
+        for n_, p in dec.named_parameters():
+            if n_.endswith("bias"):
+                p.normal_(0, 0.1)
+    keys = list(dec.state_dict().keys())
+    assert "vnocond_mod.12.weight_v" in keys and "vcond_mod.0.bias" in keys and "encmod.0.weight_g" in keys and "albedo" in keys
+    embs = th.randn(B, 16, generator=gen)
+    campos = th.tensor([[0.0, 0.0, 1000.0]])
+    light_sh = th.randn(B, 3, 81, generator=gen)
+    li_pos = 1100 * th.nn.functional.normalize(th.randn(B, 4, 3, generator=gen), dim=-1)
+    li_int = th.rand(B, 4, 3, generator=gen) + 0.5
+    nl = th.tensor([4], dtype=th.int32)
+    out = dec(embs.to(cuda), pos.to(cuda), campos.to(cuda), li_int.to(cuda), li_pos.to(cuda), light_sh.to(cuda), nl.to(cuda))
+    # torch fp64 restatement from the same parameters
+    sd = {k: v.detach().double().cpu() for k, v in dec.state_dict().items()}
+    def lin(x, pre): 
+        w = sd[pre + ".weight_g"] * sd[pre + ".weight_v"] / sd[pre + ".weight_v"].norm()
+        return th.nn.functional.leaky_relu(th.nn.functional.linear(x, w, sd[pre + ".bias"]), 0.2)
+    def tower(x, pre):
+        for i in range(7):
+            p = "%s.%d" % (pre, 2 * i)
+            w = sd[p + ".weight_g"] * sd[p + ".weight_v"] / sd[p + ".weight_v"].norm()
+            x = th.nn.functional.conv_transpose2d(x, w, None, 2, 1) + sd[p + ".bias"][None]
+            if i < 6:
+                x = th.nn.functional.leaky_relu(x, 0.2)
+        return x
+    x = lin(embs.double(), "encmod.0").view(-1, 256, 1, 1)
+    f1 = tower(x, "vnocond_mod")
+    v = lin(th.nn.functional.normalize(campos.double(), dim=1), "viewmod.0")[:, :, None, None]
+    f2 = tower(th.cat([x, v], 1), "vcond_mod")
+    ref = ho.gaussian_heads(f1, f2, pos.double(), th.nn.functional.normalize(nml.double(), dim=1), sd["albedo"], light_sh.double(), campos.double())
+    for k in ("primpos", "primqvec", "primscale", "opacity", "sigma", "spec_nml", "diff_color"):
+        r = ref[k].numpy()
+        assert_close(t2n(out[k]), r, rtol=2e-4, atol=2e-5 * np.abs(r).max(), frac=0.999, what="PrimDecoder " + k)
+    assert out["color"].shape == (B, S * S, 3) and bool((out["color"] >= 0).all())
+    out["color"].sum().backward()
+    assert dec.vnocond_mod[0].weight_v.grad is not None and th.isfinite(dec.vnocond_mod[12].bias.grad).all()
