@@ -119,6 +119,65 @@ class FusedLeakyReLU(nn.Identity):
     the Sequential indices (and therefore the checkpoint key names) identical to the reference's [layer, act] lists."""
 
 
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Inference forward of a deconv tower (Sequential of ConvTranspose2dWNUB [+ FusedLeakyReLU]) on the tensor cores
+    (csrc/deconv_tc.cu: tcgen05.mma kind::tf32 with 3xTF32 split, TMA-fed, TMEM accumulators).  Activations stay NHWC
+    (hi/lo split) between tensor-core layers; layers the kernel does not cover (Cin not reachable by 32-padding of a
+    previous tensor-core layer, Cout % 16 != 0 — i.e. the towers' last 16 -> {125, 4} layer) run on the SIMT kernel.
+    No autograd: use the module's normal forward for training."""
+    assert not torch.is_grad_enabled(), "tower_forward_tc is the inference path"
+    L = _lib.lib()
+    dev = x.device
+    layers = [m for m in tower if isinstance(m, ConvTranspose2dWNUB)]
+    cur_nchw, cur_hi, cur_lo, cur_c = x.contiguous(), None, None, x.shape[1]
+    B, _, H, W = x.shape
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        for i, layer in enumerate(layers):
+            Cin, Cout = layer.in_channels, layer.out_channels
+            tc_ok = Cout % 16 == 0 and 16 <= Cout <= 256
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            nxt_tc = nxt is not None and nxt.out_channels % 16 == 0 and 16 <= nxt.out_channels <= 256
+            scale = (layer.weight_g.reshape(-1) / layer.weight_v.norm()).contiguous()
+            bias = None if layer.bias is None else layer.bias.contiguous()
+            slope = layer.fused_slope
+            if tc_ok:
+                cpad = _pad32(Cin)
+                if cur_hi is None:  # enter the NHWC hi/lo format
+                    cur_hi = torch.empty(B, H, W, cpad, device=dev)
+                    cur_lo = torch.empty(B, H, W, cpad, device=dev)
+                    _lib.check(L.gb_nchw_to_nhwc_split(B, Cin, cpad, H, W, _lib.ptr(cur_nchw), _lib.ptr(cur_hi),
+                                                       _lib.ptr(cur_lo), st), "nchw_to_nhwc_split")
+                    cur_c = cpad
+                assert cur_c == cpad, "channel padding mismatch between consecutive tensor-core layers"
+                ws = torch.empty(L.gb_deconv_tc_weight_bytes(cpad, Cout) // 4, device=dev)
+                ldc = _pad32(Cout)
+                # padded output channels must be zero for the next layer's K loop
+                o_hi = (torch.zeros if ldc != Cout else torch.empty)(B, 2 * H, 2 * W, ldc, device=dev) if nxt_tc else None
+                o_lo = (torch.zeros if ldc != Cout else torch.empty)(B, 2 * H, 2 * W, ldc, device=dev) if nxt_tc else None
+                o_nchw = None if nxt_tc else torch.empty(B, Cout, 2 * H, 2 * W, device=dev)
+                _lib.check(L.gb_deconv4x4s2_tc_fwd(
+                    B, Cin, cpad, Cout, H, W, _lib.ptr(cur_hi), _lib.ptr(cur_lo), _lib.ptr(layer.weight_v.contiguous()),
+                    _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(bias), float(slope if slope is not None else 1.0),
+                    int(slope is not None), _lib.ptr(o_hi), _lib.ptr(o_lo), ldc, _lib.ptr(o_nchw), st), "deconv4x4s2_tc_fwd")
+                cur_hi, cur_lo, cur_c, cur_nchw = o_hi, o_lo, ldc, o_nchw
+            else:
+                assert cur_nchw is not None
+                out = torch.empty(B, Cout, 2 * H, 2 * W, device=dev)
+                _lib.check(L.gb_deconv4x4s2_wnub_fwd(
+                    B, Cin, Cout, H, W, _lib.ptr(cur_nchw), _lib.ptr(layer.weight_v.contiguous()), _lib.ptr(scale),
+                    _lib.ptr(bias), float(slope if slope is not None else 1.0), int(slope is not None), _lib.ptr(out), st),
+                    "deconv4x4s2_wnub_fwd")
+                cur_nchw, cur_hi, cur_lo = out, None, None
+            H, W = 2 * H, 2 * W
+    assert cur_nchw is not None, "a tower must end with a layer that produces NCHW output"
+    return cur_nchw
+
+
 def make_conv_trans(n_in, n_out, fs, stride, pad, mode, act=None, ub=None, bias=True):
     """layers.py:27-47 with trans=True, ub=(H,W).  Returns [layer] or [layer, act] like the reference; a LeakyReLU is
     executed inside the layer's kernel and replaced by a parameter-free placeholder at the same list position."""

@@ -126,3 +126,34 @@ def test_prim_decoder_end_to_end_small(cuda):
     assert out["color"].shape == (B, S * S, 3) and bool((out["color"] >= 0).all())
     out["color"].sum().backward()
     assert dec.vnocond_mod[0].weight_v.grad is not None and th.isfinite(dec.vnocond_mod[12].bias.grad).all()
+
+
+@pytest.mark.parametrize("plan,size", [([(64, 32), (32, 16), (16, 8)], (16, 12)), ([(264, 256), (256, 128)], (8, 8)),
+                                       ([(32, 48), (48, 16)], (40, 24))])
+def test_tensor_core_tower_matches_simt(cuda, plan, size):
+    """csrc/deconv_tc.cu (tcgen05 + TMA + TMEM, 3xTF32) against the SIMT kernel on the same parameters: multi-layer
+    NHWC hi/lo chaining, channel padding (264 -> 288, 48 -> 64), partial tiles, and the SIMT tail for Cout % 16 != 0."""
+    from goliath_b200 import nn as gnn
+
+    gen = torch.Generator().manual_seed(len(plan) * 100 + plan[0][0])
+    H, W = size
+    layers, h, w = [], H, W
+    for i, (a, b) in enumerate(plan):
+        act = torch.nn.LeakyReLU(0.2) if i < len(plan) - 1 else None
+        layers += gnn.make_conv_trans(a, b, 4, 2, 1, "wn", act, ub=(2 * h, 2 * w))
+        h, w = 2 * h, 2 * w
+    tower = torch.nn.Sequential(*layers)
+    with torch.no_grad():
+        for m in tower:
+            if isinstance(m, gnn.ConvTranspose2dWNUB):
+                m.weight_v.copy_(torch.randn(m.weight_v.shape, generator=gen) * 0.1)
+                m.weight_g.copy_(torch.rand(m.weight_g.shape, generator=gen) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=gen) * 0.3)
+    tower = tower.to(cuda)
+    x = torch.randn(2, plan[0][0], H, W, generator=gen).to(cuda)
+    with torch.no_grad():
+        ref = tower(x)
+        out = gnn.tower_forward_tc(tower, x)
+    torch.cuda.synchronize()
+    r = t2n(ref)
+    assert_close(t2n(out), r, rtol=1e-4, atol=2e-5 * np.abs(r).max(), what="tensor-core tower vs SIMT")
