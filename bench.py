@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--lights", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mvp-density", type=float, default=2000.0, help="template alpha scale of the --ext-compare MVP scene")
+    ap.add_argument("--decoder", action="store_true",
+                    help="time the RGCA PrimDecoder forward at native size (1024^2 Gaussians): towers on tcgen05 vs SIMT, "
+                         "fused heads kernel; prints its own JSON line")
     ap.add_argument("--ext-compare", action="store_true",
                     help="time the reference's own extensions rebuilt for sm_100a (oracle/_ref) against ours: SG shade, "
                          "raydirs, MVP raymarch (BASELINE config 4 shape); prints its own JSON line")
@@ -414,6 +417,83 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ decoder (rows R1 + R2)
+def run_decoder(args):
+    """Inference forward of the RGCA PrimDecoder at native size (B=1, 1024x1024 Gaussians, 162.8 M parameters,
+    random init): the two 7-layer towers on the tensor cores (tcgen05 + TMA) and on the SIMT kernels, then the fused heads
+    kernel and the SG shade.  Reports ms per part and the last layer's achieved HBM bandwidth on its mandatory bytes
+    (2*Cout*H*W*4 + Cin*(H/2)*(W/2)*4)."""
+    from goliath_b200 import nn as gnn
+    from goliath_b200 import synthetic
+    from goliath_b200.rgca import PrimDecoder
+    from goliath_b200.rgca_heads import gaussian_heads, shade_and_compose
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    S = 1024
+
+    class Geo:
+        def __init__(self, pos, nml): self.pos, self.nml = pos, nml
+        def to_uv(self, x): return x
+        def vn(self, g): return self.nml
+
+    gen = torch.Generator().manual_seed(1)
+    pos = (100 * torch.randn(1, 3, S, S, generator=gen)).to(dev)
+    nml = torch.randn(1, 3, S, S, generator=gen).to(dev)
+    dec = PrimDecoder(256, Geo(pos, nml), 255 * torch.rand(3, S, S, generator=gen), slabsize=S).to(dev)
+    with torch.no_grad():
+        for n_, p in dec.named_parameters():
+            if n_.endswith("bias"):
+                p.normal_(0, 0.05)
+    embs = torch.randn(1, 256, generator=gen).to(dev)
+    campos = torch.tensor([[0.0, 0.0, 1000.0]], device=dev)
+    li = {k: v.to(dev) for k, v in synthetic.lights(args.lights).items()}
+    light_sh = torch.randn(1, 3, 81, generator=gen).to(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush_buf.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    res = {}
+    with torch.no_grad():
+        x = dec.encmod(embs).view(-1, 256, 8, 8)
+        view = dec.viewmod(torch.nn.functional.normalize(campos, dim=1))[:, :, None, None].expand(-1, -1, 8, 8)
+        xv = torch.cat([x, view], 1).contiguous()
+        res["tower_vnocond_ms_tc"] = timeit(lambda: gnn.tower_forward_tc(dec.vnocond_mod, x))
+        res["tower_vnocond_ms_simt"] = timeit(lambda: dec.vnocond_mod(x))
+        res["tower_vcond_ms_tc"] = timeit(lambda: gnn.tower_forward_tc(dec.vcond_mod, xv))
+        res["tower_vcond_ms_simt"] = timeit(lambda: dec.vcond_mod(xv))
+        f1, f2 = gnn.tower_forward_tc(dec.vnocond_mod, x), gnn.tower_forward_tc(dec.vcond_mod, xv)
+        g1 = dec.vnocond_mod(x)
+        res["tc_vs_simt_rel_err"] = float((f1 - g1).norm() / g1.norm())
+        tn = torch.nn.functional.normalize(nml, dim=1)
+        res["heads_ms"] = timeit(lambda: gaussian_heads(f1, f2, pos, tn, dec.albedo, light_sh, campos))
+        heads = gaussian_heads(f1, f2, pos, tn, dec.albedo, light_sh, campos)
+        res["shade_compose_ms"] = timeit(lambda: shade_and_compose(heads, li["light_intensity"], li["light_pos"], li["n_lights"]))
+        res["full_decoder_ms_tc"] = timeit(lambda: dec(embs, pos, campos, li["light_intensity"], li["light_pos"], light_sh, li["n_lights"]))
+        # last layer alone (16 -> 125 @ 1024^2): mandatory traffic = output + untied bias + input
+        last = dec.vnocond_mod[12]
+        h5 = torch.randn(1, 16, 512, 512, device=dev)
+        seq = torch.nn.Sequential(last)
+        res["last_layer_ms_tc"] = timeit(lambda: gnn.tower_forward_tc(seq, h5))
+        res["last_layer_ms_simt"] = timeit(lambda: last(h5))
+        bytes_last = 2 * 125 * S * S * 4 + 16 * 512 * 512 * 4
+        res["last_layer_alg_GBs_tc"] = bytes_last / res["last_layer_ms_tc"] / 1e6
+        res["last_layer_alg_GBs_simt"] = bytes_last / res["last_layer_ms_simt"] / 1e6
+        heads_bytes = S * S * (129 * 4 + 36 + 130)
+        res["heads_alg_GBs"] = heads_bytes / res["heads_ms"] / 1e6
+    print(json.dumps({"decoder": res, "config": {"slabsize": S, "params_M": sum(p.numel() for p in dec.parameters()) / 1e6,
+                                                 "lights": args.lights}}))
+
+
 # ------------------------------------------------------------------------------------------ extension-level comparison
 def run_ext_compare(args):
     """Reference arm at the EXTENSION level: the reference's sgutilslib / utilslib / mvpraymarchlib
@@ -515,7 +595,9 @@ def run_ext_compare(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.ext_compare:
+    if a.decoder:
+        run_decoder(a)
+    elif a.ext_compare:
         run_ext_compare(a)
     elif a.impl == "reference":
         run_reference(a)

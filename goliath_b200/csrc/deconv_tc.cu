@@ -85,7 +85,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 struct TcArgs {
-  int B, Cin, Cout, Hi, Wi;      // Cin = padded channel count (multiple of 32) of the NHWC input
+  int B, Cin, Cout, Npad, Hi, Wi;  // Cin = padded channel count (multiple of 32); Npad = Cout rounded up to 16
   int tile_r, tile_c;            // tile = tile_r rows x tile_c columns of input positions, tile_r * tile_c == 128
   int stages;
   const float* scale;            // [Cout]
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
                                                                  const __grid_constant__ CUtensorMap map_b_lo, TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: per stage [A_hi | A_lo | B_hi | B_lo], all 1024-byte aligned
-  const int b_bytes = a.Cout * kBlockK * 4;
+  const int b_bytes = a.Npad * kBlockK * 4;
   const int stage_bytes = 2 * kABytes + 2 * b_bytes;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long s_full[4], s_empty[4], s_done;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
   const int m0 = ty * a.tile_r, n0 = tx * a.tile_c;
   const int kb_per_tap = a.Cin / kBlockK, num_kb = 4 * kb_per_tap;
   unsigned tmem_cols = 32;
-  while ((int)tmem_cols < a.Cout) tmem_cols <<= 1;
+  while ((int)tmem_cols < a.Npad) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
         mbar_expect_tx(&s_full[s], (unsigned)stage_bytes);
         tma_load_4d(st, &map_a_hi, cblk * kBlockK, n0 + dx, m0 + dy, b, &s_full[s]);
         tma_load_4d(st + kABytes, &map_a_lo, cblk * kBlockK, n0 + dx, m0 + dy, b, &s_full[s]);
-        const int krow = phase_id * a.Cout;          // weight matrix rows: [phase][co]
+        const int krow = phase_id * a.Npad;          // weight matrix rows: [phase][co padded]
         const int kcol = tap * a.Cin + cblk * kBlockK;  // columns: [tap][ci]
         tma_load_2d(st + 2 * kABytes, &map_b_hi, kcol, krow, &s_full[s]);
         tma_load_2d(st + 2 * kABytes + b_bytes, &map_b_lo, kcol, krow, &s_full[s]);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       // instruction descriptor: D = F32, A = B = TF32, both K-major, N = Cout, M = 128
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.Cout >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.Npad >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % a.stages, it = kb / a.stages;
         mbar_wait(&s_full[s], (unsigned)(it & 1));
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
     const bool valid = (m < a.Hi) && (n < a.Wi);
     const int Ho = 2 * a.Hi, Wo = 2 * a.Wi;
     const int Y = 2 * m + py, X = 2 * n + px;
-    for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+    for (int c0 = 0; c0 < a.Npad; c0 += 16) {
       unsigned r[16];
       const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
       asm volatile(
@@ -202,14 +202,18 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int co = c0 + j;
-          float o = __uint_as_float(r[j]) * a.scale[co];
-          if (a.bias) o += a.bias[((size_t)co * Ho + Y) * Wo + X];
-          if (a.apply_act) o = o > 0.f ? o : o * a.slope;
+          float o = 0.f;
+          if (co < a.Cout) {  // columns beyond Cout are zero padding of the N dimension
+            o = __uint_as_float(r[j]) * a.scale[co];
+            if (a.bias) o += a.bias[((size_t)co * Ho + Y) * Wo + X];
+            if (a.apply_act) o = o > 0.f ? o : o * a.slope;
+          }
           v[j] = o;
         }
         if (a.out_nchw) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) a.out_nchw[(((size_t)b * a.Cout + c0 + j) * Ho + Y) * Wo + X] = v[j];
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < a.Cout) a.out_nchw[(((size_t)b * a.Cout + c0 + j) * Ho + Y) * Wo + X] = v[j];
         }
         if (a.out_hi) {
           const size_t base = (((size_t)b * Ho + Y) * Wo + X) * a.ldc + c0;
@@ -247,19 +251,19 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(int B, int C, i
   lo[i] = v - h;
 }
 
-__global__ void __launch_bounds__(256) weight_prep_kernel(int Cin, int Cpad, int Cout, const float* __restrict__ v,
+__global__ void __launch_bounds__(256) weight_prep_kernel(int Cin, int Cpad, int Cout, int Npad, const float* __restrict__ v,
                                                           float* __restrict__ w_hi, float* __restrict__ w_lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over 4*Cout*4*Cpad
-  const long long total = 16ll * Cout * Cpad;
+  const long long total = 16ll * Npad * Cpad;
   if (i >= total) return;
   const int ci = (int)(i % Cpad);
   const int tap = (int)((i / Cpad) % 4);
-  const int co = (int)((i / (4ll * Cpad)) % Cout);
-  const int phase = (int)(i / (4ll * Cpad * Cout));
+  const int co = (int)((i / (4ll * Cpad)) % Npad);
+  const int phase = (int)(i / (4ll * Cpad * Npad));
   const int py = phase >> 1, px = phase & 1, tyy = tap >> 1, txx = tap & 1;
   const int ky = (tyy == 0) ? (py ? 2 : 1) : (py ? 0 : 3);
   const int kx = (txx == 0) ? (px ? 2 : 1) : (px ? 0 : 3);
-  const float val = ci < Cin ? v[(((size_t)ci * Cout + co) * 4 + ky) * 4 + kx] : 0.f;
+  const float val = (ci < Cin && co < Cout) ? v[(((size_t)ci * Cout + co) * 4 + ky) * 4 + kx] : 0.f;
   const float h = to_tf32(val);
   w_hi[i] = h;
   w_lo[i] = val - h;
@@ -279,7 +283,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }  // namespace
 
 // bytes of scratch for the weight matrices of one layer (hi + lo)
-GB_API size_t gb_deconv_tc_weight_bytes(int Cin_pad, int Cout) { return (size_t)2 * 16 * Cout * Cin_pad * sizeof(float); }
+GB_API size_t gb_deconv_tc_weight_bytes(int Cin_pad, int Cout) {
+  return (size_t)2 * 16 * ((Cout + 15) / 16 * 16) * Cin_pad * sizeof(float);
+}
 
 // NCHW fp32 -> NHWC hi/lo with the channel count padded to Cpad (multiple of 32): the tensor-core layers' input format
 GB_API int gb_nchw_to_nhwc_split(int B, int C, int Cpad, int H, int W, const float* x, float* hi, float* lo, void* stream) {
@@ -294,22 +300,23 @@ GB_API int gb_nchw_to_nhwc_split(int B, int C, int Cpad, int H, int W, const flo
 // Tensor-core forward of ConvTranspose2dWNUB(k=4,s=2,p=1) [+LeakyReLU].  x_hi/x_lo: NHWC [B,Hi,Wi,Cin_pad] (tf32 hi
 // part and remainder), v [Cin,Cout,4,4], w_scratch of gb_deconv_tc_weight_bytes(Cin_pad, Cout) bytes, scale [Cout],
 // bias [Cout,2Hi,2Wi] or NULL.  Outputs (either or both): out_hi/out_lo NHWC [B,2Hi,2Wi,ldc] for a following
-// tensor-core layer, out_nchw [B,Cout,2Hi,2Wi] fp32.  Requires Cin_pad % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 256.
+// tensor-core layer, out_nchw [B,Cout,2Hi,2Wi] fp32.  Requires Cin_pad % 32 == 0 and Cout <= 256 (N is padded to 16).
 GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, int Wi, const float* x_hi,
                                  const float* x_lo, const float* v, float* w_scratch, const float* scale,
                                  const float* bias, float slope, int apply_act, float* out_hi, float* out_lo, int ldc,
                                  float* out_nchw, void* stream) {
   if (B <= 0 || Hi <= 0 || Wi <= 0) return 0;
-  if (Cin_pad % 32 != 0 || Cin > Cin_pad || Cout % 16 != 0 || Cout < 16 || Cout > 256) return (int)cudaErrorInvalidValue;
+  const int Npad = (Cout + 15) / 16 * 16;
+  if (Cin_pad % 32 != 0 || Cin > Cin_pad || Cout < 1 || Npad > 256) return (int)cudaErrorInvalidValue;
   if (out_hi && (ldc < Cout || ldc % 4 != 0)) return (int)cudaErrorInvalidValue;
   PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
   if (!encode) return (int)cudaErrorNotSupported;
   cudaStream_t s = (cudaStream_t)stream;
   float* w_hi = w_scratch;
-  float* w_lo = w_scratch + (size_t)16 * Cout * Cin_pad;
+  float* w_lo = w_scratch + (size_t)16 * Npad * Cin_pad;
   {
-    const long long total = 16ll * Cout * Cin_pad;
-    weight_prep_kernel<<<(unsigned)gb::cdiv64(total, 256), 256, 0, s>>>(Cin, Cin_pad, Cout, v, w_hi, w_lo);
+    const long long total = 16ll * Npad * Cin_pad;
+    weight_prep_kernel<<<(unsigned)gb::cdiv64(total, 256), 256, 0, s>>>(Cin, Cin_pad, Cout, Npad, v, w_hi, w_lo);
   }
   // tile geometry: 128 positions = tile_r rows x tile_c columns
   int tile_c = 128;
@@ -331,9 +338,9 @@ GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, 
       return (int)cudaErrorInvalidValue;
   }
   {
-    const cuuint64_t gdim[2] = {(cuuint64_t)4 * Cin_pad, (cuuint64_t)4 * Cout};
+    const cuuint64_t gdim[2] = {(cuuint64_t)4 * Cin_pad, (cuuint64_t)4 * Npad};
     const cuuint64_t gstr[1] = {(cuuint64_t)4 * Cin_pad * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)Cout};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)Npad};
     const cuuint32_t estr[2] = {1, 1};
     if (encode(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -343,10 +350,10 @@ GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, 
       return (int)cudaErrorInvalidValue;
   }
   TcArgs a = {};
-  a.B = B; a.Cin = Cin_pad; a.Cout = Cout; a.Hi = Hi; a.Wi = Wi; a.tile_r = tile_r; a.tile_c = tile_c;
+  a.B = B; a.Cin = Cin_pad; a.Cout = Cout; a.Npad = Npad; a.Hi = Hi; a.Wi = Wi; a.tile_r = tile_r; a.tile_c = tile_c;
   a.scale = scale; a.bias = bias; a.slope = slope; a.apply_act = apply_act; a.out_hi = out_hi; a.out_lo = out_lo;
   a.ldc = ldc; a.out_nchw = out_nchw;
-  const int stage_bytes = 2 * kABytes + 2 * Cout * kBlockK * 4;
+  const int stage_bytes = 2 * kABytes + 2 * Npad * kBlockK * 4;
   a.stages = stage_bytes <= 64 * 1024 ? 3 : 2;
   const size_t smem = (size_t)a.stages * stage_bytes + 1024;
   GB_CUDA(cudaFuncSetAttribute(deconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -126,8 +126,8 @@ def _pad32(c):
 def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """Inference forward of a deconv tower (Sequential of ConvTranspose2dWNUB [+ FusedLeakyReLU]) on the tensor cores
     (csrc/deconv_tc.cu: tcgen05.mma kind::tf32 with 3xTF32 split, TMA-fed, TMEM accumulators).  Activations stay NHWC
-    (hi/lo split) between tensor-core layers; layers the kernel does not cover (Cin not reachable by 32-padding of a
-    previous tensor-core layer, Cout % 16 != 0 — i.e. the towers' last 16 -> {125, 4} layer) run on the SIMT kernel.
+    (hi/lo split) between tensor-core layers (channels padded to 32, N padded to 16 inside the kernel); only layers
+    with Cout > 256 would fall back to the SIMT kernel.
     No autograd: use the module's normal forward for training."""
     assert not torch.is_grad_enabled(), "tower_forward_tc is the inference path"
     L = _lib.lib()
@@ -139,9 +139,9 @@ def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         st = _lib.stream_ptr(dev)
         for i, layer in enumerate(layers):
             Cin, Cout = layer.in_channels, layer.out_channels
-            tc_ok = Cout % 16 == 0 and 16 <= Cout <= 256
+            tc_ok = Cout <= 256
             nxt = layers[i + 1] if i + 1 < len(layers) else None
-            nxt_tc = nxt is not None and nxt.out_channels % 16 == 0 and 16 <= nxt.out_channels <= 256
+            nxt_tc = nxt is not None and nxt.out_channels <= 256
             scale = (layer.weight_g.reshape(-1) / layer.weight_v.norm()).contiguous()
             bias = None if layer.bias is None else layer.bias.contiguous()
             slope = layer.fused_slope

@@ -43,6 +43,14 @@ class PrimDecoder(nn.Module):
         self.vcond_mod = _tower(256 + 8, 4, slabsize)
         rgb = color_mean / 255.0
         self.albedo = nn.Parameter((2.0 * rgb / 2.2974).permute(1, 2, 0).reshape(1, -1, 3))
+        # inference (no_grad) runs the towers on the tensor cores (tcgen05 + TMA, csrc/deconv_tc.cu); training uses
+        # the SIMT kernels that also provide the backward (csrc/deconv_wnub.cu)
+        self.use_tensor_cores = True
+
+    def _run_tower(self, tower, x):
+        if self.use_tensor_cores and not th.is_grad_enabled():
+            return gnn.tower_forward_tc(tower, x)
+        return tower(x)
 
     def forward(self, embs, geom, headrel_campos, light_intensity, headrel_light_pos, headrel_light_sh, n_lights,
                 preconv_envmap: Optional[th.Tensor] = None, lightrot: Optional[th.Tensor] = None):
@@ -51,8 +59,8 @@ class PrimDecoder(nn.Module):
         postex = self.geo_fn.to_uv(geom)
         tn = F.normalize(self.geo_fn.to_uv(self.geo_fn.vn(geom)), dim=1)
         x = self.encmod(embs).view(-1, 256, self.base, self.base)
-        f_vnocond = self.vnocond_mod(x)
+        f_vnocond = self._run_tower(self.vnocond_mod, x)
         view = self.viewmod(F.normalize(headrel_campos, dim=1))[:, :, None, None].expand(-1, -1, self.base, self.base)
-        f_vcond = self.vcond_mod(th.cat([x, view], dim=1))
+        f_vcond = self._run_tower(self.vcond_mod, th.cat([x, view], dim=1))
         heads = gaussian_heads(f_vnocond, f_vcond, postex, tn, self.albedo, headrel_light_sh, headrel_campos, PRIMSCALE_RANGE)
         return shade_and_compose(heads, light_intensity, headrel_light_pos, n_lights)
