@@ -34,6 +34,10 @@ SIGNATURES = {
     "gb_pack_records": (_i, [_i64, _i] + [_vp] * 6 + [_vp]),
     "gb_tile_order": (_i, [_i, _vp, _vp, _vp]),
     "gb_pack_records_fused": (_i, [_i64] + [_vp] * 8 + [_vp]),
+    "gb_pack_records_fused_dn": (_i, [_i64] + [_vp] * 9 + [_vp]),
+    "gb_map_gaussian_to_intersects_dn": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
+    "gb_sort_intersects_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "gb_get_tile_bin_edges_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "gb_splat_grad_unpack": (_i, [_i] + [_vp] * 8 + [_vp]),
     "gb_rasterize_packed_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_packed_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) map_to_intersects_kernel(int G, const flo
                                                                 const int* __restrict__ cum_tiles_hit, int tbx,
                                                                 int tby, int block_width,
                                                                 long long* __restrict__ isect_ids,
-                                                                int* __restrict__ gaussian_ids) {
+                                                                int* __restrict__ gaussian_ids, long long cap) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= G) return;
   const int r = radii[i];
@@ -124,11 +124,17 @@ __global__ void __launch_bounds__(256) map_to_intersects_kernel(int G, const flo
   const long long depth_id = (long long)__float_as_int(depths[i]);
   for (int ty = y0; ty < y1; ++ty)
     for (int tx = x0; tx < x1; ++tx) {
+      if (cur >= cap) return;  // capacity of the sync-free path (flagged by the bin-edges kernel)
       const long long tile_id = (long long)ty * tbx + tx;
       isect_ids[cur] = (tile_id << 32) | depth_id;
       gaussian_ids[cur] = i;
       ++cur;
     }
+}
+
+// The element count may live on the device (sync-free path): n = min(*n_dev, capacity) when n_dev != null.
+__device__ __forceinline__ long long resolve_n(long long n_cap, const int* __restrict__ n_dev) {
+  return n_dev ? min((long long)*n_dev, n_cap) : n_cap;
 }
 
 // ------------------------------------------------------------------ radix sort (u64 keys, i32 values)
@@ -139,10 +145,12 @@ constexpr int kRadix = 256;
 
 // warp w of a CTA owns the contiguous chunk [tile_base + w*512, +512); lane-strided inside the chunk so
 // that "earlier in memory" == (smaller item index j, then smaller lane) — needed for stability.
-__global__ void __launch_bounds__(kSortBlock) sort_hist_kernel(long long n, const unsigned long long* __restrict__ keys,
+__global__ void __launch_bounds__(kSortBlock) sort_hist_kernel(long long n_cap, const int* __restrict__ n_dev,
+                                                               const unsigned long long* __restrict__ keys,
                                                                int shift, int num_tiles,
                                                                unsigned* __restrict__ hist /* [256][num_tiles] */) {
   __shared__ unsigned s_hist[kRadix];
+  const long long n = resolve_n(n_cap, n_dev);
   s_hist[threadIdx.x] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortTile;
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(kScanBlock) sort_scan_kernel(unsigned* __restr
 }
 
 __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(
-    long long n, const unsigned long long* __restrict__ keys_in, const int* __restrict__ vals_in,
+    long long n_cap, const int* __restrict__ n_dev, const unsigned long long* __restrict__ keys_in, const int* __restrict__ vals_in,
     unsigned long long* __restrict__ keys_out, int* __restrict__ vals_out, int shift, int num_tiles,
     const unsigned* __restrict__ offsets /* per-digit scanned [256][num_tiles] */,
     const unsigned* __restrict__ totals /* [256] keys per digit */) {
@@ -182,6 +190,7 @@ __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(
   __shared__ unsigned s_whist[kWarps][kRadix];  // per-warp digit counts -> per-warp running offsets (8 KB)
   __shared__ int s_scan[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n = resolve_n(n_cap, n_dev);
   // digit bases = exclusive scan of the 256 digit totals (every CTA recomputes it: 256 loads from L2);
   // a digit holding every key makes the pass a no-op (typical for the top depth byte)
   const unsigned my_total = totals[threadIdx.x];
@@ -251,9 +260,12 @@ __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(
 }
 
 // ------------------------------------------------------------------ tile bin edges
-__global__ void __launch_bounds__(256) tile_bin_edges_kernel(long long n, const long long* __restrict__ isect_sorted,
-                                                             int2* __restrict__ tile_bins) {
+__global__ void __launch_bounds__(256) tile_bin_edges_kernel(long long n_cap, const int* __restrict__ n_dev,
+                                                             const long long* __restrict__ isect_sorted,
+                                                             int2* __restrict__ tile_bins, int* __restrict__ overflow) {
+  const long long n = resolve_n(n_cap, n_dev);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && overflow && n_dev && (long long)*n_dev > n_cap) *overflow = 1;  // capacity exceeded: caller must re-run
   if (i >= n) return;
   const int cur = (int)(isect_sorted[i] >> 32);
   if (i == 0) tile_bins[cur].x = 0;
@@ -286,16 +298,30 @@ GB_API int gb_cumsum_i32(int n, const int32_t* in, int32_t* out, void* workspace
 }
 
 // replaces gsplat._C.map_gaussian_to_intersects
-GB_API int gb_map_gaussian_to_intersects(int G, const float* xys, const float* depths, const int32_t* radii,
-                                         const int32_t* cum_tiles_hit, int img_h, int img_w, int block_width,
-                                         int64_t* isect_ids, int32_t* gaussian_ids, void* stream) {
+static int map_impl(int G, const float* xys, const float* depths, const int32_t* radii, const int32_t* cum_tiles_hit,
+                    int img_h, int img_w, int block_width, int64_t* isect_ids, int32_t* gaussian_ids, long long cap,
+                    void* stream) {
   if (G <= 0) return 0;
   const int tbx = gb::cdiv(img_w, block_width), tby = gb::cdiv(img_h, block_width);
   map_to_intersects_kernel<<<gb::cdiv(G, 256), 256, 0, (cudaStream_t)stream>>>(
-      G, (const float2*)xys, depths, radii, cum_tiles_hit, tbx, tby, block_width, (long long*)isect_ids, gaussian_ids);
+      G, (const float2*)xys, depths, radii, cum_tiles_hit, tbx, tby, block_width, (long long*)isect_ids, gaussian_ids, cap);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;
+}
+
+GB_API int gb_map_gaussian_to_intersects(int G, const float* xys, const float* depths, const int32_t* radii,
+                                         const int32_t* cum_tiles_hit, int img_h, int img_w, int block_width,
+                                         int64_t* isect_ids, int32_t* gaussian_ids, void* stream) {
+  return map_impl(G, xys, depths, radii, cum_tiles_hit, img_h, img_w, block_width, isect_ids, gaussian_ids,
+                  0x7fffffffffffffffLL, stream);
+}
+// sync-free variant: the buffers hold `cap` intersections; writes beyond are dropped (and flagged by
+// gb_get_tile_bin_edges_dn), the true count stays on the device (last element of cum_tiles_hit)
+GB_API int gb_map_gaussian_to_intersects_dn(int G, const float* xys, const float* depths, const int32_t* radii,
+                                            const int32_t* cum_tiles_hit, int img_h, int img_w, int block_width,
+                                            int64_t cap, int64_t* isect_ids, int32_t* gaussian_ids, void* stream) {
+  return map_impl(G, xys, depths, radii, cum_tiles_hit, img_h, img_w, block_width, isect_ids, gaussian_ids, cap, stream);
 }
 
 // workspace for gb_sort_intersects: ping-pong key/value buffers + histogram table + flag
@@ -313,9 +339,8 @@ GB_API size_t gb_sort_workspace_bytes(int64_t n) {
 
 // replaces torch.sort(isect_ids) + gather(gaussian_ids) inside gsplat bin_and_sort_gaussians.
 // Stable ascending sort on the low `key_bits` bits (keys are non-negative: depth > 0).
-GB_API int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t* gaussian_ids,
-                              int64_t* isect_sorted, int32_t* gids_sorted, int key_bits, void* workspace,
-                              void* stream) {
+static int sort_impl(int64_t n, const int* n_dev, const int64_t* isect_ids, const int32_t* gaussian_ids,
+                     int64_t* isect_sorted, int32_t* gids_sorted, int key_bits, void* workspace, void* stream) {
   if (n <= 0) return 0;
   if (key_bits < 1 || key_bits > 64) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
@@ -336,9 +361,9 @@ GB_API int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t
     unsigned long long* dst_k = to_out ? (unsigned long long*)isect_sorted : alt_k;
     int* dst_v = to_out ? gids_sorted : alt_v;
     const int shift = 8 * p;
-    sort_hist_kernel<<<tiles, kSortBlock, 0, s>>>(n, src_k, shift, tiles, hist);
+    sort_hist_kernel<<<tiles, kSortBlock, 0, s>>>(n, n_dev, src_k, shift, tiles, hist);
     sort_scan_kernel<<<kRadix, kScanBlock, 0, s>>>(hist, tiles, totals);
-    sort_scatter_kernel<<<tiles, kSortBlock, 0, s>>>(n, src_k, src_v, dst_k, dst_v, shift, tiles, hist, totals);
+    sort_scatter_kernel<<<tiles, kSortBlock, 0, s>>>(n, n_dev, src_k, src_v, dst_k, dst_v, shift, tiles, hist, totals);
     src_k = dst_k;
     src_v = dst_v;
   }
@@ -347,12 +372,34 @@ GB_API int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t
   return 0;
 }
 
-// replaces gsplat._C.get_tile_bin_edges; tile_bins [T,2] int32 must be zeroed by the caller
-GB_API int gb_get_tile_bin_edges(int64_t n, const int64_t* isect_sorted, int32_t* tile_bins, void* stream) {
+GB_API int gb_sort_intersects(int64_t n, const int64_t* isect_ids, const int32_t* gaussian_ids,
+                              int64_t* isect_sorted, int32_t* gids_sorted, int key_bits, void* workspace,
+                              void* stream) {
+  return sort_impl(n, nullptr, isect_ids, gaussian_ids, isect_sorted, gids_sorted, key_bits, workspace, stream);
+}
+// sync-free variant: `cap` sizes the launch and the workspace, the element count is read from *n_dev on the device
+GB_API int gb_sort_intersects_dn(int64_t cap, const int32_t* n_dev, const int64_t* isect_ids,
+                                 const int32_t* gaussian_ids, int64_t* isect_sorted, int32_t* gids_sorted, int key_bits,
+                                 void* workspace, void* stream) {
+  return sort_impl(cap, n_dev, isect_ids, gaussian_ids, isect_sorted, gids_sorted, key_bits, workspace, stream);
+}
+
+static int edges_impl(int64_t n, const int* n_dev, const int64_t* isect_sorted, int32_t* tile_bins, int* overflow,
+                      void* stream) {
   if (n <= 0) return 0;
   tile_bin_edges_kernel<<<(unsigned)gb::cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      n, (const long long*)isect_sorted, (int2*)tile_bins);
+      n, n_dev, (const long long*)isect_sorted, (int2*)tile_bins, overflow);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;
+}
+
+// replaces gsplat._C.get_tile_bin_edges; tile_bins [T,2] int32 must be zeroed by the caller
+GB_API int gb_get_tile_bin_edges(int64_t n, const int64_t* isect_sorted, int32_t* tile_bins, void* stream) {
+  return edges_impl(n, nullptr, isect_sorted, tile_bins, nullptr, stream);
+}
+// sync-free variant; *overflow (int32, device) is set to 1 when the true count exceeds `cap`
+GB_API int gb_get_tile_bin_edges_dn(int64_t cap, const int32_t* n_dev, const int64_t* isect_sorted, int32_t* tile_bins,
+                                    int32_t* overflow, void* stream) {
+  return edges_impl(cap, n_dev, isect_sorted, tile_bins, overflow, stream);
 }

@@ -102,13 +102,15 @@ __global__ void __launch_bounds__(256) pack_records_kernel(long long n, const in
 // Fused-render variant of the packing: the record's opacity is opacity * compensation and its 4th colour channel is
 // the view-space depth, i.e. exactly what ca_code/utils/render_gsplat.py:72 and :97 feed to the two rasterise calls,
 // without materialising those tensors.
-__global__ void __launch_bounds__(256) pack_records_fused_kernel(long long n, const int* __restrict__ gids_sorted,
+__global__ void __launch_bounds__(256) pack_records_fused_kernel(long long n_cap, const int* __restrict__ n_dev,
+                                                                 const int* __restrict__ gids_sorted,
                                                                  const float2* __restrict__ xys,
                                                                  const float* __restrict__ conics,
                                                                  const float* __restrict__ colors3,
                                                                  const float* __restrict__ depths,
                                                                  const float* __restrict__ opacity,
                                                                  const float* __restrict__ comp, float4* __restrict__ rec) {
+  const long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;  // count may live on the device (sync-free path)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int g = gids_sorted[i];
@@ -527,15 +529,26 @@ GB_API int gb_pack_records(int64_t n, int channels, const int32_t* gids_sorted, 
 }
 
 // Fused-render packing: records carry opacity*compensation and (rgb, depth); see pack_records_fused_kernel.
-GB_API int gb_pack_records_fused(int64_t n, const int32_t* gids_sorted, const float* xys, const float* conics,
-                                 const float* colors3, const float* depths, const float* opacity,
-                                 const float* compensation, float* records, void* stream) {
+static int pack_fused_impl(int64_t n, const int32_t* n_dev, const int32_t* gids_sorted, const float* xys,
+                           const float* conics, const float* colors3, const float* depths, const float* opacity,
+                           const float* compensation, float* records, void* stream) {
   if (n <= 0) return 0;
   pack_records_fused_kernel<<<(unsigned)gb::cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      n, gids_sorted, (const float2*)xys, conics, colors3, depths, opacity, compensation, (float4*)records);
+      n, n_dev, gids_sorted, (const float2*)xys, conics, colors3, depths, opacity, compensation, (float4*)records);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;
+}
+GB_API int gb_pack_records_fused(int64_t n, const int32_t* gids_sorted, const float* xys, const float* conics,
+                                 const float* colors3, const float* depths, const float* opacity,
+                                 const float* compensation, float* records, void* stream) {
+  return pack_fused_impl(n, nullptr, gids_sorted, xys, conics, colors3, depths, opacity, compensation, records, stream);
+}
+// sync-free variant: `cap` sizes the launch, the count is read from *n_dev on the device
+GB_API int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* xys,
+                                    const float* conics, const float* colors3, const float* depths,
+                                    const float* opacity, const float* compensation, float* records, void* stream) {
+  return pack_fused_impl(cap, n_dev, gids_sorted, xys, conics, colors3, depths, opacity, compensation, records, stream);
 }
 
 // Backward glue of the fused render (all outputs overwritten): v_colors3 [G,3], v_opacity [G], v_comp [G], v_depth [G].

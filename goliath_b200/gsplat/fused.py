@@ -8,13 +8,38 @@ import torch
 from torch.autograd import Function
 
 from .. import _lib
-from .utils import _tile_bounds, bin_and_sort_gaussians, compute_cumulative_intersects
+from .utils import _tile_bounds, _workspace, bin_and_sort_gaussians, compute_cumulative_intersects, key_bits
+
+# sync-free mode: per-device overflow flag (int32 on the device, set by the bin-edges kernel when the intersection
+# count exceeded the capacity of the buffers) — read it with check_overflow() at a point where a sync is acceptable
+_OVERFLOW = {}
+
+
+def _overflow_flag(dev):
+    f = _OVERFLOW.get(dev.index)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=dev)
+        _OVERFLOW[dev.index] = f
+    return f
+
+
+def check_overflow(device=None) -> bool:
+    """True if any sync-free render on `device` since the last check dropped intersections (capacity too small).
+    Synchronises; call it once per step / per epoch, not per render."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    f = _OVERFLOW.get(dev.index)
+    if f is None:
+        return False
+    hit = bool(f.item())
+    if hit:
+        f.zero_()
+    return hit
 
 
 class _RenderFused(Function):
     @staticmethod
     def forward(ctx, means3d, scales, quats, opacity, colors, viewmat, background, glob_scale, fx, fy, cx, cy, img_height,
-                img_width, clip_thresh):
+                img_width, clip_thresh, capacity):
         ins = [t.contiguous() for t in (means3d, scales, quats, opacity, colors, viewmat, background)]
         for t, n in zip(ins, ("means3d", "scales", "quats", "opacity", "colors", "viewmat", "background")):
             _lib.check_input(t, n)
@@ -39,9 +64,42 @@ class _RenderFused(Function):
                 float(fy), float(cx), float(cy), H, W, BW, float(clip_thresh), _lib.ptr(cov3d), _lib.ptr(xys),
                 _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics), _lib.ptr(comp), _lib.ptr(num_tiles_hit), st),
                 "project_gaussians_forward")
-            num_intersects, cum = compute_cumulative_intersects(num_tiles_hit)
             tb = _tile_bounds(H, W, BW)
-            if num_intersects < 1:
+            T = tb[0] * tb[1]
+            if capacity is not None:
+                # ---- sync-free path: the count never visits the host; buffers hold `capacity` intersections
+                cap = int(capacity)
+                cum = torch.empty_like(num_tiles_hit)
+                ws = _workspace(dev, max(L.gb_cumsum_workspace_bytes(G), L.gb_sort_workspace_bytes(cap)))
+                _lib.check(L.gb_cumsum_i32(G, _lib.ptr(num_tiles_hit), _lib.ptr(cum), _lib.ptr(ws), st), "cumsum")
+                n_dev = cum.data_ptr() + 4 * (G - 1)
+                isect = torch.empty(cap, device=dev, dtype=torch.int64)
+                gids_u = torch.empty(cap, **i32)
+                isect_s = torch.empty(cap, device=dev, dtype=torch.int64)
+                gids = torch.empty(cap, **i32)
+                bins = torch.zeros(T, 2, **i32)
+                order = torch.empty(T, **i32)
+                records = torch.empty(cap, 12, **f32)
+                _lib.check(L.gb_map_gaussian_to_intersects_dn(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
+                                                              _lib.ptr(cum), H, W, BW, cap, _lib.ptr(isect),
+                                                              _lib.ptr(gids_u), st), "map_dn")
+                _lib.check(L.gb_sort_intersects_dn(cap, n_dev, _lib.ptr(isect), _lib.ptr(gids_u), _lib.ptr(isect_s),
+                                                   _lib.ptr(gids), key_bits(T), _lib.ptr(ws), st), "sort_dn")
+                _lib.check(L.gb_get_tile_bin_edges_dn(cap, n_dev, _lib.ptr(isect_s), _lib.ptr(bins),
+                                                      _lib.ptr(_overflow_flag(dev)), st), "edges_dn")
+                _lib.check(L.gb_tile_order(T, _lib.ptr(bins), _lib.ptr(order), st), "tile_order")
+                _lib.check(L.gb_pack_records_fused_dn(cap, n_dev, _lib.ptr(gids), _lib.ptr(xys), _lib.ptr(conics),
+                                                      _lib.ptr(colors), _lib.ptr(depths), _lib.ptr(opacity),
+                                                      _lib.ptr(comp), _lib.ptr(records), st), "pack_records_fused_dn")
+                _lib.check(L.gb_rasterize_packed_fwd(H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records),
+                                                     _lib.ptr(bg4), _lib.ptr(out4), _lib.ptr(final_Ts),
+                                                     _lib.ptr(final_idx), st), "rasterize_packed_forward")
+                num_intersects = cap  # "some": the backward walks the bins, not the count
+            else:
+                num_intersects, cum = compute_cumulative_intersects(num_tiles_hit)
+            if capacity is not None:
+                pass
+            elif num_intersects < 1:
                 # reference behaviour with nothing to draw (gsplat 0.1.11 rasterize.py): background, final_Ts = 0
                 out4.copy_(bg4.expand(H, W, 4))
                 final_Ts.zero_()
@@ -49,7 +107,6 @@ class _RenderFused(Function):
                 gids = bins = order = records = torch.empty(0, **i32)
             else:
                 _, _, _, gids, bins = bin_and_sort_gaussians(G, num_intersects, xys, depths, radii, cum, tb, BW)
-                T = tb[0] * tb[1]
                 order = torch.empty(T, **i32)
                 records = torch.empty(num_intersects, 12, **f32)
                 _lib.check(L.gb_tile_order(T, _lib.ptr(bins), _lib.ptr(order), st), "tile_order")
@@ -97,11 +154,17 @@ class _RenderFused(Function):
                 _lib.ptr(cov3d), _lib.ptr(radii), _lib.ptr(conics), _lib.ptr(comp), _lib.ptr(v_xy), _lib.ptr(v_depth),
                 _lib.ptr(v_conic), _lib.ptr(v_comp), _lib.ptr(g_cov2d), _lib.ptr(g_cov3d), _lib.ptr(g_mean),
                 _lib.ptr(g_scale), _lib.ptr(g_quat), st), "project_gaussians_backward")
-        return (g_mean, g_scale, g_quat, v_opacity, v_colors, None, None, None, None, None, None, None, None, None, None)
+        return (g_mean, g_scale, g_quat, v_opacity, v_colors) + (None,) * 11
 
 
 def render_fused(means3d, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, img_height, img_width, opacity, colors,
-                 background, clip_thresh=0.01):
-    """Returns (out4 [H,W,4] = rgb + depth, alpha [H,W], radii [G] i32).  block_width is 16."""
+                 background, clip_thresh=0.01, capacity=None):
+    """Returns (out4 [H,W,4] = rgb + depth, alpha [H,W], radii [G] i32).  block_width is 16.
+
+    capacity=None keeps the reference's behaviour (one host sync to size the intersection buffers exactly).
+    capacity=N runs sync-free: buffers hold N intersections, the count stays on the device, nothing blocks the host, and
+    the call can be captured in a CUDA graph; if a view ever needs more than N intersections the excess is dropped and
+    `check_overflow()` reports it (results of that call are then incomplete — re-run with a larger capacity).  With
+    zero intersections the sync-free path returns alpha = 0, not the reference's alpha = 1 quirk."""
     return _RenderFused.apply(means3d, scales, quats, opacity, colors, viewmat, background, glob_scale, fx, fy, cx, cy,
-                              img_height, img_width, clip_thresh)
+                              img_height, img_width, clip_thresh, capacity)

@@ -139,9 +139,11 @@ def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         st = _lib.stream_ptr(dev)
         for i, layer in enumerate(layers):
             Cin, Cout = layer.in_channels, layer.out_channels
-            tc_ok = Cout <= 256
+            # measured on B200 (bench.py --decoder): with Cin = 16 the layer is pure output/bias bandwidth and the
+            # per-pixel NCHW epilogue of the tensor-core kernel loses to the SIMT kernel (4.2 vs 1.1 ms), so it stays SIMT
+            tc_ok = Cout <= 256 and Cin >= 32
             nxt = layers[i + 1] if i + 1 < len(layers) else None
-            nxt_tc = nxt is not None and nxt.out_channels <= 256
+            nxt_tc = nxt is not None and nxt.out_channels <= 256 and nxt.in_channels >= 32
             scale = (layer.weight_g.reshape(-1) / layer.weight_v.norm()).contiguous()
             bias = None if layer.bias is None else layer.bias.contiguous()
             slope = layer.fused_slope

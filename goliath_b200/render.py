@@ -30,6 +30,7 @@ def render(
     global_scale: float = 1.0,
     z_near: float = 0.1,
     fused: bool = True,
+    capacity: Optional[int] = None,
 ):
     means3D = primpos.view(-1, 3).contiguous()
     scales = primscale.view(-1, 3).contiguous()
@@ -45,7 +46,7 @@ def render(
         from .gsplat.fused import render_fused
 
         out4, alpha, radii = render_fused(means3D, scales, global_scale, rotations, Rt, fx, fy, cx, cy, cam_img_h,
-                                          cam_img_w, opacity, colors, bg_color, z_near)
+                                          cam_img_w, opacity, colors, bg_color, z_near, capacity)
         return {"render": out4[..., :3].permute(2, 0, 1), "final_T": (1.0 - alpha)[None], "alpha": alpha[None],
                 "radii": radii, "depth": out4[..., 3][None]}
 
@@ -78,7 +79,8 @@ def render(
     return out
 
 
-def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None, fused=True):
+def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None, fused=True,
+                 capacity=None):
     """rgca.AutoEncoder.render (rgca.py:112-151): loop over the batch, stack, alpha from the DETACHED final_T,
     depth normalised by alpha.clamp(0.05, 1).  `intrinsics_host` (list of (fx,fy,cx,cy)) avoids the reference's
     four `.item()` device syncs per view when the caller already has them on the host."""
@@ -90,7 +92,7 @@ def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, in
         else:
             fx, fy, cx, cy = K[b, 0, 0].item(), K[b, 1, 1].item(), K[b, 0, 2].item(), K[b, 1, 2].item()
         o = render(width, height, fx, fy, cx, cy, Rt[b], preds["primpos"][b], preds["primqvec"][b],
-                   preds["primscale"][b], preds["opacity"][b], preds["color"][b], return_depth=True, fused=fused)
+                   preds["primscale"][b], preds["opacity"][b], preds["color"][b], return_depth=True, fused=fused, capacity=capacity)
         rgbs.append(o["render"])
         Ts.append(o["final_T"].detach())
         depths.append(o["depth"])

@@ -120,6 +120,21 @@ int gb_splat_grad_unpack(int G, const float* v_colors4, const float* v_opac_eff,
                          const float* compensation, float* v_colors3, float* v_opacity, float* v_comp, float* v_depth,
                          void* stream);
 
+/* ---- sync-free ("_dn": device-side n) variants: the intersection count stays on the device (n_dev = last element of
+ * cum_tiles_hit), buffers hold `cap` intersections, *overflow is set when the true count exceeds cap.  They remove
+ * the host synchronisation the reference performs (gsplat utils: cum_tiles_hit[-1].item()) and make the whole render
+ * capturable in a CUDA graph. */
+int gb_map_gaussian_to_intersects_dn(int G, const float* xys, const float* depths, const int32_t* radii,
+                                     const int32_t* cum_tiles_hit, int img_h, int img_w, int block_width, int64_t cap,
+                                     int64_t* isect_ids, int32_t* gaussian_ids, void* stream);
+int gb_sort_intersects_dn(int64_t cap, const int32_t* n_dev, const int64_t* isect_ids, const int32_t* gaussian_ids,
+                          int64_t* isect_sorted, int32_t* gids_sorted, int key_bits, void* workspace, void* stream);
+int gb_get_tile_bin_edges_dn(int64_t cap, const int32_t* n_dev, const int64_t* isect_sorted, int32_t* tile_bins,
+                             int32_t* overflow, void* stream);
+int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* xys,
+                             const float* conics, const float* colors3, const float* depths, const float* opacity,
+                             const float* compensation, float* records, void* stream);
+
 /* launch order of the tiles, longest list first: order [T] int32 */
 int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
 

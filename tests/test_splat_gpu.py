@@ -400,3 +400,53 @@ def test_fused_render_equals_two_pass_and_bin_cache(cuda):
     L.gb_launch_count_reset()
     i2 = rasterize_gaussians(xys, depths, radii, conics, nth, t["colors"], t["opacity"], s["img_h"], s["img_w"], bw, bg)
     assert L.gb_launch_count() > 6, "binning must be recomputed when depths changed"
+
+
+def test_sync_free_render_and_cuda_graph(cuda):
+    """capacity=N: no host sync, same pixels and gradients as the exact path; overflow is detected; the whole
+    forward+backward can be captured in a CUDA graph and replayed on new inputs."""
+    from goliath_b200.gsplat.fused import check_overflow
+    from goliath_b200.render import render
+
+    kw, bw, mult = CASES["dense96"]
+    s = small_scene(**kw)
+    t = _dev(s, cuda)
+    H, W = s["img_h"], s["img_w"]
+
+    def run(means, capacity):
+        leaves = [means.clone().requires_grad_(), t["quats"].clone().requires_grad_(),
+                  (t["scales"] * mult).clone().requires_grad_(), t["opacity"].clone().requires_grad_(),
+                  t["colors"].clone().requires_grad_()]
+        o = render(W, H, s["fx"], s["fy"], s["cx"], s["cy"], t["viewmat"], *leaves, capacity=capacity)
+        (o["render"].sum() + 1e-3 * o["depth"].sum() + o["alpha"].sum()).backward()
+        return o, [x.grad for x in leaves]
+
+    o_ref, g_ref = run(t["means3d"], None)
+    o_sf, g_sf = run(t["means3d"], 1 << 16)
+    assert not check_overflow(cuda)
+    for k in ("render", "depth", "alpha"):
+        assert torch.equal(o_ref[k], o_sf[k]), k
+    for a_, b_ in zip(g_ref, g_sf):
+        assert_close(t2n(b_), t2n(a_), rtol=1e-4, atol=2e-5 * float(a_.abs().max()), frac=0.999, what="sync-free grads")
+    # too small a capacity is reported, not silently ignored
+    run(t["means3d"], 64)
+    assert check_overflow(cuda) and not check_overflow(cuda)
+
+    # CUDA graph: static input buffer, capture forward + backward, replay with other content
+    static_means = t["means3d"].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            run(static_means, 1 << 16)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o_g, g_g = run(static_means, 1 << 16)
+    shifted = t["means3d"] + torch.tensor([3.0, -2.0, 1.0], device=cuda)
+    static_means.copy_(shifted)
+    graph.replay()
+    torch.cuda.synchronize()
+    o_e, g_e = run(shifted, None)
+    assert torch.equal(o_g["render"], o_e["render"]) and torch.equal(o_g["alpha"], o_e["alpha"])
+    assert_close(t2n(g_g[0]), t2n(g_e[0]), rtol=1e-4, atol=2e-5 * float(g_e[0].abs().max()), frac=0.999, what="graph grads")
