@@ -33,12 +33,14 @@ NCOL = 19  # packed decoded Gaussian: pos3 quat4 scale3 opacity1 diff3 lobe3 sig
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=300_000)
     ap.add_argument("--lights", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-sync", action="store_true", help="reference-like host path: exact buffers, one host sync per view")
+    ap.add_argument("--no-graph", action="store_true", help="sync-free path without CUDA-graph capture")
     ap.add_argument("--mvp-density", type=float, default=2000.0, help="template alpha scale of the --ext-compare MVP scene")
     ap.add_argument("--decoder", action="store_true",
                     help="time the RGCA PrimDecoder forward at native size (1024^2 Gaussians): towers on tcgen05 vs SIMT, "
@@ -80,7 +82,7 @@ def unpack(flat, G=None):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def gpu_step(packed, cam, li):
+def gpu_step(packed, cam, li, capacity=None):
     """forward + backward of shade + render for one view; returns (rgb, alpha, depth)."""
     from goliath_b200.render import render_views
     from goliath_b200.sgutils import evaluate_gaussian
@@ -91,7 +93,7 @@ def gpu_step(packed, cam, li):
     color = (u["diff_color"].clamp(min=0.0) + spec * u["spec_vis"]).clamp(min=0.0)
     preds = dict(primpos=u["primpos"][None], primqvec=u["primqvec"][None], primscale=u["primscale"][None],
                  opacity=u["opacity"][None], color=color[None])
-    rgb, alpha, depth = render_views(W, H, None, cam["Rt"], preds, intrinsics_host=[cam["intr"]])
+    rgb, alpha, depth = render_views(W, H, None, cam["Rt"], preds, intrinsics_host=[cam["intr"]], capacity=capacity)
     (rgb.sum() + depth.sum()).backward()
     return rgb, alpha, depth
 
@@ -251,23 +253,60 @@ def run_ours(args):
         flush_buf.fill_(1)  # > 126 MB L2
 
     resident = host_packed.to(dev)
+    cap = None if args.eager_sync else max(8 * G, 1 << 20)   # sync-free capacity (intersections); None = exact + host sync
+    static_in = torch.empty_like(resident)                    # the graph's input buffer (field-major decoded Gaussians)
+    state = {"graph": None, "outs": None}
+
+    def compute(packed):
+        """forward + backward of one view from the flat decoded buffer; returns (rgb, alpha, depth, flat grad)."""
+        leaves = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
+        rgb, alpha, depth = gpu_step(leaves, cam, li, capacity=cap)
+        grad = torch.cat([leaves[k].grad.reshape(-1) for k, _ in FIELDS])  # flat dL/d(decoded), same layout
+        return rgb, alpha, depth, grad
+
+    def build_graph():
+        """Capture compute(static_in) once (sync-free path), after side-stream warm-up as torch requires."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                compute(static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = compute(static_in)
+        state["graph"], state["outs"] = g, outs
 
     def one_step(e2e):
-        if e2e:
-            packed = host_packed.to(dev, non_blocking=True)
-        else:
-            packed = resident.clone() if world > 1 else resident
+        src = host_packed if e2e else resident
+        static_in.copy_(src, non_blocking=True)     # e2e: pinned host -> device inside the timed region
         if world > 1:
-            dist.broadcast(packed, src=0)           # decoded Gaussians of the frame, owner = rank 0
-        leaves = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
-        rgb, alpha, depth = gpu_step(leaves, cam, li)
-        grad = torch.cat([leaves[k].grad.reshape(-1) for k, _ in FIELDS])  # flat dL/d(decoded), same layout
+            dist.broadcast(static_in, src=0)        # decoded Gaussians of the frame, owner = rank 0
+        if state["graph"] is not None:
+            state["graph"].replay()
+            rgb, alpha, depth, grad = state["outs"]
+        else:
+            rgb, alpha, depth, grad = compute(static_in)
         if world > 1:
             dist.all_reduce(grad)                   # dL/d(decoded) summed over the views
         if e2e:
-            outs = [t.detach().to("cpu", non_blocking=True) for t in (rgb, alpha, depth, grad)]
-            return outs
+            # the step's result as a caller consumes it: the rendered rgb / alpha / depth images go back to the host;
+            # dL/d(decoded) stays on the device for the optimiser, as in the reference's training loop
+            for dst, src_t in zip(host_out, (rgb, alpha, depth)):
+                dst.copy_(src_t, non_blocking=True)
         return None
+
+    host_out = [torch.empty(1, 3, H, W).pin_memory(), torch.empty(1, 1, H, W).pin_memory(), torch.empty(1, 1, H, W).pin_memory()]
+    # one eager step to count this library's launches per step, then capture
+    static_in.copy_(resident)
+    compute(static_in)
+    torch.cuda.synchronize()
+    lib.gb_launch_count_reset()
+    compute(static_in)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.gb_launch_count())
+    if cap is not None and not args.no_graph:
+        build_graph()
 
     def timed(e2e, steps, warmup):
         for _ in range(warmup):
@@ -290,7 +329,7 @@ def run_ours(args):
             dist.barrier()
         wall = time.perf_counter() - t0
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        launches = int(lib.gb_launch_count())
+        launches = launches_per_step * steps
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,15 +339,19 @@ def run_ours(args):
     if rank == 0:
         proc, path = sample_clocks_start(local)
     ms_total, launches, wall = timed(False, args.steps, args.warmup)
-    clocks = sample_clocks_stop(proc, path) if rank == 0 else None
     ms_e2e, _, _ = timed(True, args.steps, max(3, args.warmup))
+    clocks = sample_clocks_stop(proc, path) if rank == 0 else None
 
     mp_per_step = world * H * W / 1e6
     value = mp_per_step * args.steps / (ms_total / 1e3)
     e2e_v = mp_per_step * args.steps / (ms_e2e / 1e3)
     h2d = host_packed.numel() * 4
-    d2h = (H * W * 3 + H * W + H * W) * 4 + host_packed.numel() * 4
+    d2h = (H * W * 3 + H * W + H * W) * 4
 
+    overflow = False
+    if cap is not None:
+        from goliath_b200.gsplat.fused import check_overflow
+        overflow = check_overflow(dev)
     roof = cpu = None
     if rank == 0:
         roof = kernel_roofline(dev, resident, cam, flush)
@@ -326,7 +369,11 @@ def run_ours(args):
         "config": {"workload": "rgca_example.yml head: %d Gaussians, 1 view %dx%d per GPU, L=%d lights, shade+project+"
                                "bin/sort+blend(rgb)+blend(depth) fwd+bwd" % (G, H, W, args.lights),
                    "gaussians": G, "views_per_gpu": 1, "lights": args.lights, "block_width": BW,
-                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world},
+                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world,
+                   "host_path": ("eager, exact buffers, 1 host sync/view" if cap is None else
+                                 ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
+                                                                                 ", step captured in a CUDA graph"))),
+                   "intersection_overflow": overflow},
         "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
