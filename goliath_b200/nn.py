@@ -94,6 +94,124 @@ class ConvTranspose2dWNUB(nn.Module):
         return _Deconv4x4s2WNUB.apply(input, self.weight_v, self.weight_g, self.bias, slope)
 
 
+class _ConvS1WN(Function):
+    """stride-1 KxK conv + weight-norm scale + tied/untied bias [+ LeakyReLU], csrc/conv_wnub.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight_v, weight_g, bias, slope):
+        x, weight_v = x.contiguous(), weight_v.contiguous()
+        _lib.check_input(x, "input")
+        _lib.check_input(weight_v, "weight_v")
+        B, Cin, H, W = x.shape
+        Cout, K = weight_v.shape[0], weight_v.shape[2]
+        if weight_v.shape != (Cout, Cin, K, K) or K not in (1, 3):
+            raise RuntimeError("weight_v must be [Cout, Cin, K, K] with K in (1, 3)")
+        mode = 0
+        b = None
+        if bias is not None:
+            b = bias.contiguous()
+            if b.shape == (Cout,):
+                mode = 1
+            elif b.shape == (Cout, H, W):
+                mode = 2
+            else:
+                raise RuntimeError("bias must be [Cout] or [Cout, H, W]")
+        scale = (weight_g.reshape(-1) / weight_v.norm()).contiguous()
+        out = torch.empty(B, Cout, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().gb_conv2d_wnub_fwd(
+                B, Cin, Cout, H, W, K, _lib.ptr(x), _lib.ptr(weight_v), _lib.ptr(scale), _lib.ptr(b), mode,
+                float(slope if slope is not None else 1.0), int(slope is not None), _lib.ptr(out),
+                _lib.stream_ptr(x.device)), "conv2d_wnub_fwd")
+        ctx.save_for_backward(x, weight_v, weight_g, out)
+        ctx.slope, ctx.mode = slope, mode
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, v, g, out = ctx.saved_tensors
+        B, Cin, H, W = x.shape
+        Cout, K = v.shape[0], v.shape[2]
+        dev = x.device
+        gout = gout.contiguous()
+        vnorm = v.norm()
+        scale = (g.reshape(-1) / vnorm).contiguous()
+        gz = torch.empty_like(out)
+        gb = None
+        if ctx.mode == 1:
+            gb = torch.zeros(Cout, device=dev, dtype=torch.float32)
+        elif ctx.mode == 2:
+            gb = torch.empty(Cout, H, W, device=dev, dtype=torch.float32)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.zeros_like(v)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gb_conv2d_wnub_bwd(
+                B, Cin, Cout, H, W, K, _lib.ptr(x), _lib.ptr(v), _lib.ptr(scale), _lib.ptr(out), _lib.ptr(gout),
+                float(ctx.slope if ctx.slope is not None else 1.0), int(ctx.slope is not None), ctx.mode, _lib.ptr(gz),
+                _lib.ptr(gb), _lib.ptr(gx), _lib.ptr(gw), _lib.stream_ptr(dev)), "conv2d_wnub_bwd")
+        # weight-norm chain rule, g per OUTPUT channel (dim 0), norm over the whole tensor
+        w = g * v / vnorm
+        gg = (gw * v).sum(dim=(1, 2, 3), keepdim=True) / vnorm
+        gv = g * gw / vnorm - (gw * w).sum() * v / (vnorm * vnorm)
+        return gx, gv, gg.view_as(g), gb, None
+
+
+class Conv2dWNUB(nn.Module):
+    """Conv2d (stride 1, k in {1,3}, "same" padding) with weight norm and untied bias (layers.py:276-327,472).
+    Constructor argument order is the reference's: (in, out, height, width, kernel_size, stride, padding)."""
+
+    def __init__(self, in_channels, out_channels, height, width, kernel_size=3, stride=1, padding=1, bias=True):
+        super().__init__()
+        if stride != 1 or kernel_size not in (1, 3) or padding != (kernel_size - 1) // 2:
+            raise NotImplementedError("the fused kernel covers the hand-MVP decoders' stride-1 'same' 1x1 / 3x3 layers")
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, (kernel_size, kernel_size)
+        self.weight_v = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+        self.weight_g = nn.Parameter(torch.ones(out_channels, 1, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(out_channels, height, width)) if bias else None
+        self.fused_slope: Optional[float] = None
+        nn.init.kaiming_uniform_(self.weight_v, a=math.sqrt(5))
+        with torch.no_grad():
+            self.weight_g.fill_(float(self.weight_v.norm()))
+
+    @property
+    def weight(self):
+        return self.weight_g * self.weight_v / self.weight_v.norm()
+
+    def forward(self, input, slope: Optional[float] = None):
+        slope = self.fused_slope if slope is None else slope
+        return _ConvS1WN.apply(input, self.weight_v, self.weight_g, self.bias, slope)
+
+
+class Conv2dWN(Conv2dWNUB):
+    """th.nn.Conv2d with the reference's weight norm and a tied bias [Cout] (layers.py:470; ConvBlock.conv_resize)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=0, bias=True):
+        super().__init__(in_channels, out_channels, 1, 1, kernel_size, stride, padding, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+
+def tile2d(x, size: int):
+    """[N,F] -> [N,F,size,size] (blocks.py:731-743)."""
+    return x[:, :, None, None].expand(-1, -1, size, size)
+
+
+class ConvBlock(nn.Module):
+    """blocks.py:232-280: 1x1 Conv2dWN skip + two Conv2dWNUB with LeakyReLU (fused into the conv kernels)."""
+
+    def __init__(self, in_channels, out_channels, size, lrelu_slope=0.2, kernel_size=3, padding=1, wnorm_dim=0):
+        super().__init__()
+        assert wnorm_dim == 0
+        self.conv_resize = Conv2dWN(in_channels, out_channels, kernel_size=1)
+        self.conv1 = Conv2dWNUB(in_channels, in_channels, size, size, kernel_size, 1, padding)
+        self.conv2 = Conv2dWNUB(in_channels, out_channels, size, size, kernel_size, 1, padding)
+        self.conv1.fused_slope = self.conv2.fused_slope = float(lrelu_slope)
+        self.lrelu1, self.lrelu2 = FusedLeakyReLU(), FusedLeakyReLU()
+
+    def forward(self, x):
+        x_skip = self.conv_resize(x)
+        return self.conv2(self.conv1(x)) + x_skip
+
+
 class LinearWN(nn.Module):
     """nn.Linear with the reference's weight norm (layers.py:468): weight_g [out,1], weight_v [out,in]."""
 
@@ -199,3 +317,31 @@ def make_linear(n_in, n_out, mode, act=None, bias=True):
     if act is not None:
         layers.append(act)
     return layers
+
+
+def glorot(m: nn.Module, alpha: float = 1.0) -> None:
+    """Initialisation used by the decoders (layers.py:605-650): uniform with the Glorot std scaled for a LeakyReLU of
+    slope `alpha`; a stride-2 transposed kernel gets its four sub-pixel phases tied at init; bias zero.  For the
+    weight-normalised layers of this module the direction tensor receives the sample and g its Frobenius norm, i.e.
+    the effective weight equals the sample."""
+    gain = math.sqrt(2.0 / (1.0 + alpha ** 2))
+    if isinstance(m, (Conv2dWNUB,)):
+        k = m.kernel_size[0] * m.kernel_size[1]
+        fan = (m.in_channels + m.out_channels) * k
+    elif isinstance(m, ConvTranspose2dWNUB):
+        fan = (m.in_channels + m.out_channels) * 4  # 4x4 kernel, stride 2: k*k // 4
+    elif isinstance(m, LinearWN):
+        fan = m.weight_v.shape[0] + m.weight_v.shape[1]
+    else:
+        return
+    bound = gain * math.sqrt(2.0 / fan) * math.sqrt(3.0)
+    with torch.no_grad():
+        m.weight_v.uniform_(-bound, bound)
+        if isinstance(m, ConvTranspose2dWNUB):
+            base = m.weight_v[:, :, 0::2, 0::2].clone()
+            m.weight_v[:, :, 0::2, 1::2] = base
+            m.weight_v[:, :, 1::2, 0::2] = base
+            m.weight_v[:, :, 1::2, 1::2] = base
+        m.weight_g.fill_(float(m.weight_v.norm()))
+        if m.bias is not None:
+            m.bias.zero_()

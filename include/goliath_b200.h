@@ -239,6 +239,44 @@ int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, int Wi,
                           const float* v, float* w_scratch, const float* scale, const float* bias, float slope,
                           int apply_act, float* out_hi, float* out_lo, int ldc, float* out_nchw, void* stream);
 
+/* ---------------------------------------------------------------- hand-MVP decoders (row R8) */
+
+/* replaces conv2d + bias add (+ LeakyReLU) of la.Conv2dWNUB / Conv2dWN (ca_code/nn/layers.py:276-327,468-472;
+ * users: hand_mvp.py:297-321 TransDecoder, hand_mvp.py:269-294 PoseEncoder via blocks.py:232-280 ConvBlock), stride 1,
+ * K = 1 or 3, padding (K-1)/2, with the weight-norm scale folded in: out = act(scale[co] * conv(x, v) + bias).
+ * x [B,Cin,H,W], v [Cout,Cin,K,K], scale [Cout] = g / ||v||_F; bias_mode 0 none, 1 tied [Cout], 2 untied [Cout,H,W]. */
+int gb_conv2d_wnub_fwd(int B, int Cin, int Cout, int H, int W, int K, const float* x, const float* v, const float* scale,
+                       const float* bias, int bias_mode, float slope, int apply_act, float* out, void* stream);
+
+/* backward of the above.  gz [B,Cout,H,W] scratch; g_bias: [Cout,H,W] written (mode 2) or [Cout] ACCUMULATED (mode 1,
+ * caller zeroes) or NULL; gx [B,Cin,H,W] or NULL; gw [Cout,Cin,K,K] = dL/d(effective weight at unit scale),
+ * ACCUMULATED (caller zeroes it and applies the weight-norm chain rule). */
+int gb_conv2d_wnub_bwd(int B, int Cin, int Cout, int H, int W, int K, const float* x, const float* v, const float* scale,
+                       const float* out, const float* gout, float slope, int apply_act, int bias_mode, float* gz,
+                       float* g_bias, float* gx, float* gw, void* stream);
+
+/* replaces the slab -> primitive-template sequence: relu(25*rgb+100) (hand_mvp.py:472), relu(alpha) (:434),
+ * cat/view/permute/reshape (hand_mvp.py:172-185) and the valid-primitive gather (ca_code/utils/render_raymarcher.py:44-46)
+ * with one pass.  rgb [B,PZ,3,U,U], alpha [B,PZ,1,U,U]; prim_slot [(U/PSY)*(U/PSX)] i32 (slot of a primitive in the
+ * output, -1 = dropped) or NULL; tpl [B,Kout,PZ,PSY,PSX,4].  rgb_mul/rgb_add/apply_relu carry the output activation
+ * (1, 0, 0 for a plain re-layout of already-activated slabs). */
+int gb_mvp_slab_to_prims_fwd(int B, int PZ, int U, int PSX, int PSY, int Kout, const float* rgb, const float* alpha,
+                             const int* prim_slot, float rgb_mul, float rgb_add, int apply_relu, float* tpl,
+                             void* stream);
+int gb_mvp_slab_to_prims_bwd(int B, int PZ, int U, int PSX, int PSY, int Kout, const float* rgb, const float* alpha,
+                             const int* prim_slot, float rgb_mul, float rgb_add, int apply_relu, const float* g_tpl,
+                             float* g_rgb, float* g_alpha, void* stream);
+
+/* replaces TransDecoder's head scaling (hand_mvp.py:317-321) + GeomDecoder's transform composition
+ * (hand_mvp.py:410-425, axisangle_to_matrix :477-510).  dec [B,9,K] (dec0 output viewed [B,9,64*64]);
+ * posbase [B,K,3], rotbase [B,K,3,3]; zero_delta = the `iteration < primposstart` warm start (:412-415). */
+int gb_mvp_prim_transform_fwd(int B, int K, const float* dec, const float* posbase, const float* rotbase,
+                              float prim_scale, int zero_delta, float* primpos, float* primrot, float* primscale,
+                              void* stream);
+int gb_mvp_prim_transform_bwd(int B, int K, const float* dec, const float* posbase, const float* rotbase,
+                              float prim_scale, int zero_delta, const float* g_primpos, const float* g_primrot,
+                              const float* g_primscale, float* g_dec, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
