@@ -108,6 +108,168 @@ __global__ void __launch_bounds__(TQ* TQ) deconv4x4s2_fwd_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide variant for the high-resolution layers (Cin <= 32: 32->16 @512^2, 16->125 @1024^2 in the RGCA towers, every
+// layer of the hand-MVP content decoders).  ncu on the kernel above at 16->125 @1024^2: 720 M warp instructions for
+// 262 M FFMA-equivalents (shared-memory operand loads, per-co-block input re-staging), 1.07 ms, 13 % of DRAM peak,
+// and the epilogue's untied-bias loads sit exposed at the end of every CTA.  Here:
+//  * a thread owns TWO horizontally adjacent quads (4 consecutive output columns x 2 rows -> 16-byte bias loads/stores);
+//  * output channels are processed in PAIRS with the packed FFMA2 instruction (fma.rn.f32x2): the x operand is stored
+//    duplicated in shared memory, the weights as [ci][tap][co] so that a channel pair is one 64-bit operand;
+//  * the input tile is staged once per CTA and reused for several blocks of output channels;
+//  * the bias of a block is loaded into registers BEFORE its FMA loop (4 channels per block keep that affordable)
+//    and its lines are pulled into L2 one block ahead, so no warp waits on HBM in the epilogue.
+constexpr int WQ_X = 32, WQ_Y = 16;       // input positions per CTA: 16 rows x 32 columns (256 threads x 2 quads)
+constexpr int W_CO = 4, W_CI = 16;
+constexpr int W_HX = WQ_X + 2, W_HY = WQ_Y + 2, W_HS = 36;  // halo tile; row stride in float2 (rows 16-byte aligned)
+
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 2) deconv4x4s2_fwd_wide_kernel(
+    int Cin, int Cout, int Hi, int Wi, int co_blocks_per_cta, const float* __restrict__ x, const float* __restrict__ v,
+    const float* __restrict__ scale, const float* __restrict__ bias, float slope, int apply_act,
+    float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char wsm[];
+  float2* s_x = reinterpret_cast<float2*>(wsm);                                 // [W_CI][W_HY][W_HS] (a, a)
+  float* s_w = reinterpret_cast<float*>(wsm + (size_t)W_CI * W_HY * W_HS * 8);  // [W_CI][16][W_CO]
+  const int tiles_x = (Wi + WQ_X - 1) / WQ_X;
+  const int ty0 = (blockIdx.x / tiles_x) * WQ_Y, tx0 = (blockIdx.x % tiles_x) * WQ_X;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x, qy = tid >> 4, qx = tid & 15;
+  const int m = ty0 + qy, n = tx0 + 2 * qx;  // first of the thread's two positions
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const float* xb = x + (size_t)b * Cin * Hi * Wi;
+  const int nblk = (Cout + W_CO - 1) / W_CO;
+  const int blk0 = blockIdx.y * co_blocks_per_cta, blk1 = min(nblk, blk0 + co_blocks_per_cta);
+  const bool single_chunk = Cin <= W_CI;
+  const bool inside = m < Hi && n < Wi;  // Wi and n are even: both positions are inside together
+
+  auto stage_x = [&](int ci0) {
+    for (int i = tid; i < W_CI * W_HY * W_HX; i += 256) {
+      const int ci = i / (W_HY * W_HX), r = (i / W_HX) % W_HY, c = i % W_HX;
+      const int yy = ty0 - 1 + r, xx = tx0 - 1 + c;
+      float val = 0.f;
+      if (ci0 + ci < Cin && yy >= 0 && yy < Hi && xx >= 0 && xx < Wi) val = xb[((size_t)(ci0 + ci) * Hi + yy) * Wi + xx];
+      s_x[(ci * W_HY + r) * W_HS + c] = make_float2(val, val);
+    }
+  };
+  auto prefetch_bias = [&](int blk) {
+    if (!bias || !inside || blk >= blk1) return;
+#pragma unroll
+    for (int c = 0; c < W_CO; ++c) {
+      if (blk * W_CO + c < Cout) {
+        const float* bp = bias + ((size_t)(blk * W_CO + c) * Ho + 2 * m) * Wo + 2 * n;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(bp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + Wo));
+      }
+    }
+  };
+  prefetch_bias(blk0);
+  if (single_chunk) stage_x(0);
+
+  for (int blk = blk0; blk < blk1; ++blk) {
+    const int co0 = blk * W_CO;
+    prefetch_bias(blk + 1);
+    float4 b4[W_CO][2];  // this block's bias, in flight during the FMA loop
+#pragma unroll
+    for (int c = 0; c < W_CO; ++c)
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        b4[c][row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && inside && co0 + c < Cout)
+          b4[c][row] = gb::ld_nc_f4(reinterpret_cast<const float4*>(bias + ((size_t)(co0 + c) * Ho + 2 * m + row) * Wo + 2 * n));
+      }
+    unsigned long long acc[2][2][4];  // [co pair][quad][j], j = 2 * row + column inside the quad
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[cp][q][j] = 0ull;
+
+    for (int ci0 = 0; ci0 < Cin; ci0 += W_CI) {
+      __syncthreads();  // previous users of s_w (and s_x when re-staged) are done
+      if (!single_chunk) stage_x(ci0);
+      for (int i = tid; i < W_CI * 16 * W_CO; i += 256) {
+        const int ci = i / (16 * W_CO), k = (i / W_CO) % 16, co = i % W_CO;
+        float val = 0.f;
+        if (ci0 + ci < Cin && co0 + co < Cout) val = v[((size_t)(ci0 + ci) * Cout + (co0 + co)) * 16 + k];
+        s_w[i] = val;
+      }
+      __syncthreads();
+      const int nci = min(W_CI, Cin - ci0);
+      for (int ci = 0; ci < nci; ++ci) {
+        unsigned long long X[3][4];  // rows m-1..m+1, columns n-1..n+2, each value duplicated (a, a)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(&s_x[(ci * W_HY + qy + r) * W_HS + 2 * qx]);
+          const ulonglong2 x01 = xp[0], x23 = xp[1];
+          X[r][0] = x01.x; X[r][1] = x01.y; X[r][2] = x23.x; X[r][3] = x23.y;
+        }
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_w + (size_t)ci * 16 * W_CO);
+        // one tap = the weights of 4 output channels (one 16-byte broadcast load) feeding one output of each quad
+#define GB_TAP(ky, kx, j, r, c)                                      \
+  {                                                                  \
+    const ulonglong2 wa = wp[(ky) * 4 + (kx)];                       \
+    _Pragma("unroll") for (int q = 0; q < 2; ++q) {                  \
+      acc[0][q][j] = ffma2(X[r][(c) + q], wa.x, acc[0][q][j]);       \
+      acc[1][q][j] = ffma2(X[r][(c) + q], wa.y, acc[1][q][j]);       \
+    }                                                                \
+  }
+        // out(2m  ,2n  ): x(m,n) w11 + x(m,n-1) w13 + x(m-1,n) w31 + x(m-1,n-1) w33
+        GB_TAP(1, 1, 0, 1, 1) GB_TAP(1, 3, 0, 1, 0) GB_TAP(3, 1, 0, 0, 1) GB_TAP(3, 3, 0, 0, 0)
+        // out(2m  ,2n+1): x(m,n+1) w10 + x(m,n) w12 + x(m-1,n+1) w30 + x(m-1,n) w32
+        GB_TAP(1, 0, 1, 1, 2) GB_TAP(1, 2, 1, 1, 1) GB_TAP(3, 0, 1, 0, 2) GB_TAP(3, 2, 1, 0, 1)
+        // out(2m+1,2n  ): x(m+1,n) w01 + x(m+1,n-1) w03 + x(m,n) w21 + x(m,n-1) w23
+        GB_TAP(0, 1, 2, 2, 1) GB_TAP(0, 3, 2, 2, 0) GB_TAP(2, 1, 2, 1, 1) GB_TAP(2, 3, 2, 1, 0)
+        // out(2m+1,2n+1): x(m+1,n+1) w00 + x(m+1,n) w02 + x(m,n+1) w20 + x(m,n) w22
+        GB_TAP(0, 0, 3, 2, 2) GB_TAP(0, 2, 3, 2, 1) GB_TAP(2, 0, 3, 1, 2) GB_TAP(2, 2, 3, 1, 1)
+#undef GB_TAP
+      }
+    }
+    if (inside) {
+      float* ob = out + (size_t)b * Cout * Ho * Wo;
+#pragma unroll
+      for (int cp = 0; cp < 2; ++cp) {
+        float o[2][2][4];  // [co parity][row][x]
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 pr = unpack2(acc[cp][q][j]);
+            o[0][j >> 1][2 * q + (j & 1)] = pr.x;
+            o[1][j >> 1][2 * q + (j & 1)] = pr.y;
+          }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 2 * cp + h, co = co0 + c;
+          if (co >= Cout) continue;
+          const float sc = scale[co];
+#pragma unroll
+          for (int row = 0; row < 2; ++row) {
+            float4 r4 = make_float4(o[h][row][0] * sc + b4[c][row].x, o[h][row][1] * sc + b4[c][row].y,
+                                    o[h][row][2] * sc + b4[c][row].z, o[h][row][3] * sc + b4[c][row].w);
+            if (apply_act) {
+              r4.x = r4.x > 0.f ? r4.x : r4.x * slope; r4.y = r4.y > 0.f ? r4.y : r4.y * slope;
+              r4.z = r4.z > 0.f ? r4.z : r4.z * slope; r4.w = r4.w > 0.f ? r4.w : r4.w * slope;
+            }
+            *reinterpret_cast<float4*>(ob + ((size_t)co * Ho + 2 * m + row) * Wo + 2 * n) = r4;
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // Fused ConvTranspose2dWNUB(k=4, s=2, p=1) [+ LeakyReLU] forward.  x [B,Cin,Hi,Wi], v = weight_v [Cin,Cout,4,4],
@@ -117,6 +279,25 @@ GB_API int gb_deconv4x4s2_wnub_fwd(int B, int Cin, int Cout, int Hi, int Wi, con
                                    const float* scale, const float* bias, float slope, int apply_act, float* out,
                                    void* stream) {
   if (B <= 0 || Cin <= 0 || Cout <= 0 || Hi <= 0 || Wi <= 0) return 0;
+  if (Cin <= 32 && Wi % 2 == 0 && Wi >= 32 && Hi >= 16) {
+    // high-resolution layers: wide FFMA2 kernel, several blocks of output channels per staged input tile
+    const int tiles = gb::cdiv(Hi, WQ_Y) * gb::cdiv(Wi, WQ_X);
+    const int nblk = gb::cdiv(Cout, W_CO);
+    int per_cta = 1;  // grow while the grid still fills the machine a few times over
+    while (per_cta < nblk && (long long)tiles * B * gb::cdiv(nblk, per_cta * 2) >= 4LL * 2 * gb::kNumSMs) per_cta *= 2;
+    const size_t smem = (size_t)W_CI * W_HY * W_HS * 8 + (size_t)W_CI * 16 * W_CO * 4;
+    static bool configured = false;
+    if (!configured) {
+      GB_CUDA(cudaFuncSetAttribute(deconv4x4s2_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    dim3 grid(tiles, gb::cdiv(nblk, per_cta), B);
+    deconv4x4s2_fwd_wide_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Cin, Cout, Hi, Wi, per_cta, x, v, scale, bias,
+                                                                           slope, apply_act, out);
+    gb::count_launches(1);
+    GB_CHECK_LAUNCH();
+    return 0;
+  }
   const int tiles = gb::cdiv(Hi, TQ) * gb::cdiv(Wi, TQ);
   dim3 grid(tiles, gb::cdiv(Cout, CO_T), B);
   deconv4x4s2_fwd_kernel<<<grid, TQ * TQ, 0, (cudaStream_t)stream>>>(Cin, Cout, Hi, Wi, x, v, scale, bias, slope, apply_act, out);
