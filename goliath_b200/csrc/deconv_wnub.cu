@@ -128,6 +128,10 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(valid ? 4 : 0) : "memory");
+}
 __device__ __forceinline__ float2 unpack2(unsigned long long v) {
   float2 r;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) deconv4x4s2_fwd_wide_kernel(
     float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char wsm[];
   float2* s_x = reinterpret_cast<float2*>(wsm);                                 // [W_CI][W_HY][W_HS] (a, a)
-  float* s_w = reinterpret_cast<float*>(wsm + (size_t)W_CI * W_HY * W_HS * 8);  // [W_CI][16][W_CO]
+  float* s_w = reinterpret_cast<float*>(wsm + (size_t)W_CI * W_HY * W_HS * 8);  // [2][W_CI][16][W_CO]
   const int tiles_x = (Wi + WQ_X - 1) / WQ_X;
   const int ty0 = (blockIdx.x / tiles_x) * WQ_Y, tx0 = (blockIdx.x % tiles_x) * WQ_X;
   const int b = blockIdx.z;
@@ -153,13 +157,26 @@ __global__ void __launch_bounds__(256, 2) deconv4x4s2_fwd_wide_kernel(
   const bool single_chunk = Cin <= W_CI;
   const bool inside = m < Hi && n < Wi;  // Wi and n are even: both positions are inside together
 
+  // all staging is asynchronous (cp.async, 4-byte granules: the layouts are transposed / duplicated on the fly), so
+  // no warp holds registers across a global-memory round trip; out-of-range elements are zero-filled by src-size 0
   auto stage_x = [&](int ci0) {
     for (int i = tid; i < W_CI * W_HY * W_HX; i += 256) {
       const int ci = i / (W_HY * W_HX), r = (i / W_HX) % W_HY, c = i % W_HX;
       const int yy = ty0 - 1 + r, xx = tx0 - 1 + c;
-      float val = 0.f;
-      if (ci0 + ci < Cin && yy >= 0 && yy < Hi && xx >= 0 && xx < Wi) val = xb[((size_t)(ci0 + ci) * Hi + yy) * Wi + xx];
-      s_x[(ci * W_HY + r) * W_HS + c] = make_float2(val, val);
+      const bool ok = ci0 + ci < Cin && yy >= 0 && yy < Hi && xx >= 0 && xx < Wi;
+      const float* src = ok ? xb + ((size_t)(ci0 + ci) * Hi + yy) * Wi + xx : xb;
+      float2* dst = &s_x[(ci * W_HY + r) * W_HS + c];
+      cp_async4_zfill(&dst->x, src, ok);
+      cp_async4_zfill(&dst->y, src, ok);
+    }
+  };
+  auto stage_w = [&](int buf, int co0, int ci0) {
+    float* dstw = s_w + buf * (W_CI * 16 * W_CO);
+    for (int i = tid; i < W_CI * 16 * W_CO; i += 256) {
+      const int ci = i / (16 * W_CO), co = (i / 16) % W_CO, k = i % 16;  // consecutive lanes read consecutive taps
+      const bool ok = ci0 + ci < Cin && co0 + co < Cout;
+      const float* src = ok ? v + ((size_t)(ci0 + ci) * Cout + (co0 + co)) * 16 + k : v;
+      cp_async4_zfill(dstw + (ci * 16 + k) * W_CO + co, src, ok);
     }
   };
   auto prefetch_bias = [&](int blk) {
@@ -174,7 +191,11 @@ __global__ void __launch_bounds__(256, 2) deconv4x4s2_fwd_wide_kernel(
     }
   };
   prefetch_bias(blk0);
-  if (single_chunk) stage_x(0);
+  if (single_chunk) {
+    stage_x(0);
+    stage_w(0, blk0 * W_CO, 0);
+    gb::cp_async_commit();
+  }
 
   for (int blk = blk0; blk < blk1; ++blk) {
     const int co0 = blk * W_CO;
@@ -197,16 +218,27 @@ __global__ void __launch_bounds__(256, 2) deconv4x4s2_fwd_wide_kernel(
         for (int j = 0; j < 4; ++j) acc[cp][q][j] = 0ull;
 
     for (int ci0 = 0; ci0 < Cin; ci0 += W_CI) {
-      __syncthreads();  // previous users of s_w (and s_x when re-staged) are done
-      if (!single_chunk) stage_x(ci0);
-      for (int i = tid; i < W_CI * 16 * W_CO; i += 256) {
-        const int ci = i / (16 * W_CO), k = (i / W_CO) % 16, co = i % W_CO;
-        float val = 0.f;
-        if (ci0 + ci < Cin && co0 + co < Cout) val = v[((size_t)(ci0 + ci) * Cout + (co0 + co)) * 16 + k];
-        s_w[i] = val;
+      int buf = 0;
+      if (single_chunk) {
+        // weights of this block were issued one block ago into buffer (blk - blk0) & 1; the x tile at kernel start
+        buf = (blk - blk0) & 1;
+        gb::cp_async_wait<0>();
+        __syncthreads();  // everybody's copies have landed, everybody left the previous block's FMA loop
+        if (blk + 1 < blk1) {
+          stage_w(buf ^ 1, (blk + 1) * W_CO, 0);
+          gb::cp_async_commit();
+        }
+      } else {
+        __syncthreads();  // previous users of s_x / s_w are done
+        stage_x(ci0);
+        stage_w(0, co0, ci0);
+        gb::cp_async_commit();
+        gb::cp_async_wait<0>();
+        __syncthreads();
       }
-      __syncthreads();
+      const float* s_wb = s_w + buf * (W_CI * 16 * W_CO);
       const int nci = min(W_CI, Cin - ci0);
+#pragma unroll 2
       for (int ci = 0; ci < nci; ++ci) {
         unsigned long long X[3][4];  // rows m-1..m+1, columns n-1..n+2, each value duplicated (a, a)
 #pragma unroll
@@ -215,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) deconv4x4s2_fwd_wide_kernel(
           const ulonglong2 x01 = xp[0], x23 = xp[1];
           X[r][0] = x01.x; X[r][1] = x01.y; X[r][2] = x23.x; X[r][3] = x23.y;
         }
-        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_w + (size_t)ci * 16 * W_CO);
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(s_wb + (size_t)ci * 16 * W_CO);
         // one tap = the weights of 4 output channels (one 16-byte broadcast load) feeding one output of each quad
 #define GB_TAP(ky, kx, j, r, c)                                      \
   {                                                                  \
@@ -285,7 +317,7 @@ GB_API int gb_deconv4x4s2_wnub_fwd(int B, int Cin, int Cout, int Hi, int Wi, con
     const int nblk = gb::cdiv(Cout, W_CO);
     int per_cta = 1;  // grow while the grid still fills the machine a few times over
     while (per_cta < nblk && (long long)tiles * B * gb::cdiv(nblk, per_cta * 2) >= 4LL * 2 * gb::kNumSMs) per_cta *= 2;
-    const size_t smem = (size_t)W_CI * W_HY * W_HS * 8 + (size_t)W_CI * 16 * W_CO * 4;
+    const size_t smem = (size_t)W_CI * W_HY * W_HS * 8 + (size_t)2 * W_CI * 16 * W_CO * 4;
     static bool configured = false;
     if (!configured) {
       GB_CUDA(cudaFuncSetAttribute(deconv4x4s2_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
