@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--decoder", action="store_true",
                     help="time the RGCA PrimDecoder forward at native size (1024^2 Gaussians): towers on tcgen05 vs SIMT, "
                          "fused heads kernel; prints its own JSON line")
+    ap.add_argument("--decoder-library", action="store_true",
+                    help="time the same decoder tower the reference's way (library conv_transpose2d + bias + LeakyReLU "
+                         "passes, cuDNN); run under `timeout`: cuDNN may compile engines for minutes on a fresh box")
     ap.add_argument("--ext-compare", action="store_true",
                     help="time the reference's own extensions rebuilt for sm_100a (oracle/_ref) against ours: SG shade, "
                          "raydirs, MVP raymarch (BASELINE config 4 shape); prints its own JSON line")
@@ -485,8 +488,9 @@ def run_decoder(args):
         def vn(self, g): return self.nml
 
     gen = torch.Generator().manual_seed(1)
-    pos = (100 * torch.randn(1, 3, S, S, generator=gen)).to(dev)
-    nml = torch.randn(1, 3, S, S, generator=gen).to(dev)
+    shell = synthetic.head_gaussians(S * S)["means3d"]  # SURVEY.md §8d ellipsoid shell, as the posed-mesh UV map
+    pos = shell.t().reshape(1, 3, S, S).contiguous().to(dev)
+    nml = torch.nn.functional.normalize(shell, dim=1).t().reshape(1, 3, S, S).contiguous().to(dev)
     dec = PrimDecoder(256, Geo(pos, nml), 255 * torch.rand(3, S, S, generator=gen), slabsize=S).to(dev)
     with torch.no_grad():
         for n_, p in dec.named_parameters():
@@ -537,8 +541,102 @@ def run_decoder(args):
         res["last_layer_alg_GBs_simt"] = bytes_last / res["last_layer_ms_simt"] / 1e6
         heads_bytes = S * S * (129 * 4 + 36 + 130)
         res["heads_alg_GBs"] = heads_bytes / res["heads_ms"] / 1e6
+        # (iii) of SURVEY.md §8d: decode + shade + render of one frame/view at native G = 1024^2, inference
+        from goliath_b200.gsplat.fused import check_overflow
+        from goliath_b200.render import render_views
+        cam = synthetic.ring_camera(0, img_h=H, img_w=W)
+        Rt = cam["viewmat"][None].to(dev)
+        intr = [(cam["fx"], cam["fy"], cam["cx"], cam["cy"])]
+        cap = 16 << 20
+
+        def frame():
+            preds = dec(embs, pos, campos, li["light_intensity"], li["light_pos"], light_sh, li["n_lights"])
+            return render_views(W, H, None, Rt, preds, intrinsics_host=intr, capacity=cap)
+
+        res["frame_decode_shade_render_fwd_ms"] = timeit(frame)
+        # the same pieces replayed from CUDA graphs (frozen parameters, static shapes): launch latency removed
+        from goliath_b200.graph import Graphed
+        g_tower = Graphed(lambda: gnn.tower_forward_tc(dec.vnocond_mod, x))
+        res["tower_vnocond_ms_tc_graph"] = timeit(g_tower)
+        g_dec = Graphed(lambda: dec(embs, pos, campos, li["light_intensity"], li["light_pos"], light_sh, li["n_lights"]))
+        res["full_decoder_ms_tc_graph"] = timeit(g_dec)
+        g_frame = Graphed(frame)
+        res["frame_decode_shade_render_fwd_ms_graph"] = timeit(g_frame)
+        res["frame_MP_per_s_fwd_graph"] = H * W / 1e6 / (res["frame_decode_shade_render_fwd_ms_graph"] * 1e-3)
+        res["frame_intersection_overflow_graph"] = bool(check_overflow(dev))
+        # last layer on the tensor cores (pair-phase epilogue), for comparison with the FFMA2 kernel
+        gnn.TC_MIN_CIN = 16
+        for m_ in dec.vnocond_mod:
+            if hasattr(m_, "_tc_cache"):
+                del m_._tc_cache
+        res["last_layer_ms_tc16"] = timeit(lambda: gnn.tower_forward_tc(seq, h5))
+        f1b = gnn.tower_forward_tc(dec.vnocond_mod, x)
+        res["tc16_vs_simt_rel_err"] = float((f1b - g1).norm() / g1.norm())
+        g_tower16 = Graphed(lambda: gnn.tower_forward_tc(dec.vnocond_mod, x))
+        res["tower_vnocond_ms_tc16_graph"] = timeit(g_tower16)
+        gnn.TC_MIN_CIN = 32
+        for m_ in dec.vnocond_mod:
+            if hasattr(m_, "_tc_cache"):
+                del m_._tc_cache
+        res["frame_intersection_overflow"] = bool(check_overflow(dev))
+        res["frame_MP_per_s_fwd"] = H * W / 1e6 / (res["frame_decode_shade_render_fwd_ms"] * 1e-3)
+    # training direction: forward + backward of the big tower through the autograd layers (SIMT kernels, no cuDNN)
+    x_t = x.detach().clone().requires_grad_()
+
+    def tower_train():
+        out = dec.vnocond_mod(x_t)
+        out.backward(torch.ones_like(out))
+        for p_ in dec.vnocond_mod.parameters():
+            p_.grad = None
+
+    res["tower_vnocond_fwd_bwd_ms_simt"] = timeit(tower_train, reps=3, warm=1)
     print(json.dumps({"decoder": res, "config": {"slabsize": S, "params_M": sum(p.numel() for p in dec.parameters()) / 1e6,
                                                  "lights": args.lights}}))
+
+
+def run_decoder_library(args):
+    """The reference's own way of running a decoder tower (ca_code/nn/layers.py:380-396): library transposed
+    convolution (cuDNN, TF32 allowed as by torch's default) + a bias-add pass + a LeakyReLU pass per layer, same weights
+    layout and sizes as `--decoder`.  Separate flag and process because the first cuDNN call may spend minutes in
+    engine compilation on a fresh box: run it under `timeout`."""
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    plan = [256, 256, 128, 128, 64, 32, 16, 125]
+    gen = torch.Generator().manual_seed(1)
+    ws, bs = [], []
+    size = 8
+    for cin, cout in zip(plan[:-1], plan[1:]):
+        size *= 2
+        ws.append((torch.randn(cin, cout, 4, 4, generator=gen) * 0.05).to(dev))
+        bs.append((torch.randn(cout, size, size, generator=gen) * 0.05).to(dev))
+    x = torch.randn(1, 256, 8, 8, generator=gen).to(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def tower(inp):
+        h = inp
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            h = torch.nn.functional.conv_transpose2d(h, w, None, 2, 1) + b[None]
+            if i + 1 < len(ws):
+                h = torch.nn.functional.leaky_relu(h, 0.2)
+        return h
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush_buf.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    res = {"tf32_allowed": bool(torch.backends.cudnn.allow_tf32)}
+    with torch.no_grad():
+        res["tower_vnocond_ms_library"] = timeit(lambda: tower(x))
+        h5 = torch.randn(1, 16, 512, 512, device=dev)
+        res["last_layer_ms_library"] = timeit(lambda: torch.nn.functional.conv_transpose2d(h5, ws[-1], None, 2, 1) + bs[-1][None])
+    print(json.dumps({"decoder_library": res}))
 
 
 # ------------------------------------------------------------------------------------------ extension-level comparison
@@ -642,7 +740,9 @@ def run_ext_compare(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.decoder:
+    if a.decoder_library:
+        run_decoder_library(a)
+    elif a.decoder:
         run_decoder(a)
     elif a.ext_compare:
         run_ext_compare(a)

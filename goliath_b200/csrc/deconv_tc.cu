@@ -86,8 +86,10 @@ __device__ __forceinline__ float to_tf32(float x) {
 
 struct TcArgs {
   int B, Cin, Cout, Npad, Hi, Wi;  // Cin = padded channel count (multiple of 32); Npad = Cout rounded up to 16
+  int Nchunk;                    // output channels per CTA (divides Npad, multiple of 16): grid.z = Npad / Nchunk
   int tile_r, tile_c;            // tile = tile_r rows x tile_c columns of input positions, tile_r * tile_c == 128
   int stages;
+  int pair;                      // 1: the CTA computes both column parities (px = 0, 1) of its row parity
   const float* scale;            // [Cout]
   const float* bias;             // [Cout, 2Hi, 2Wi] or null
   float slope; int apply_act;
@@ -96,21 +98,49 @@ struct TcArgs {
   float* out_nchw;               // NCHW [B,Cout,2Hi,2Wi] fp32, or null
 };
 
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_nc_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+// 16 consecutive channels of one output pixel -> the NHWC hi/lo pair the next tensor-core layer reads
+__device__ __forceinline__ void store_nhwc_split(const TcArgs& a, size_t base, const float (&v)[16]) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { hi[j] = to_tf32(v[j]); lo[j] = v[j] - hi[j]; }
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    *reinterpret_cast<float4*>(a.out_hi + base + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+    *reinterpret_cast<float4*>(a.out_lo + base + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                                                                  const __grid_constant__ CUtensorMap map_a_lo,
                                                                  const __grid_constant__ CUtensorMap map_b_hi,
                                                                  const __grid_constant__ CUtensorMap map_b_lo, TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: per stage [A_hi | A_lo | B_hi | B_lo], all 1024-byte aligned
-  const int b_bytes = a.Npad * kBlockK * 4;
+  const int b_bytes = a.Nchunk * kBlockK * 4;
+  const int nc0 = blockIdx.z * a.Nchunk;      // first output channel of this CTA
   const int stage_bytes = 2 * kABytes + 2 * b_bytes;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long s_full[4], s_empty[4], s_done;
   __shared__ unsigned s_tmem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int phase_id = blockIdx.y;            // output parity: py = phase_id >> 1, px = phase_id & 1
-  const int py = phase_id >> 1, px = phase_id & 1;
+  // output parity (py, px): one CTA per parity, or (pair mode) one CTA per row parity that computes px = 0 and 1 into
+  // two accumulators, so that its epilogue owns pairs of adjacent output pixels (8-byte bias loads / stores)
+  const int py = a.pair ? (int)blockIdx.y : (int)(blockIdx.y >> 1);
+  const int npx = a.pair ? 2 : 1;
   const int tiles_x = (a.Wi + a.tile_c - 1) / a.tile_c, tiles_y = (a.Hi + a.tile_r - 1) / a.tile_r;
   const int tile = blockIdx.x;
   const int b = tile / (tiles_x * tiles_y);
@@ -118,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
   const int m0 = ty * a.tile_r, n0 = tx * a.tile_c;
   const int kb_per_tap = a.Cin / kBlockK, num_kb = 4 * kb_per_tap;
   unsigned tmem_cols = 32;
-  while ((int)tmem_cols < a.Npad) tmem_cols <<= 1;
+  while ((int)tmem_cols < npx * a.Nchunk) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
@@ -137,8 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
   if (warp == 4) {
     // ===== TMA producer (one elected lane) =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % a.stages, it = kb / a.stages;
+      for (int g = 0; g < npx * num_kb; ++g) {
+        const int px = a.pair ? g / num_kb : (int)(blockIdx.y & 1), kb = g % num_kb;
+        const int phase_id = py * 2 + px;
+        const int s = g % a.stages, it = g / a.stages;
         if (it > 0) mbar_wait(&s_empty[s], (unsigned)((it - 1) & 1));
         const int tap = kb / kb_per_tap, cblk = kb % kb_per_tap;
         const int tyy = tap >> 1, txx = tap & 1;
@@ -148,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
         mbar_expect_tx(&s_full[s], (unsigned)stage_bytes);
         tma_load_4d(st, &map_a_hi, cblk * kBlockK, n0 + dx, m0 + dy, b, &s_full[s]);
         tma_load_4d(st + kABytes, &map_a_lo, cblk * kBlockK, n0 + dx, m0 + dy, b, &s_full[s]);
-        const int krow = phase_id * a.Npad;          // weight matrix rows: [phase][co padded]
+        const int krow = phase_id * a.Npad + nc0;    // weight matrix rows: [phase][co padded]
         const int kcol = tap * a.Cin + cblk * kBlockK;  // columns: [tap][ci]
         tma_load_2d(st + 2 * kABytes, &map_b_hi, kcol, krow, &s_full[s]);
         tma_load_2d(st + 2 * kABytes + b_bytes, &map_b_lo, kcol, krow, &s_full[s]);
@@ -158,9 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       // instruction descriptor: D = F32, A = B = TF32, both K-major, N = Cout, M = 128
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.Npad >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % a.stages, it = kb / a.stages;
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.Nchunk >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+      for (int g = 0; g < npx * num_kb; ++g) {
+        const int kb = g % num_kb;
+        const unsigned tmem_d = tmem_base + (unsigned)((g / num_kb) * a.Nchunk);  // accumulator of this column parity
+        const int s = g % a.stages, it = g / a.stages;
         mbar_wait(&s_full[s], (unsigned)(it & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned st = smem_u32(smem + (size_t)s * stage_bytes);
@@ -170,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
           const unsigned long long adv = (unsigned long long)((k * kUmmaK * 4) >> 4);  // +32 bytes per K slice
           // small terms first, then the main product
-          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0);
-          umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+          umma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0);
+          umma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+          umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
         }
         umma_commit(&s_empty[s]);  // frees the stage when these MMAs have read it
       }
@@ -187,43 +221,71 @@ __global__ void __launch_bounds__(kThreads, 1) deconv_tc_kernel(const __grid_con
     const int m = m0 + ry, n = n0 + rx;
     const bool valid = (m < a.Hi) && (n < a.Wi);
     const int Ho = 2 * a.Hi, Wo = 2 * a.Wi;
-    const int Y = 2 * m + py, X = 2 * n + px;
-    for (int c0 = 0; c0 < a.Npad; c0 += 16) {
-      unsigned r[16];
-      const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
-        float v[16];
+    const int Y = 2 * m + py;
+    if (!a.pair) {
+      const int px = (int)(blockIdx.y & 1), X = 2 * n + px;
+      for (int c0 = 0; c0 < a.Nchunk; c0 += 16) {
+        unsigned r[16];
+        tmem_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c0, r);
+        if (valid) {
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = c0 + j;
-          float o = 0.f;
-          if (co < a.Cout) {  // columns beyond Cout are zero padding of the N dimension
-            o = __uint_as_float(r[j]) * a.scale[co];
-            if (a.bias) o += a.bias[((size_t)co * Ho + Y) * Wo + X];
-            if (a.apply_act) o = o > 0.f ? o : o * a.slope;
+          for (int j = 0; j < 16; ++j) {
+            const int co = nc0 + c0 + j;
+            float o = 0.f;
+            if (co < a.Cout) {  // columns beyond Cout are zero padding of the N dimension
+              o = __uint_as_float(r[j]) * a.scale[co];
+              if (a.bias) o += a.bias[((size_t)co * Ho + Y) * Wo + X];
+              if (a.apply_act) o = o > 0.f ? o : o * a.slope;
+            }
+            v[j] = o;
           }
-          v[j] = o;
+          if (a.out_nchw) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nc0 + c0 + j < a.Cout) a.out_nchw[(((size_t)b * a.Cout + nc0 + c0 + j) * Ho + Y) * Wo + X] = v[j];
+          }
+          if (a.out_hi) store_nhwc_split(a, (((size_t)b * Ho + Y) * Wo + X) * a.ldc + nc0 + c0, v);
         }
-        if (a.out_nchw) {
+      }
+    } else {
+      // both column parities: lane = input column n -> output columns 2n, 2n+1: a warp's 32 lanes cover 256 contiguous
+      // bytes of a bias / output row per channel
+      for (int c0 = 0; c0 < a.Nchunk; c0 += 16) {
+        unsigned r0[16], r1[16];
+        tmem_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c0, r0);
+        tmem_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(a.Nchunk + c0), r1);
+        if (valid) {
+          float2 bb[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < a.Cout) a.out_nchw[(((size_t)b * a.Cout + c0 + j) * Ho + Y) * Wo + X] = v[j];
-        }
-        if (a.out_hi) {
-          const size_t base = (((size_t)b * Ho + Y) * Wo + X) * a.ldc + c0;
-          float hi[16], lo[16];
+          for (int j = 0; j < 16; ++j) {
+            bb[j] = make_float2(0.f, 0.f);
+            if (a.bias && nc0 + c0 + j < a.Cout)
+              bb[j] = ld_nc_f2(reinterpret_cast<const float2*>(a.bias + ((size_t)(nc0 + c0 + j) * Ho + Y) * Wo + 2 * n));
+          }
+          float v0[16], v1[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { hi[j] = to_tf32(v[j]); lo[j] = v[j] - hi[j]; }
+          for (int j = 0; j < 16; ++j) {
+            const int co = nc0 + c0 + j;
+            float o0 = 0.f, o1 = 0.f;
+            if (co < a.Cout) {
+              const float sc = a.scale[co];
+              o0 = __uint_as_float(r0[j]) * sc + bb[j].x;
+              o1 = __uint_as_float(r1[j]) * sc + bb[j].y;
+              if (a.apply_act) { o0 = o0 > 0.f ? o0 : o0 * a.slope; o1 = o1 > 0.f ? o1 : o1 * a.slope; }
+            }
+            v0[j] = o0; v1[j] = o1;
+          }
+          if (a.out_nchw) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            *reinterpret_cast<float4*>(a.out_hi + base + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-            *reinterpret_cast<float4*>(a.out_lo + base + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+            for (int j = 0; j < 16; ++j)
+              if (nc0 + c0 + j < a.Cout)
+                *reinterpret_cast<float2*>(a.out_nchw + (((size_t)b * a.Cout + nc0 + c0 + j) * Ho + Y) * Wo + 2 * n) = make_float2(v0[j], v1[j]);
+          }
+          if (a.out_hi) {
+            const size_t base = (((size_t)b * Ho + Y) * Wo + 2 * n) * a.ldc + nc0 + c0;
+            store_nhwc_split(a, base, v0);
+            store_nhwc_split(a, base + a.ldc, v1);
           }
         }
       }
@@ -301,6 +363,7 @@ GB_API int gb_nchw_to_nhwc_split(int B, int C, int Cpad, int H, int W, const flo
 // part and remainder), v [Cin,Cout,4,4], w_scratch of gb_deconv_tc_weight_bytes(Cin_pad, Cout) bytes, scale [Cout],
 // bias [Cout,2Hi,2Wi] or NULL.  Outputs (either or both): out_hi/out_lo NHWC [B,2Hi,2Wi,ldc] for a following
 // tensor-core layer, out_nchw [B,Cout,2Hi,2Wi] fp32.  Requires Cin_pad % 32 == 0 and Cout <= 256 (N is padded to 16).
+// v == NULL skips the weight preparation: w_scratch must then hold the result of an earlier call with the same v.
 GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, int Wi, const float* x_hi,
                                  const float* x_lo, const float* v, float* w_scratch, const float* scale,
                                  const float* bias, float slope, int apply_act, float* out_hi, float* out_lo, int ldc,
@@ -314,15 +377,28 @@ GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, 
   cudaStream_t s = (cudaStream_t)stream;
   float* w_hi = w_scratch;
   float* w_lo = w_scratch + (size_t)16 * Npad * Cin_pad;
-  {
+  int launches = 1;
+  if (v) {  // v == NULL: w_scratch still holds the matrices prepared by an earlier call with the same weight_v
     const long long total = 16ll * Npad * Cin_pad;
     weight_prep_kernel<<<(unsigned)gb::cdiv64(total, 256), 256, 0, s>>>(Cin, Cin_pad, Cout, Npad, v, w_hi, w_lo);
+    ++launches;
   }
   // tile geometry: 128 positions = tile_r rows x tile_c columns
   int tile_c = 128;
   while (tile_c > Wi && tile_c > 1) tile_c >>= 1;
   if (tile_c < 8) tile_c = 8;
   const int tile_r = kTileM / tile_c;
+
+  const int tiles = B * gb::cdiv(Hi, tile_r) * gb::cdiv(Wi, tile_c);
+  // pair mode needs two accumulators in TMEM and enough tiles to fill the machine with half as many CTAs
+  const int pair = (2 * Npad <= 512 && tiles * 2 >= 2 * gb::kNumSMs && Wi % 2 == 0) ? 1 : 0;
+  // the low-resolution layers have a handful of tiles: split the output channels over CTAs (grid.z) until the
+  // machine is covered; every CTA then streams the same A tiles (L2 hits) against its own slice of the weights
+  int Nchunk = Npad;
+  while (tiles * (pair ? 2 : 4) * (Npad / Nchunk) < gb::kNumSMs && Nchunk >= 32 && (Nchunk / 2) % 16 == 0 &&
+         Npad % (Nchunk / 2) == 0)
+    Nchunk /= 2;
+  const int ctas = tiles * (pair ? 2 : 4) * (Npad / Nchunk);
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
@@ -340,7 +416,7 @@ GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, 
   {
     const cuuint64_t gdim[2] = {(cuuint64_t)4 * Cin_pad, (cuuint64_t)4 * Npad};
     const cuuint64_t gstr[1] = {(cuuint64_t)4 * Cin_pad * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)Npad};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)Nchunk};
     const cuuint32_t estr[2] = {1, 1};
     if (encode(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w_hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -350,16 +426,23 @@ GB_API int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, 
       return (int)cudaErrorInvalidValue;
   }
   TcArgs a = {};
-  a.B = B; a.Cin = Cin_pad; a.Cout = Cout; a.Npad = Npad; a.Hi = Hi; a.Wi = Wi; a.tile_r = tile_r; a.tile_c = tile_c;
+  a.B = B; a.Cin = Cin_pad; a.Cout = Cout; a.Npad = Npad; a.Nchunk = Nchunk; a.Hi = Hi; a.Wi = Wi; a.tile_r = tile_r;
+  a.tile_c = tile_c; a.pair = pair;
   a.scale = scale; a.bias = bias; a.slope = slope; a.apply_act = apply_act; a.out_hi = out_hi; a.out_lo = out_lo;
   a.ldc = ldc; a.out_nchw = out_nchw;
-  const int stage_bytes = 2 * kABytes + 2 * Npad * kBlockK * 4;
-  a.stages = stage_bytes <= 64 * 1024 ? 3 : 2;
+  // every CTA is a serial TMA -> MMA -> epilogue chain: with few CTAs give each a deep ring (up to 4 stages); with
+  // many, keep the ring short so that 2-3 CTAs share an SM and overlap each other's epilogues
+  const int stage_bytes = 2 * kABytes + 2 * Nchunk * kBlockK * 4;
+  const int num_kb_total = (pair ? 2 : 1) * 4 * (Cin_pad / kBlockK);
+  int stages = ctas > gb::kNumSMs ? 2 : 4;
+  while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 200 * 1024) --stages;
+  if (stages > num_kb_total) stages = num_kb_total;
+  if (stages < 1) stages = 1;
+  a.stages = stages;
   const size_t smem = (size_t)a.stages * stage_bytes + 1024;
-  GB_CUDA(cudaFuncSetAttribute(deconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = B * gb::cdiv(Hi, tile_r) * gb::cdiv(Wi, tile_c);
-  deconv_tc_kernel<<<dim3(tiles, 4), kThreads, smem, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
-  gb::count_launches(2);
+  GB_CUDA(cudaFuncSetAttribute(deconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+  deconv_tc_kernel<<<dim3(tiles, pair ? 2 : 4, Npad / Nchunk), kThreads, smem, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+  gb::count_launches(launches);
   GB_CHECK_LAUNCH();
   return 0;
 }

@@ -241,6 +241,15 @@ def _pad32(c):
     return (c + 31) // 32 * 32
 
 
+# which layers of a tower run on the tensor cores; TC_MIN_CIN can be lowered to 16 to put the last (16 -> 125) layer
+# on them too (its K dimension is then half zero padding)
+TC_MIN_CIN = 32
+
+
+def _tc_layer_ok(cin, cout):
+    return cout <= 256 and cin >= TC_MIN_CIN
+
+
 def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """Inference forward of a deconv tower (Sequential of ConvTranspose2dWNUB [+ FusedLeakyReLU]) on the tensor cores
     (csrc/deconv_tc.cu: tcgen05.mma kind::tf32 with 3xTF32 split, TMA-fed, TMEM accumulators).  Activations stay NHWC
@@ -259,12 +268,22 @@ def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
             Cin, Cout = layer.in_channels, layer.out_channels
             # measured on B200 (bench.py --decoder): with Cin = 16 the layer is pure output/bias bandwidth and the
             # per-pixel NCHW epilogue of the tensor-core kernel loses to the SIMT kernel (4.2 vs 1.1 ms), so it stays SIMT
-            tc_ok = Cout <= 256 and Cin >= 32
+            tc_ok = _tc_layer_ok(Cin, Cout)
             nxt = layers[i + 1] if i + 1 < len(layers) else None
-            nxt_tc = nxt is not None and nxt.out_channels <= 256 and nxt.in_channels >= 32
-            scale = (layer.weight_g.reshape(-1) / layer.weight_v.norm()).contiguous()
+            nxt_tc = nxt is not None and _tc_layer_ok(nxt.in_channels, nxt.out_channels)
             bias = None if layer.bias is None else layer.bias.contiguous()
             slope = layer.fused_slope
+            # frozen-parameter cache: weight-norm scale and the prepared tensor-core weight matrices are functions of
+            # (weight_v, weight_g) only; they are rebuilt when either tensor is modified in place or replaced
+            key = (layer.weight_v.data_ptr(), layer.weight_v._version, layer.weight_g.data_ptr(), layer.weight_g._version)
+            cache = getattr(layer, "_tc_cache", None)
+            fresh = cache is None or cache[0] != key
+            if fresh:
+                scale = (layer.weight_g.reshape(-1) / layer.weight_v.norm()).contiguous()
+                ws = torch.empty(L.gb_deconv_tc_weight_bytes(_pad32(Cin), Cout) // 4, device=dev) if tc_ok else None
+                layer._tc_cache = (key, scale, ws)
+            else:
+                _, scale, ws = cache
             if tc_ok:
                 cpad = _pad32(Cin)
                 if cur_hi is None:  # enter the NHWC hi/lo format
@@ -274,15 +293,14 @@ def tower_forward_tc(tower: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
                                                        _lib.ptr(cur_lo), st), "nchw_to_nhwc_split")
                     cur_c = cpad
                 assert cur_c == cpad, "channel padding mismatch between consecutive tensor-core layers"
-                ws = torch.empty(L.gb_deconv_tc_weight_bytes(cpad, Cout) // 4, device=dev)
                 ldc = _pad32(Cout)
                 # padded output channels must be zero for the next layer's K loop
                 o_hi = (torch.zeros if ldc != Cout else torch.empty)(B, 2 * H, 2 * W, ldc, device=dev) if nxt_tc else None
                 o_lo = (torch.zeros if ldc != Cout else torch.empty)(B, 2 * H, 2 * W, ldc, device=dev) if nxt_tc else None
                 o_nchw = None if nxt_tc else torch.empty(B, Cout, 2 * H, 2 * W, device=dev)
                 _lib.check(L.gb_deconv4x4s2_tc_fwd(
-                    B, Cin, cpad, Cout, H, W, _lib.ptr(cur_hi), _lib.ptr(cur_lo), _lib.ptr(layer.weight_v.contiguous()),
-                    _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(bias), float(slope if slope is not None else 1.0),
+                    B, Cin, cpad, Cout, H, W, _lib.ptr(cur_hi), _lib.ptr(cur_lo),
+                    _lib.ptr(layer.weight_v.contiguous()) if fresh else None, _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(bias), float(slope if slope is not None else 1.0),
                     int(slope is not None), _lib.ptr(o_hi), _lib.ptr(o_lo), ldc, _lib.ptr(o_nchw), st), "deconv4x4s2_tc_fwd")
                 cur_hi, cur_lo, cur_c, cur_nchw = o_hi, o_lo, ldc, o_nchw
             else:

@@ -232,7 +232,9 @@ int gb_deconv4x4s2_wnub_bwd(int B, int Cin, int Cout, int Hi, int Wi, const floa
 
 /* ---- tensor-core (tcgen05 + TMA + TMEM) forward of the same layer, inference path; Cin_pad % 32 == 0,
  * Cout % 16 == 0, 16 <= Cout <= 256.  Activations are NHWC split into a tf32 "hi" part and the fp32 remainder "lo"
- * (3xTF32 accumulation keeps the 1e-4 bar).  Same reference lines as gb_deconv4x4s2_wnub_fwd. */
+ * (3xTF32 accumulation keeps the 1e-4 bar).  Same reference lines as gb_deconv4x4s2_wnub_fwd.
+ * v may be NULL when w_scratch still holds the matrices prepared by an earlier call with the same weight_v
+ * (inference with frozen parameters). */
 size_t gb_deconv_tc_weight_bytes(int Cin_pad, int Cout);
 int gb_nchw_to_nhwc_split(int B, int C, int Cpad, int H, int W, const float* x, float* hi, float* lo, void* stream);
 int gb_deconv4x4s2_tc_fwd(int B, int Cin, int Cin_pad, int Cout, int Hi, int Wi, const float* x_hi, const float* x_lo,

@@ -129,7 +129,10 @@ def test_prim_decoder_end_to_end_small(cuda):
 
 
 @pytest.mark.parametrize("plan,size", [([(64, 32), (32, 16), (16, 8)], (16, 12)), ([(264, 256), (256, 128)], (8, 8)),
-                                       ([(32, 48), (48, 16)], (40, 24))])
+                                       ([(32, 48), (48, 16)], (40, 24)),
+                                       # large enough for the pair-phase mode (one CTA, both column parities), first
+                                       # layer -> NHWC pair stores, second -> NCHW float2 stores with Cout = 21 (padded N)
+                                       ([(32, 32), (32, 21)], (96, 200))])
 def test_tensor_core_tower_matches_simt(cuda, plan, size):
     """csrc/deconv_tc.cu (tcgen05 + TMA + TMEM, 3xTF32) against the SIMT kernel on the same parameters: multi-layer
     NHWC hi/lo chaining, channel padding (264 -> 288, 48 -> 64), partial tiles, and the SIMT tail for Cout % 16 != 0."""
