@@ -311,6 +311,68 @@ def run_ours(args):
     if cap is not None and not args.no_graph:
         build_graph()
 
+    def timed_resident(steps, warmup):
+        """`value` arm: inputs resident in HBM.  With N > 1 the two exchange steps run on a communication stream:
+        the broadcast of frame i+1's decoded table overlaps step i's graph, the all-reduce of step i's gradient overlaps
+        step i+1 (double-buffered staging); whatever is NOT hidden shows up as a wait inside the per-step event pair."""
+        main = torch.cuda.current_stream()
+        if world == 1:
+            return timed(False, steps, warmup)
+        comm = torch.cuda.Stream()
+        next_in = [torch.empty_like(resident) for _ in range(2)]
+        grad_stage = [torch.empty_like(resident) for _ in range(2)]
+        ev = lambda: [torch.cuda.Event() for _ in range(2)]
+        bc_done, in_free, g_ready, g_free = ev(), ev(), ev(), ev()
+
+        def bcast(i):
+            k = i & 1
+            with torch.cuda.stream(comm):
+                if i >= 2:
+                    comm.wait_event(in_free[k])
+                next_in[k].copy_(resident, non_blocking=True)   # stands for the owner's decoder output of frame i
+                dist.broadcast(next_in[k], src=0)
+                bc_done[k].record(comm)
+
+        def run(n, evs):
+            bcast(0)
+            for i in range(n):
+                k = i & 1
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                main.wait_event(bc_done[k])
+                static_in.copy_(next_in[k], non_blocking=True)
+                in_free[k].record(main)
+                if i + 1 < n:
+                    bcast(i + 1)
+                state["graph"].replay() if state["graph"] is not None else None
+                grad = state["outs"][3] if state["graph"] is not None else compute(static_in)[3]
+                if i >= 2:
+                    main.wait_event(g_free[k])
+                grad_stage[k].copy_(grad, non_blocking=True)
+                g_ready[k].record(main)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(g_ready[k])
+                    dist.all_reduce(grad_stage[k])              # dL/d(decoded) summed over the views
+                    g_free[k].record(comm)
+                if i + 1 == n:
+                    main.wait_stream(comm)
+                b.record()
+                evs.append((a, b))
+
+        run(warmup, [])
+        torch.cuda.synchronize()
+        dist.barrier()
+        evs = []
+        t0 = time.perf_counter()
+        run(steps, evs)
+        torch.cuda.synchronize()
+        dist.barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches_per_step * steps, wall
+
     def timed(e2e, steps, warmup):
         for _ in range(warmup):
             one_step(e2e)
@@ -348,6 +410,7 @@ def run_ours(args):
         stage_out = [[torch.empty(1, 3, H, W, device=dev), torch.empty(1, 1, H, W, device=dev),
                       torch.empty(1, 1, H, W, device=dev)] for _ in range(2)]
         hosts = [host_out, [torch.empty_like(t).pin_memory() for t in host_out]]
+        stage_grad = [torch.empty_like(resident) for _ in range(2)] if world > 1 else None
         ev = lambda: [torch.cuda.Event() for _ in range(2)]
         in_ready, in_free, out_ready, out_free = ev(), ev(), ev(), ev()
 
@@ -357,6 +420,8 @@ def run_ours(args):
                 if i >= 2:
                     s_in.wait_event(in_free[k])
                 stage_in[k].copy_(host_packed, non_blocking=True)
+                if world > 1:
+                    dist.broadcast(stage_in[k], src=0)          # decoded Gaussians of the frame, owner = rank 0
                 in_ready[k].record(s_in)
 
         def run(n):
@@ -369,22 +434,22 @@ def run_ours(args):
                 main.wait_event(in_ready[k])
                 static_in.copy_(stage_in[k], non_blocking=True)
                 in_free[k].record(main)
-                if world > 1:
-                    dist.broadcast(static_in, src=0)
                 if state["graph"] is not None:
                     state["graph"].replay()
                     rgb, alpha, depth, grad = state["outs"]
                 else:
                     rgb, alpha, depth, grad = compute(static_in)
-                if world > 1:
-                    dist.all_reduce(grad)
                 if i >= 2:
                     main.wait_event(out_free[k])
                 for dst, src_t in zip(stage_out[k], (rgb, alpha, depth)):
                     dst.copy_(src_t, non_blocking=True)
+                if world > 1:
+                    stage_grad[k].copy_(grad, non_blocking=True)
                 out_ready[k].record(main)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(out_ready[k])
+                    if world > 1:
+                        dist.all_reduce(stage_grad[k])          # dL/d(decoded) summed over the views
                     for dst, src_t in zip(hosts[k], stage_out[k]):
                         dst.copy_(src_t, non_blocking=True)
                     out_free[k].record(s_out)
@@ -409,7 +474,7 @@ def run_ours(args):
     proc = path = None
     if rank == 0:
         proc, path = sample_clocks_start(local)
-    ms_total, launches, wall = timed(False, args.steps, args.warmup)
+    ms_total, launches, wall = timed_resident(args.steps, args.warmup)
     ms_e2e_serial, _, _ = timed(True, max(20, args.steps // 4), 3)
     ms_e2e_serial *= args.steps / max(20, args.steps // 4)
     ms_e2e = timed_e2e(args.steps, max(3, args.warmup))
@@ -447,6 +512,8 @@ def run_ours(args):
                                "bin/sort+blend(rgb)+blend(depth) fwd+bwd" % (G, H, W, args.lights),
                    "gaussians": G, "views_per_gpu": 1, "lights": args.lights, "block_width": BW,
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world,
+                   "collectives": (None if world == 1 else "NCCL broadcast of frame i+1's decoded table and all-reduce of "
+                                   "step i's gradient on a communication stream, overlapped with the neighbouring steps"),
                    "host_path": ("eager, exact buffers, 1 host sync/view" if cap is None else
                                  ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
                                                                                  ", step captured in a CUDA graph"))),
