@@ -88,17 +88,28 @@ def unpack(flat, G=None):
 def gpu_step(packed, cam, li, capacity=None):
     """forward + backward of shade + render for one view; returns (rgb, alpha, depth)."""
     from goliath_b200.render import render_views
-    from goliath_b200.sgutils import evaluate_gaussian
+    from goliath_b200.rgca_heads import shade_compose
 
     u = packed  # dict of leaf tensors (contiguous views of the flat buffer)
-    spec = evaluate_gaussian(u["lobe_dirs"][None], u["sigma"][None], li["light_intensity"],
-                             li["light_pos"], u["primpos"][None], li["n_lights"], w_type=0)[0]
-    color = (u["diff_color"].clamp(min=0.0) + spec * u["spec_vis"]).clamp(min=0.0)
+    # rgca.py:557-575: SG specular shade * spec_vis + clamped diffuse, clamped (one fused kernel each way)
+    color = shade_compose(u["lobe_dirs"][None], u["sigma"][None], li["light_intensity"], li["light_pos"],
+                          u["primpos"][None], li["n_lights"], u["diff_color"][None], u["spec_vis"][None])
     preds = dict(primpos=u["primpos"][None], primqvec=u["primqvec"][None], primscale=u["primscale"][None],
-                 opacity=u["opacity"][None], color=color[None])
+                 opacity=u["opacity"][None], color=color)
     rgb, alpha, depth = render_views(W, H, None, cam["Rt"], preds, intrinsics_host=[cam["intr"]], capacity=capacity)
-    (rgb.sum() + depth.sum()).backward()
+    torch.autograd.backward([rgb, depth], [_ones_like(rgb), _ones_like(depth)])  # v_out = 1 (SURVEY.md §8d)
     return rgb, alpha, depth
+
+
+_ONES = {}
+
+
+def _ones_like(t):
+    key = (tuple(t.shape), t.device)
+    o = _ONES.get(key)
+    if o is None:
+        o = _ONES[key] = torch.ones_like(t)
+    return o
 
 
 def sample_clocks_start(dev_index):

@@ -58,6 +58,10 @@ SIGNATURES = {
     "gb_mvp_slab_to_prims_bwd": (_i, [_i] * 6 + [_vp] * 3 + [_f, _f, _i] + [_vp] * 3 + [_vp]),
     "gb_mvp_prim_transform_fwd": (_i, [_i, _i] + [_vp] * 3 + [_f, _i] + [_vp] * 3 + [_vp]),
     "gb_mvp_prim_transform_bwd": (_i, [_i, _i] + [_vp] * 3 + [_f, _i] + [_vp] * 4 + [_vp]),
+    "gb_sg_shade_compose_fwd": (_i, [_vp] * 10 + [_i] * 4 + [_vp]),
+    "gb_sg_shade_compose_bwd": (_i, [_vp] * 16 + [_i] * 4 + [_vp]),
+    "gb_render_finish_fwd": (_i, [_i, _i] + [_vp] * 5 + [_vp]),
+    "gb_render_finish_bwd": (_i, [_i, _i] + [_vp] * 4 + [_vp]),
     "gb_rgca_heads_fwd": (_i, [_i, _i] + [_vp] * 7 + [_f, _f] + [_vp] * 13 + [_vp]),
     "gb_rgca_heads_bwd": (_i, [_i, _i] + [_vp] * 7 + [_f, _f] + [_vp] * 18 + [_vp]),
     "gb_mvp_raymarch_bwd": (_i, [_i] * 4 + [_vp, _vp, _f] + [_vp] * 5 + [_i] * 3 + [_vp] + [_i] * 3 + [_vp] * 8

@@ -28,14 +28,37 @@ constexpr int kLightChunk = 256;  // 256 lights * 24 B = 6 KB of shared memory
 
 __device__ __forceinline__ float sq(float v) { return v * v; }
 
-template <int WT>
+// Optional fusion of the shade's surroundings in ca_code/models/rgca.py:557-575 (and F.normalize of
+// extensions/sgutils/sgutils.py:74-75) into the same pass: lobe direction normalised in-kernel, specular = integral *
+// spec_vis, colour = clamp(clamp(diffuse, 0) + specular, 0).  The per-(Gaussian, light) arithmetic is untouched.
+// The stored colour carries the sign of the pre-clamp value in its sign bit (-0.0f where it was negative) so that the
+// backward can apply torch's clamp rule (gradient passes where pre >= 0) without a second pass over the lights.
+struct Compose {
+  const float* diff_color;  // [N,D,3]
+  const float* spec_vis;    // [N,D]
+  float* color;             // [N,D,3] out (fwd) / saved (bwd)
+  float* spec_color;        // [N,D,3] out or null
+  // backward only
+  const float* g_color;       // [N,D,3]
+  const float* g_spec_color;  // [N,D,3] or null
+  float* g_diff;              // [N,D,3]
+  float* g_vis;               // [N,D]
+};
+
+__device__ __forceinline__ float3 normalize_rn(float3 r, float& len_out) {  // F.normalize(eps = 1e-12), exact div/sqrt
+  const float len = fmaxf(__fsqrt_rn(r.x * r.x + r.y * r.y + r.z * r.z), 1e-12f);
+  len_out = len;
+  return make_float3(__fdiv_rn(r.x, len), __fdiv_rn(r.y, len), __fdiv_rn(r.z, len));
+}
+
+template <int WT, bool FUSED>
 __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict__ lobe_dirs,
                                                         const float* __restrict__ lobe_sigmas,
                                                         const float* __restrict__ light_values,
                                                         const float* __restrict__ light_pts,
                                                         const float* __restrict__ prim_pts,
                                                         const int* __restrict__ n_lights,
-                                                        float* __restrict__ integral, int D, int L) {
+                                                        float* __restrict__ integral, int D, int L, Compose cz) {
   __shared__ float s_lp[kLightChunk * 3];
   __shared__ float s_lv[kLightChunk * 3];
   const int n = blockIdx.y;
@@ -48,6 +71,7 @@ __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict_
     dir = make_float3(lobe_dirs[3 * o], lobe_dirs[3 * o + 1], lobe_dirs[3 * o + 2]);
     pp = make_float3(prim_pts[3 * o], prim_pts[3 * o + 1], prim_pts[3 * o + 2]);
     sigma = lobe_sigmas[o];
+    if (FUSED) { float len; dir = normalize_rn(dir, len); }
   }
   const int nL = min(n_lights[n], L);
   float3 sum = make_float3(0.f, 0.f, 0.f);
@@ -80,12 +104,22 @@ __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict_
       sum.x += s_lv[3 * l] * w; sum.y += s_lv[3 * l + 1] * w; sum.z += s_lv[3 * l + 2] * w;
     }
   }
-  if (active) {
+  if (active && !FUSED) {
     integral[3 * o] = sum.x; integral[3 * o + 1] = sum.y; integral[3 * o + 2] = sum.z;
+  }
+  if (active && FUSED) {
+    const float vis = cz.spec_vis[o];
+    const float sp[3] = {sum.x * vis, sum.y * vis, sum.z * vis};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float pre = fmaxf(cz.diff_color[3 * o + c], 0.f) + sp[c];
+      cz.color[3 * o + c] = pre >= 0.f ? pre : -0.f;
+      if (cz.spec_color) cz.spec_color[3 * o + c] = sp[c];
+    }
   }
 }
 
-template <int WT, bool LIGHT_GRAD>
+template <int WT, bool LIGHT_GRAD, bool FUSED>
 __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict__ lobe_dirs,
                                                         const float* __restrict__ lobe_sigmas,
                                                         const float* __restrict__ light_values,
@@ -95,7 +129,8 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ grad_integral,
                                                         float* __restrict__ grad_dirs,
                                                         float* __restrict__ grad_sigmas,
-                                                        float* __restrict__ grad_light_values, int D, int L) {
+                                                        float* __restrict__ grad_light_values, int D, int L,
+                                                        Compose cz) {
   __shared__ float s_lp[kLightChunk * 3];
   __shared__ float s_lv[kLightChunk * 3];
   __shared__ float s_gl[LIGHT_GRAD ? kLightChunk * 3 : 1];
@@ -105,11 +140,28 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
   const size_t o = (size_t)n * D + (active ? d : 0);
   float3 dir = make_float3(0.f, 0.f, 0.f), pp = dir, gi = dir;
   float sigma = 1.f;
+  float3 raw = dir, gsp = dir, integ = dir;  // fused: un-normalised direction, dL/d(spec_color), recomputed integral
+  float rawlen = 1.f, vis = 0.f;
   if (active) {
     dir = make_float3(lobe_dirs[3 * o], lobe_dirs[3 * o + 1], lobe_dirs[3 * o + 2]);
     pp = make_float3(prim_pts[3 * o], prim_pts[3 * o + 1], prim_pts[3 * o + 2]);
-    gi = make_float3(grad_integral[3 * o], grad_integral[3 * o + 1], grad_integral[3 * o + 2]);
     sigma = lobe_sigmas[o];
+    if (!FUSED) {
+      gi = make_float3(grad_integral[3 * o], grad_integral[3 * o + 1], grad_integral[3 * o + 2]);
+    } else {
+      raw = dir;
+      dir = normalize_rn(raw, rawlen);
+      vis = cz.spec_vis[o];
+      float g[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float gpre = signbit(cz.color[3 * o + c]) ? 0.f : cz.g_color[3 * o + c];  // outer clamp(min=0)
+        cz.g_diff[3 * o + c] = cz.diff_color[3 * o + c] >= 0.f ? gpre : 0.f;            // inner clamp(min=0)
+        g[c] = gpre + (cz.g_spec_color ? cz.g_spec_color[3 * o + c] : 0.f);
+      }
+      gsp = make_float3(g[0], g[1], g[2]);
+      gi = make_float3(g[0] * vis, g[1] * vis, g[2] * vis);
+    }
   }
   const int nL = min(n_lights[n], L);
   float3 gdir = make_float3(0.f, 0.f, 0.f);
@@ -159,6 +211,7 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
         dL_cos = dLw * ev / sigma;
       }
       gdir.x += dL_cos * lx; gdir.y += dL_cos * ly; gdir.z += dL_cos * lz;
+      if (FUSED) { integ.x += e0 * weight; integ.y += e1 * weight; integ.z += e2 * weight; }
       if (LIGHT_GRAD) {
         const float wa = active ? weight : 0.f;
         const float r0 = gb::warp_sum(gi.x * wa), r1 = gb::warp_sum(gi.y * wa), r2 = gb::warp_sum(gi.z * wa);
@@ -175,6 +228,15 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
   }
   if (active) {
     grad_sigmas[o] = gsig;
+    if (FUSED) {
+      cz.g_vis[o] = gsp.x * integ.x + gsp.y * integ.y + gsp.z * integ.z;
+      // backward of x / max(|x|, eps): (g - n (n . g)) / |x| on the regular branch, g / eps below it
+      const float nd = dir.x * gdir.x + dir.y * gdir.y + dir.z * gdir.z;
+      const bool regular = rawlen > 1e-12f;
+      gdir = regular ? make_float3(__fdiv_rn(gdir.x - dir.x * nd, rawlen), __fdiv_rn(gdir.y - dir.y * nd, rawlen),
+                                   __fdiv_rn(gdir.z - dir.z * nd, rawlen))
+                     : make_float3(gdir.x * 1e12f, gdir.y * 1e12f, gdir.z * 1e12f);
+    }
     grad_dirs[3 * o] = gdir.x; grad_dirs[3 * o + 1] = gdir.y; grad_dirs[3 * o + 2] = gdir.z;
   }
 }
@@ -190,7 +252,7 @@ GB_API int gb_sg_evaluate_fwd(const float* lobe_dirs, const float* lobe_sigmas, 
   dim3 grid(gb::cdiv(D, kBlock), N);
   cudaStream_t s = (cudaStream_t)stream;
 #define GB_SG_FWD(WT) \
-  sg_fwd_kernel<WT><<<grid, kBlock, 0, s>>>(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, n_lights, integral, D, L)
+  sg_fwd_kernel<WT, false><<<grid, kBlock, 0, s>>>(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, n_lights, integral, D, L, Compose{})
   switch (w_type) {
     case 0: GB_SG_FWD(0); break;
     case 1: GB_SG_FWD(1); break;
@@ -214,9 +276,77 @@ GB_API int gb_sg_evaluate_bwd(const float* lobe_dirs, const float* lobe_sigmas, 
   dim3 grid(gb::cdiv(D, kBlock), N);
   cudaStream_t s = (cudaStream_t)stream;
 #define GB_SG_BWD(WT, LG)                                                                                   \
-  sg_bwd_kernel<WT, LG><<<grid, kBlock, 0, s>>>(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, \
-                                                n_lights, grad_integral, grad_dirs, grad_sigmas, grad_light_values, D, L)
+  sg_bwd_kernel<WT, LG, false><<<grid, kBlock, 0, s>>>(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, \
+                                                       n_lights, grad_integral, grad_dirs, grad_sigmas,          \
+                                                       grad_light_values, D, L, Compose{})
   if (grad_light_values) {
+    switch (w_type) {
+      case 0: GB_SG_BWD(0, true); break;
+      case 1: GB_SG_BWD(1, true); break;
+      case 2: GB_SG_BWD(2, true); break;
+      default: GB_SG_BWD(3, true); break;
+    }
+  } else {
+    switch (w_type) {
+      case 0: GB_SG_BWD(0, false); break;
+      case 1: GB_SG_BWD(1, false); break;
+      case 2: GB_SG_BWD(2, false); break;
+      default: GB_SG_BWD(3, false); break;
+    }
+  }
+#undef GB_SG_BWD
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Fused shade + compose (rgca.py:557-575 with sgutils.py:74-75 folded in): lobe_dirs are the UN-normalised reflection
+// directions, diff_color [N,D,3], spec_vis [N,D]; color [N,D,3] = clamp(clamp(diff,0) + integral*spec_vis, 0) (sign bit
+// keeps the pre-clamp sign for the backward), spec_color [N,D,3] optional (NULL to skip).
+GB_API int gb_sg_shade_compose_fwd(const float* lobe_dirs, const float* lobe_sigmas, const float* light_values,
+                                   const float* light_pts, const float* prim_pts, const int32_t* n_lights,
+                                   const float* diff_color, const float* spec_vis, float* color, float* spec_color,
+                                   int N, int D, int L, int w_type, void* stream) {
+  if (N <= 0 || D <= 0) return 0;
+  if (w_type < 0 || w_type > 3) return (int)cudaErrorInvalidValue;
+  dim3 grid(gb::cdiv(D, kBlock), N);
+  cudaStream_t s = (cudaStream_t)stream;
+  Compose cz{};
+  cz.diff_color = diff_color; cz.spec_vis = spec_vis; cz.color = color; cz.spec_color = spec_color;
+#define GB_SG_FWD(WT) \
+  sg_fwd_kernel<WT, true><<<grid, kBlock, 0, s>>>(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, n_lights, nullptr, D, L, cz)
+  switch (w_type) {
+    case 0: GB_SG_FWD(0); break;
+    case 1: GB_SG_FWD(1); break;
+    case 2: GB_SG_FWD(2); break;
+    default: GB_SG_FWD(3); break;
+  }
+#undef GB_SG_FWD
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Backward of the above.  color is the forward's output (unmodified), g_color [N,D,3], g_spec_color [N,D,3] or NULL;
+// writes g_dirs [N,D,3] (w.r.t. the un-normalised directions), g_sigmas [N,D], g_diff [N,D,3], g_vis [N,D];
+// g_light_values (nullable) is accumulated into (caller zeroes it).
+GB_API int gb_sg_shade_compose_bwd(const float* lobe_dirs, const float* lobe_sigmas, const float* light_values,
+                                   const float* light_pts, const float* prim_pts, const int32_t* n_lights,
+                                   const float* diff_color, const float* spec_vis, const float* color,
+                                   const float* g_color, const float* g_spec_color, float* g_dirs, float* g_sigmas,
+                                   float* g_diff, float* g_vis, float* g_light_values, int N, int D, int L, int w_type,
+                                   void* stream) {
+  if (N <= 0 || D <= 0) return 0;
+  if (w_type < 0 || w_type > 3) return (int)cudaErrorInvalidValue;
+  dim3 grid(gb::cdiv(D, kBlock), N);
+  cudaStream_t s = (cudaStream_t)stream;
+  Compose cz{};
+  cz.diff_color = diff_color; cz.spec_vis = spec_vis; cz.color = const_cast<float*>(color);
+  cz.g_color = g_color; cz.g_spec_color = g_spec_color; cz.g_diff = g_diff; cz.g_vis = g_vis;
+#define GB_SG_BWD(WT, LG)                                                                                          \
+  sg_bwd_kernel<WT, LG, true><<<grid, kBlock, 0, s>>>(lobe_dirs, lobe_sigmas, light_values, light_pts, prim_pts, \
+                                                      n_lights, nullptr, g_dirs, g_sigmas, g_light_values, D, L, cz)
+  if (g_light_values) {
     switch (w_type) {
       case 0: GB_SG_BWD(0, true); break;
       case 1: GB_SG_BWD(1, true); break;

@@ -133,8 +133,9 @@ class _RenderFused(Function):
         f32 = dict(device=dev, dtype=torch.float32)
         v_out4 = torch.zeros(H, W, 4, **f32) if v_out4 is None else v_out4.contiguous()
         v_alpha = torch.zeros(H, W, **f32) if v_alpha is None else v_alpha.contiguous()
-        v_xy, v_conic = torch.zeros(G, 2, **f32), torch.zeros(G, 3, **f32)
-        v_col4, v_opeff = torch.zeros(G, 4, **f32), torch.zeros(G, **f32)
+        acc = torch.zeros(G * 10, **f32)  # the four atomically-accumulated gradient arrays, one fill
+        v_xy, v_conic = acc[:2 * G].view(G, 2), acc[2 * G:5 * G].view(G, 3)
+        v_col4, v_opeff = acc[5 * G:9 * G].view(G, 4), acc[9 * G:]
         v_colors, v_opacity = torch.empty(G, 3, **f32), torch.empty(G, 1, **f32)
         v_comp, v_depth = torch.empty(G, **f32), torch.empty(G, **f32)
         g_cov2d, g_cov3d = torch.empty(G, 3, **f32), torch.empty(G, 6, **f32)

@@ -79,12 +79,77 @@ def render(
     return out
 
 
+_BLACK = {}
+
+
+def _black(dev):
+    """the default background, allocated once per device"""
+    t = _BLACK.get(dev)
+    if t is None:
+        t = _BLACK[dev] = th.zeros(3, device=dev)
+    return t
+
+
+class _FinishView(th.autograd.Function):
+    """out4 [H,W,4] + alpha [H,W] -> (rgb [3,H,W], alpha [1,H,W], depth [1,H,W]) in one kernel (csrc/render_finish.cu)."""
+
+    @staticmethod
+    def forward(ctx, out4, alpha):
+        from . import _lib
+        out4, alpha = out4.contiguous(), alpha.contiguous()
+        _lib.check_input(out4, "out4")
+        H, W = out4.shape[0], out4.shape[1]
+        dev = out4.device
+        rgb = th.empty(3, H, W, device=dev)
+        a_img, depth = th.empty(1, H, W, device=dev), th.empty(1, H, W, device=dev)
+        with th.cuda.device(dev):
+            _lib.check(_lib.lib().gb_render_finish_fwd(H, W, _lib.ptr(out4), _lib.ptr(alpha), _lib.ptr(rgb), _lib.ptr(a_img),
+                                                       _lib.ptr(depth), _lib.stream_ptr(dev)), "render_finish_fwd")
+        ctx.save_for_backward(alpha)
+        ctx.hw = (H, W)
+        ctx.mark_non_differentiable(a_img)
+        ctx.set_materialize_grads(False)
+        return rgb, a_img, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, _g_alpha, g_depth):
+        from . import _lib
+        (alpha,) = ctx.saved_tensors
+        H, W = ctx.hw
+        g_out4 = th.empty(H, W, 4, device=alpha.device)
+        g_rgb = None if g_rgb is None else g_rgb.contiguous()
+        g_depth = None if g_depth is None else g_depth.contiguous()
+        with th.cuda.device(alpha.device):
+            _lib.check(_lib.lib().gb_render_finish_bwd(H, W, _lib.ptr(alpha), _lib.ptr(g_rgb), _lib.ptr(g_depth),
+                                                       _lib.ptr(g_out4), _lib.stream_ptr(alpha.device)), "render_finish_bwd")
+        return g_out4, None
+
+
 def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None, fused=True,
                  capacity=None):
     """rgca.AutoEncoder.render (rgca.py:112-151): loop over the batch, stack, alpha from the DETACHED final_T,
     depth normalised by alpha.clamp(0.05, 1).  `intrinsics_host` (list of (fx,fy,cx,cy)) avoids the reference's
     four `.item()` device syncs per view when the caller already has them on the host."""
     B = Rt.shape[0]
+    if fused:
+        # per view: one autograd node for project + bin/sort + pack + blend and one for the post-processing
+        from .gsplat.fused import render_fused
+        rgbs, alphas, depths = [], [], []
+        for b in range(B):
+            if intrinsics_host is not None:
+                fx, fy, cx, cy = intrinsics_host[b]
+            else:
+                fx, fy, cx, cy = K[b, 0, 0].item(), K[b, 1, 1].item(), K[b, 0, 2].item(), K[b, 1, 2].item()
+            out4, alpha, _ = render_fused(
+                preds["primpos"][b].reshape(-1, 3).contiguous(), preds["primscale"][b].reshape(-1, 3).contiguous(), 1.0,
+                preds["primqvec"][b].reshape(-1, 4).contiguous(), Rt[b], fx, fy, cx, cy, height, width,
+                preds["opacity"][b].reshape(-1, 1).contiguous(), preds["color"][b].reshape(-1, 3).contiguous(),
+                _black(Rt.device), 0.1, capacity)
+            r, a, d = _FinishView.apply(out4, alpha)
+            rgbs.append(r); alphas.append(a); depths.append(d)
+        if B == 1:
+            return rgbs[0][None], alphas[0][None], depths[0][None]
+        return th.stack(rgbs), th.stack(alphas), th.stack(depths)
     rgbs, Ts, depths = [], [], []
     for b in range(B):
         if intrinsics_host is not None:

@@ -78,8 +78,77 @@ def gaussian_heads(f_vnocond, f_vcond, postex, tn, albedo, headrel_light_sh, hea
     return dict(zip(_OUT, outs))
 
 
-def shade_and_compose(heads: Dict[str, torch.Tensor], light_intensity, headrel_light_pos, n_lights) -> Dict[str, torch.Tensor]:
-    """rgca.py:557-575 (point-light branch): SG specular via evaluate_gaussian, times spec_vis, plus clamped diffuse."""
+class _ShadeCompose(Function):
+    """normalise + SG shade + `spec * spec_vis` + `clamp(clamp(diff, 0) + spec, 0)` as one kernel each way
+    (csrc/sg_shade.cu, FUSED instantiations)."""
+
+    @staticmethod
+    def forward(ctx, ref_dirs, sigma, light_values, light_pts, prim_pts, n_lights, diff_color, spec_vis, w_type, want_spec):
+        ins = [t.contiguous() for t in (ref_dirs, sigma, light_values, light_pts, prim_pts, diff_color, spec_vis)]
+        for t, n in zip(ins, ("ref_dirs", "sigma", "light_values", "light_pts", "prim_pts", "diff_color", "spec_vis")):
+            _lib.check_input(t, n)
+        ref_dirs, sigma, light_values, light_pts, prim_pts, diff_color, spec_vis = ins
+        n_lights = n_lights.int().contiguous()
+        N, D, L = ref_dirs.shape[0], ref_dirs.shape[1], light_values.shape[1]
+        if spec_vis.numel() != N * D or sigma.numel() != N * D or diff_color.shape != (N, D, 3):
+            raise RuntimeError("shade_compose: sigma / spec_vis must be [N,D(,1)] and diff_color [N,D,3]")
+        dev = ref_dirs.device
+        color = torch.empty(N, D, 3, device=dev, dtype=torch.float32)
+        spec = torch.empty(N, D, 3, device=dev, dtype=torch.float32) if want_spec else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gb_sg_shade_compose_fwd(
+                _lib.ptr(ref_dirs), _lib.ptr(sigma), _lib.ptr(light_values), _lib.ptr(light_pts), _lib.ptr(prim_pts),
+                _lib.ptr(n_lights), _lib.ptr(diff_color), _lib.ptr(spec_vis), _lib.ptr(color), _lib.ptr(spec), N, D, L,
+                int(w_type), _lib.stream_ptr(dev)), "sg_shade_compose_fwd")
+        ctx.save_for_backward(ref_dirs, sigma, light_values, light_pts, prim_pts, n_lights, diff_color, spec_vis, color)
+        ctx.meta = (N, D, L, int(w_type), sigma.shape, spec_vis.shape)
+        ctx.set_materialize_grads(False)
+        return (color, spec) if want_spec else (color, None)
+
+    @staticmethod
+    def backward(ctx, g_color, g_spec):
+        ref_dirs, sigma, light_values, light_pts, prim_pts, n_lights, diff_color, spec_vis, color = ctx.saved_tensors
+        N, D, L, w_type, sig_shape, vis_shape = ctx.meta
+        dev = ref_dirs.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        if g_color is None:
+            g_color = torch.zeros(N, D, 3, **f32)
+        g_color = g_color.contiguous()
+        g_spec = None if g_spec is None else g_spec.contiguous()
+        g_dirs, g_sig = torch.empty(N, D, 3, **f32), torch.empty(sig_shape, **f32)
+        g_diff, g_vis = torch.empty(N, D, 3, **f32), torch.empty(vis_shape, **f32)
+        g_light = torch.zeros_like(light_values) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gb_sg_shade_compose_bwd(
+                _lib.ptr(ref_dirs), _lib.ptr(sigma), _lib.ptr(light_values), _lib.ptr(light_pts), _lib.ptr(prim_pts),
+                _lib.ptr(n_lights), _lib.ptr(diff_color), _lib.ptr(spec_vis), _lib.ptr(color), _lib.ptr(g_color),
+                _lib.ptr(g_spec), _lib.ptr(g_dirs), _lib.ptr(g_sig), _lib.ptr(g_diff), _lib.ptr(g_vis), _lib.ptr(g_light),
+                N, D, L, w_type, _lib.stream_ptr(dev)), "sg_shade_compose_bwd")
+        return g_dirs, g_sig, g_light, None, None, None, g_diff, g_vis, None, None
+
+
+def shade_compose(ref_dirs, sigma, light_intensity, light_pos, primpos, n_lights, diff_color, spec_vis, w_type: int = 0,
+                  return_spec: bool = False):
+    """Fused form of rgca.py:557-575: `spec = evaluate_gaussian(ref_dirs, sigma, ...) * spec_vis`,
+    `color = (diff_color.clamp(min=0) + spec).clamp(min=0)`.  ref_dirs [N,D,3] un-normalised, sigma [N,D], spec_vis
+    [N,D,1] or [N,D], diff_color [N,D,3].  Returns color (and spec_color when asked).  Gradients: ref_dirs, sigma,
+    light_intensity, diff_color, spec_vis — the same set the unfused chain differentiates."""
+    color, spec = _ShadeCompose.apply(ref_dirs, sigma, light_intensity, light_pos, primpos, n_lights, diff_color, spec_vis,
+                                      w_type, return_spec)
+    return (color, spec) if return_spec else color
+
+
+def shade_and_compose(heads: Dict[str, torch.Tensor], light_intensity, headrel_light_pos, n_lights,
+                      fused: bool = True) -> Dict[str, torch.Tensor]:
+    """rgca.py:557-575 (point-light branch): SG specular via evaluate_gaussian, times spec_vis, plus clamped diffuse.
+    fused=True runs it as one kernel each way (`shade_compose`); fused=False is the reference's op-by-op chain."""
+    if fused:
+        color, spec_color = shade_compose(heads["ref_dirs"], heads["sigma"], light_intensity, headrel_light_pos,
+                                          heads["primpos"], n_lights, heads["diff_color"], heads["spec_vis"],
+                                          return_spec=True)
+        out = dict(heads)
+        out.update(spec_color=spec_color, color=color)
+        return out
     spec_color = evaluate_gaussian(heads["ref_dirs"].contiguous(), heads["sigma"].contiguous(), light_intensity.contiguous(),
                                    headrel_light_pos.contiguous(), heads["primpos"].contiguous(), n_lights.int(),
                                    w_type=0) * heads["spec_vis"]

@@ -213,6 +213,31 @@ int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* f_vcond
                       const float* g_diff_color, const float* g_ref_dirs, const float* g_primnmlbase, float* g_f_vnocond,
                       float* g_f_vcond, float* g_postex, float* g_tn, float* g_albedo, void* stream);
 
+/* replaces the per-view post-processing of rgca.AutoEncoder.render (ca_code/models/rgca.py:136-151, with
+ * render_gsplat.py:79-108): colour HWC -> CHW, alpha = 1 - final_T (detached), depth / alpha.clamp(0.05, 1).
+ * out4 [H,W,4] = rgb + depth-as-colour, alpha [H,W] -> rgb [3,H,W], alpha_img [1,H,W], depth [1,H,W]. */
+int gb_render_finish_fwd(int img_h, int img_w, const float* out4, const float* alpha, float* rgb, float* alpha_img,
+                         float* depth, void* stream);
+/* g_rgb / g_depth may be NULL; g_out4 [H,W,4] is written. */
+int gb_render_finish_bwd(int img_h, int img_w, const float* alpha, const float* g_rgb, const float* g_depth,
+                         float* g_out4, void* stream);
+
+/* fused shade + compose: replaces F.normalize (extensions/sgutils/sgutils.py:74-75) + evaluate_gaussian + the colour
+ * composition of ca_code/models/rgca.py:557-575 (`spec * spec_vis`, `diff.clamp(0) + spec`, `.clamp(0)`) with one kernel
+ * each way.  lobe_dirs are the UN-normalised reflection directions [N,D,3]; diff_color [N,D,3], spec_vis [N,D];
+ * color [N,D,3] out (its sign bit keeps the pre-clamp sign for the backward); spec_color [N,D,3] out or NULL. */
+int gb_sg_shade_compose_fwd(const float* lobe_dirs, const float* lobe_sigmas, const float* light_values,
+                            const float* light_pts, const float* prim_pts, const int32_t* n_lights,
+                            const float* diff_color, const float* spec_vis, float* color, float* spec_color, int N,
+                            int D, int L, int w_type, void* stream);
+/* backward: color = the forward's output; g_spec_color may be NULL; g_dirs / g_sigmas / g_diff / g_vis are written,
+ * g_light_values (nullable) is accumulated into (caller zeroes it). */
+int gb_sg_shade_compose_bwd(const float* lobe_dirs, const float* lobe_sigmas, const float* light_values,
+                            const float* light_pts, const float* prim_pts, const int32_t* n_lights,
+                            const float* diff_color, const float* spec_vis, const float* color, const float* g_color,
+                            const float* g_spec_color, float* g_dirs, float* g_sigmas, float* g_diff, float* g_vis,
+                            float* g_light_values, int N, int D, int L, int w_type, void* stream);
+
 /* ---------------------------------------------------------------- decoder layers (rows R1 / R8) */
 
 /* replaces conv_transpose2d + untied-bias add (ca_code/nn/layers.py:380-396) + the LeakyReLU that follows it in

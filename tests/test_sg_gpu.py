@@ -94,3 +94,41 @@ def test_sg_errors_like_reference(cuda):
     with pytest.raises(RuntimeError):  # non-contiguous
         sgutilslib.evaluate_gaussian_fwd(tc.transpose(1, 2).transpose(1, 2)[:, ::2], tc[..., 0], tc, tc, tc,
                                          torch.ones(1, dtype=torch.int32, device=cuda), tc.clone(), 0)
+
+
+@pytest.mark.parametrize("w_type", [0, 2])
+def test_shade_compose_matches_unfused_chain(cuda, w_type):
+    """rgca_heads.shade_compose (normalise + SG + spec_vis + both clamps in one kernel each way) against the
+    reference's op-by-op chain rgca.py:557-575 built from evaluate_gaussian and torch ops; negative light values and
+    negative diffuse exercise both clamp masks."""
+    from goliath_b200.rgca_heads import shade_compose
+    from goliath_b200.sgutils import evaluate_gaussian
+
+    gen = torch.Generator().manual_seed(41 + w_type)
+    N, D, L = 2, 3001, 9
+    mk = lambda *s: torch.randn(*s, generator=gen)
+    base = dict(ref_dirs=mk(N, D, 3) * 3.0, sigma=(0.1 * torch.exp(0.5 * mk(N, D))).clamp(min=0.01),
+                lint=mk(N, L, 3) * 0.7 + 0.3, diff=mk(N, D, 3) * 0.5, vis=torch.sigmoid(mk(N, D, 1)))
+    lpos = (mk(N, L, 3) * 900.0).to(cuda)
+    ppos = (mk(N, D, 3) * 100.0).to(cuda)
+    nl = torch.tensor([L, L - 2], dtype=torch.int32, device=cuda)
+    w_c, w_s = mk(N, D, 3).to(cuda), mk(N, D, 3).to(cuda)
+    outs = []
+    for fused in (False, True):
+        lv = {k: v.clone().to(cuda).requires_grad_() for k, v in base.items()}
+        if fused:
+            color, spec = shade_compose(lv["ref_dirs"], lv["sigma"], lv["lint"], lpos, ppos, nl, lv["diff"], lv["vis"],
+                                        w_type=w_type, return_spec=True)
+        else:
+            spec = evaluate_gaussian(lv["ref_dirs"], lv["sigma"], lv["lint"], lpos, ppos, nl, w_type=w_type) * lv["vis"]
+            color = (lv["diff"].clamp(min=0.0) + spec).clamp(min=0.0)
+        ((color * w_c).sum() + (spec * w_s).sum()).backward()
+        outs.append((t2n(color), t2n(spec), {k: t2n(v.grad) for k, v in lv.items()}))
+    (c0, s0, g0), (c1, s1, g1) = outs
+    assert (c0 < 1e-12).mean() > 0.01, "the outer clamp must be active somewhere in this case"
+    # the in-kernel normalisation differs from F.normalize in the last bit of the direction; sharp lobes (sigma -> 0.01)
+    # amplify that, hence the absolute tolerance relative to the largest value
+    assert_close(c1, c0, rtol=1e-4, atol=1e-5 * np.abs(c0).max(), what="color")
+    assert_close(s1, s0, rtol=1e-4, atol=1e-5 * np.abs(s0).max(), what="spec_color")
+    for k in g0:
+        assert_close(g1[k], g0[k], rtol=2e-4, atol=2e-5 * np.abs(g0[k]).max(), frac=0.9995, what="grad " + k)
