@@ -202,6 +202,25 @@ def kernel_roofline(dev, packed, cam, flush):
                                              gcol.data_ptr(), go.data_ptr(), st), "bwd")
 
     pack()
+    # the product path's binning (sync-free): depth ranks + tile buckets + bitmap sort + record packing, 9 launches
+    cap_b = int(n) + 1024
+    col3, op1 = u["diff_color"].contiguous(), u["opacity"].contiguous()
+    ws_b = torch.empty(L.gb_bin_tiles_workspace_bytes(G, T_, cap_b), dtype=torch.uint8, device=dev)
+    bins_b = torch.empty(T_, 2, dtype=torch.int32, device=dev)
+    order_b = torch.empty(T_, dtype=torch.int32, device=dev)
+    gids_b = torch.empty(cap_b, dtype=torch.int32, device=dev)
+    rec_b = torch.empty(cap_b, 12, device=dev)
+    ovf_b = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def bin_tiles():
+        _lib.check(L.gb_bin_tiles_pack(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
+                                       col3.data_ptr(), op1.data_ptr(), comp.data_ptr(), H, W, BW, cap_b,
+                                       bins_b.data_ptr(), order_b.data_ptr(), gids_b.data_ptr(), rec_b.data_ptr(), None,
+                                       ovf_b.data_ptr(), ws_b.data_ptr(), st), "bin_tiles_pack")
+
+    bin_tiles()
+    torch.cuda.synchronize()
+    assert torch.equal(bins_b, bins) and torch.equal(gids_b[:n], gids) and int(ovf_b) == 0, "bucket binning != key sort"
 
     def timeit(fn, reps=20):
         ts = []
@@ -217,12 +236,15 @@ def kernel_roofline(dev, packed, cam, flush):
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
 
-    t_p, t_f, t_b = timeit(pack), timeit(fwd), timeit(bwd)
+    t_p, t_f, t_b, t_bin = timeit(pack), timeit(fwd), timeit(bwd), timeit(bin_tiles)
     P, T, I = H * W, tb[0] * tb[1], n
     # SURVEY.md §8d per-unit figures, with C = 4 colour channels (rgb + depth in one pass)
     bytes_f = I * (4 + 24 + 4 * C) + P * (4 * C + 4 + 4) + T * 8
     bytes_b = I * (4 + 24 + 4 * C) + I * (4 * (C + 6)) + P * (8 + 4 * C + 4)
     bytes_p = I * (4 + 24 + 4 * C) + I * 48
+    # binning: keys/ranks of G Gaussians through 4 radix passes + bbox reads twice, one rank written and read per
+    # intersection, sorted id written and read, record gather + write
+    bytes_bin = G * (4 * 16 + 2 * 16) + I * (8 + 8) + I * (24 + 4 * C) + I * 48
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -234,10 +256,19 @@ def kernel_roofline(dev, packed, cam, flush):
         "blend_fwd_packed_kernel<4>": {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
         "blend_bwd_packed_kernel<4>": {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
         "pack_records_kernel<4>": {"ms": t_p, "alg_bytes": bytes_p, "gbs": bytes_p / t_p / 1e6},
+        "bin_tiles_pack (9 launches: rank sort, buckets, bitmap sort + pack)": {
+            "ms": t_bin, "alg_bytes": bytes_bin, "gbs": bytes_bin / t_bin / 1e6},
     }
-    dom = max(ks, key=lambda k: ks[k]["ms"])
+    dom = max((k for k in ks if k.startswith("blend")), key=lambda k: ks[k]["ms"])
+    # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the same scene
+    # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); not measurable live
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][dom]["dram_bytes"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": ks[dom]["gbs"] / peak, "traffic": None, "peak_source": which, "intersections": int(I),
+            "frac": ks[dom]["gbs"] / peak, "traffic": traffic, "peak_source": which, "intersections": int(I),
             "kernels": ks}
     return roof
 
@@ -528,6 +559,7 @@ def run_ours(args):
                    "host_path": ("eager, exact buffers, 1 host sync/view" if cap is None else
                                  ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
                                                                                  ", step captured in a CUDA graph"))),
+                   "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
                    "intersection_overflow": overflow},
         "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,

@@ -38,6 +38,9 @@ SIGNATURES = {
     "gb_map_gaussian_to_intersects_dn": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "gb_sort_intersects_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "gb_get_tile_bin_edges_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "gb_bin_tiles_supported": (_i, [_i]),
+    "gb_bin_tiles_workspace_bytes": (_sz, [_i, _i, _i64]),
+    "gb_bin_tiles_pack": (_i, [_i] + [_vp] * 7 + [_i, _i, _i, _i64] + [_vp] * 7 + [_vp]),
     "gb_splat_grad_unpack": (_i, [_i] + [_vp] * 8 + [_vp]),
     "gb_rasterize_packed_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_packed_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),

@@ -1,0 +1,557 @@
+// goliath_b200/csrc/splat_bin_tiles.cu — tile binning for the fused render path, B200 formulation (sm_100a).
+//
+// Produces exactly what the key sort of csrc/splat_bin.cu produces for the fused render — per-tile
+// [first,last) bins, the Gaussian ids of every tile in front-to-back order (ties: ascending id), and the
+// packed blend records — i.e. the work gsplat 0.1.11 does in bin_and_sort_gaussians (called from
+// rasterize_gaussians, call sites ca_code/utils/render_gsplat.py:65-78,90-104), but without ever sorting
+// the I (tile, depth) intersection keys:
+//
+//   1. depth_keys_kernel     G threads: depth bits -> 32-bit sort key, digit-0 histogram, and the per-tile
+//                            intersection COUNT of every visible Gaussian.  Counts are privatised per CTA in
+//                            shared memory and flushed with one RED per (CTA, non-empty tile): the hot tiles
+//                            of a head scene take ~2000 hits each, which serialise on the L2 atomic unit when
+//                            issued one by one (measured: 118 us -> see profiles/).
+//   2. rank_scatter_kernel   x4: stable LSD radix sort of the G depth keys (8-bit digits).  One kernel per
+//                            pass: a CTA derives its own scatter bases from the per-CTA histogram table
+//                            (column prefix read from L2) and accumulates the NEXT pass's table with global
+//                            atomics while it scatters; a pass whose digit is the same for every key (the
+//                            exponent byte of the depths) degenerates to a copy.  Result: rank_of[g] (unique,
+//                            ties by ascending id) and rank_to_gid[rank].  This sorts G = 300k 4-byte keys
+//                            instead of I = 1.08 M 12-byte (key, id) pairs through 6 passes.
+//   3. tile_scan_kernel      one CTA: exclusive scan of the T counts -> tile_bins (clamped to the capacity),
+//                            scatter cursors, total count, overflow flag.
+//   4. tile_scatter_kernel   G threads: every (Gaussian, tile) pair drops the Gaussian's RANK into the
+//                            tile's bucket (order inside the bucket arbitrary).  Slots are claimed per CTA:
+//                            count in shared memory, one atomicAdd per (CTA, tile) on the global cursor, then
+//                            shared-memory atomics hand out the slots.  The same threads write the 48-byte
+//                            blend record of their Gaussian into a table indexed BY RANK (cull box computed
+//                            once per Gaussian, not once per intersection).
+//   5. tile_sort_pack_kernel one CTA per tile, longest first: the ranks of a bucket are unique integers
+//                            < G, so sorting them is setting bits in a G-bit bitmap in shared memory
+//                            (37.5 KB at 300k, 128 KB at 1 M) and reading the bits back in order:
+//                            popcount prefix -> sorted ranks -> (Gaussian id, record copied from the by-rank
+//                            table with monotonically increasing addresses), written linearly.
+//
+// Integer/byte work with a BIT-EXACT contract: gids_sorted, tile_bins and records are identical to the
+// key-sort path's (tests/test_splat_gpu.py::test_bin_tiles_matches_key_sort).
+#include "common.cuh"
+#include "splat_record.cuh"
+
+extern "C" int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
+
+namespace {
+
+constexpr int kRankBlock = 256;                       // 8 warps
+constexpr int kRadix = 256;
+constexpr int kRankPasses = 4;                        // 32 key bits
+constexpr int kScatItems = 2;                         // Gaussians per thread in tile_scatter_kernel
+constexpr int kSortThreads = 512;
+constexpr int kCopyBatch = 2;                         // records copied per thread per round trip (register budget)
+constexpr int kMaxBitmapBytes = 200 * 1024;           // bitmap of one tile must fit the SM's shared memory
+constexpr int kMaxSmemTiles = 20 * 1024;              // per-CTA tile counters (x2 in the scatter) in shared memory
+
+// keys per thread of the rank sort: 8 (2048 keys per CTA: 147 CTAs at 300k, one per SM) up to ~400k Gaussians,
+// 16 beyond (the per-CTA column prefix over the histogram table grows with the square of the CTA count)
+inline int rank_items(int G) { return G <= 2048 * 192 ? 8 : 16; }
+
+// exclusive prefix of v over the CTA (any multiple of 32 threads up to 1024); total = CTA sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  total = s_warp[32];
+  const int r = s_warp[warp] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+// tile rectangle of a Gaussian: same arithmetic as map_to_intersects_kernel (csrc/splat_bin.cu)
+__device__ __forceinline__ void tile_bbox(float cx, float cy, float radius, int tbx, int tby, int bw, int& x0,
+                                          int& y0, int& x1, int& y1) {
+  const float fb = (float)bw;
+  const float tcx = __fdiv_rn(cx, fb), tcy = __fdiv_rn(cy, fb), tr = __fdiv_rn(radius, fb);
+  x0 = min(max(0, __float2int_rz(__fsub_rn(tcx, tr))), tbx);
+  x1 = min(max(0, __float2int_rz(__fadd_rn(__fadd_rn(tcx, tr), 1.f))), tbx);
+  y0 = min(max(0, __float2int_rz(__fsub_rn(tcy, tr))), tby);
+  y1 = min(max(0, __float2int_rz(__fadd_rn(__fadd_rn(tcy, tr), 1.f))), tby);
+}
+
+// ------------------------------------------------------------------ 1. keys, digit-0 histogram, tile counts
+// smem_tiles = T: per-CTA counters in dynamic shared memory; 0: global atomics (more tiles than fit).
+// A CTA covers one tile of the rank sort (kTileKeys keys) with kGaussBlock threads: few fat CTAs keep the number
+// of counter flushes low, many threads per CTA keep enough loads in flight (the kernel is latency-bound).
+constexpr int kGaussBlock = 1024;
+template <int kTileKeys>
+__global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const float2* __restrict__ xys,
+                                                                 const float* __restrict__ depths,
+                                                                 const int* __restrict__ radii, int tbx, int tby,
+                                                                 int block_width, int smem_tiles,
+                                                                 unsigned* __restrict__ keys,
+                                                                 unsigned* __restrict__ hist0 /* [ctas][256] */,
+                                                                 int* __restrict__ tile_counts) {
+  constexpr int kItems = kTileKeys / kGaussBlock;
+  extern __shared__ int s_cnt[];
+  __shared__ unsigned s_hist[kRadix];
+  if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
+  for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) s_cnt[t] = 0;
+  const int base = blockIdx.x * kTileKeys;
+  unsigned k[kItems];
+  int r[kItems];
+  float2 c[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {  // all loads first: independent, in flight together
+    const int i = base + j * kGaussBlock + threadIdx.x;
+    const bool in = i < G;
+    k[j] = in ? __float_as_uint(depths[i]) : 0u;
+    r[j] = in ? radii[i] : 0;
+    c[j] = in ? xys[i] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = base + j * kGaussBlock + threadIdx.x;
+    if (i >= G) continue;
+    keys[i] = k[j];
+    atomicAdd(&s_hist[k[j] & 0xffu], 1u);
+    if (r[j] > 0) {
+      int x0, y0, x1, y1;
+      tile_bbox(c[j].x, c[j].y, (float)r[j], tbx, tby, block_width, x0, y0, x1, y1);
+      for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) {
+          if (smem_tiles) atomicAdd(&s_cnt[ty * tbx + tx], 1);
+          else atomicAdd(&tile_counts[ty * tbx + tx], 1);
+        }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kRadix) hist0[(size_t)blockIdx.x * kRadix + threadIdx.x] = s_hist[threadIdx.x];
+  for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) {
+    const int cnt = s_cnt[t];
+    if (cnt) atomicAdd(&tile_counts[t], cnt);
+  }
+}
+
+// ------------------------------------------------------------------ 2. one radix pass over the G depth keys
+// warp w of a CTA owns the contiguous chunk [cta_base + w*32*kItems, +32*kItems), lane-strided inside the
+// chunk, so that "earlier in memory" == (smaller item index j, then smaller lane): the ranking is stable.
+template <int kItems>
+__global__ void __launch_bounds__(kRankBlock) rank_scatter_kernel(
+    int n, const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in /* null: identity */,
+    unsigned* __restrict__ keys_out /* null on the last pass */, int* __restrict__ vals_out, int shift, int ctas,
+    const unsigned* __restrict__ hist_cur /* [ctas][256] of this pass's digit */,
+    unsigned* __restrict__ hist_next /* [ctas][256], zeroed; null on the last pass */,
+    int* __restrict__ rank_of /* last pass only: rank_of[val] = position */) {
+  constexpr int kWarps = kRankBlock / 32;
+  constexpr int kTile = kRankBlock * kItems;
+  __shared__ unsigned s_whist[kWarps][kRadix];
+  __shared__ int s_scan[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // scatter base of (digit d, this CTA): keys with smaller digits anywhere + keys with digit d in earlier CTAs.
+  // Column sums of the CTA-major table, cooperatively: thread (g = t / 64, c = t % 64) adds rows g, g+4, ... of
+  // the 16-byte column group c, so each thread keeps many independent 16-byte loads in flight (a one-thread-
+  // per-digit loop over the rows is a chain of ~ctas/8 L2 round trips and dominated the pass).
+  __shared__ uint4 s_part[2][4][kRadix / 4];
+  {
+    const int g = threadIdx.x >> 6, c4 = threadIdx.x & 63;
+    const uint4* tab = reinterpret_cast<const uint4*>(hist_cur);
+    uint4 tot = make_uint4(0u, 0u, 0u, 0u), bef = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 8
+    for (int b = g; b < ctas; b += 4) {
+      const uint4 h = tab[(size_t)b * (kRadix / 4) + c4];
+      tot.x += h.x; tot.y += h.y; tot.z += h.z; tot.w += h.w;
+      if (b < (int)blockIdx.x) { bef.x += h.x; bef.y += h.y; bef.z += h.z; bef.w += h.w; }
+    }
+    s_part[0][g][c4] = tot;
+    s_part[1][g][c4] = bef;
+  }
+  __syncthreads();
+  unsigned before = 0, total = 0;
+  {
+    const unsigned* pt = reinterpret_cast<const unsigned*>(&s_part[0][0][0]);
+    const unsigned* pb = reinterpret_cast<const unsigned*>(&s_part[1][0][0]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      total += pt[g * kRadix + threadIdx.x];
+      before += pb[g * kRadix + threadIdx.x];
+    }
+  }
+  // a digit holding every key makes the pass the identity permutation (typical for the exponent byte)
+  const bool copy_only = __syncthreads_or(total == (unsigned)n) != 0;
+
+  const int warp_base = blockIdx.x * kTile + warp * (32 * kItems);
+  unsigned k[kItems];
+  int v[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = warp_base + j * 32 + lane;
+    k[j] = (i < n) ? keys_in[i] : 0xffffffffu;
+    v[j] = (i < n) ? (vals_in ? vals_in[i] : i) : 0;
+  }
+  if (copy_only) {
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int i = warp_base + j * 32 + lane;
+      if (i < n) {
+        if (keys_out) keys_out[i] = k[j];
+        vals_out[i] = v[j];
+        if (hist_next) atomicAdd(&hist_next[(size_t)blockIdx.x * kRadix + ((k[j] >> (shift + 8)) & 0xffu)], 1u);
+        if (rank_of) rank_of[v[j]] = i;
+      }
+    }
+    return;
+  }
+  int unused;
+  const unsigned digit_base = (unsigned)block_exclusive_scan((int)total, s_scan, unused);
+  const unsigned my_base = digit_base + before;
+
+  for (int d = lane; d < kRadix; d += 32) s_whist[warp][d] = 0;
+  __syncwarp();
+  unsigned rank[kItems];  // rank among equal digits inside this warp's chunk
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = warp_base + j * 32 + lane;
+    const bool valid = i < n;
+    const unsigned dgt = (k[j] >> shift) & 0xffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? dgt : 0x100u);
+    const unsigned lower = peers & ((1u << lane) - 1u);
+    unsigned prev = 0;
+    if (valid) prev = s_whist[warp][dgt];
+    __syncwarp();
+    rank[j] = prev + __popc(lower);
+    if (valid && lower == 0u) s_whist[warp][dgt] = prev + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per-warp counts -> per-warp scatter bases (exclusive over the warps, on top of the global base)
+    const int d = threadIdx.x;
+    unsigned run = my_base;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const unsigned c = s_whist[w][d];
+      s_whist[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = warp_base + j * 32 + lane;
+    if (i < n) {
+      const unsigned dgt = (k[j] >> shift) & 0xffu;
+      const unsigned dst = s_whist[warp][dgt] + rank[j];
+      if (keys_out) keys_out[dst] = k[j];
+      vals_out[dst] = v[j];
+      if (hist_next) atomicAdd(&hist_next[(size_t)(dst / kTile) * kRadix + ((k[j] >> (shift + 8)) & 0xffu)], 1u);
+      if (rank_of) rank_of[v[j]] = (int)dst;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 3. bins from the tile counts (one CTA)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int T, long long cap, const int* __restrict__ counts,
+                                                         int2* __restrict__ tile_bins, int* __restrict__ cursor,
+                                                         int* __restrict__ n_out, int* __restrict__ overflow) {
+  __shared__ int s_warp[33];
+  int carry = 0;
+  for (int base = 0; base < T; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < T) ? counts[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, s_warp, total);
+    if (i < T) {
+      const int s = carry + ex;
+      cursor[i] = s;
+      const int cs = (int)min((long long)s, cap), ce = (int)min((long long)s + v, cap);
+      tile_bins[i] = (ce > cs) ? make_int2(cs, ce) : make_int2(0, 0);  // empty tiles read (0,0), as after torch.zeros
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    if (n_out) *n_out = carry;
+    if (overflow && (long long)carry > cap) *overflow = 1;  // capacity exceeded: caller must re-run
+  }
+}
+
+// ------------------------------------------------------------------ 4. ranks into the tile buckets + by-rank records
+// smem_tiles = T: slots claimed per CTA through shared memory (s_cnt | s_base, 2*T ints); 0: one global atomic
+// per (Gaussian, tile).  kGaussBlock threads x kScatItems Gaussians per CTA (see depth_keys_kernel).
+__global__ void __launch_bounds__(kGaussBlock) tile_scatter_kernel(
+    int G, const float2* __restrict__ xys, const int* __restrict__ radii, const int* __restrict__ rank_of,
+    const float* __restrict__ conics, const float* __restrict__ colors3, const float* __restrict__ depths,
+    const float* __restrict__ opacity, const float* __restrict__ comp, int tbx, int tby, int block_width,
+    long long cap, int smem_tiles, int* __restrict__ cursor, int* __restrict__ tile_ranks,
+    float4* __restrict__ rec_by_rank) {
+  extern __shared__ int s_cnt[];
+  int* s_base = s_cnt + smem_tiles;
+  for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) s_cnt[t] = 0;
+  const int base = blockIdx.x * (kGaussBlock * kScatItems);
+  int rk[kScatItems], r[kScatItems];
+  float2 c[kScatItems];
+#pragma unroll
+  for (int j = 0; j < kScatItems; ++j) {  // all loads first: independent, in flight together
+    const int i = base + j * kGaussBlock + threadIdx.x;
+    const bool in = i < G;
+    r[j] = in ? radii[i] : 0;
+    c[j] = in ? xys[i] : make_float2(0.f, 0.f);
+    rk[j] = in ? rank_of[i] : 0;
+  }
+  __syncthreads();
+  unsigned bx[kScatItems], by[kScatItems];  // x0 | x1 << 16, y0 | y1 << 16 (tile coordinates < 65536)
+#pragma unroll
+  for (int j = 0; j < kScatItems; ++j) {
+    const int i = base + j * kGaussBlock + threadIdx.x;
+    bx[j] = by[j] = 0u;
+    if (r[j] <= 0) continue;
+    int x0, y0, x1, y1;
+    tile_bbox(c[j].x, c[j].y, (float)r[j], tbx, tby, block_width, x0, y0, x1, y1);
+    bx[j] = (unsigned)x0 | ((unsigned)x1 << 16);
+    by[j] = (unsigned)y0 | ((unsigned)y1 << 16);
+    gb::pack_record_fused(i, xys, conics, colors3, depths, opacity, comp, rec_by_rank + 3 * (size_t)rk[j]);
+    for (int ty = y0; ty < y1; ++ty)
+      for (int tx = x0; tx < x1; ++tx) {
+        if (smem_tiles) {
+          atomicAdd(&s_cnt[ty * tbx + tx], 1);
+        } else {
+          const int pos = atomicAdd(&cursor[ty * tbx + tx], 1);
+          if ((long long)pos < cap) tile_ranks[pos] = rk[j];
+        }
+      }
+  }
+  if (!smem_tiles) return;
+  __syncthreads();
+  for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) {
+    const int cnt = s_cnt[t];
+    s_base[t] = cnt ? atomicAdd(&cursor[t], cnt) : 0;
+    s_cnt[t] = 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kScatItems; ++j) {
+    const int x0 = bx[j] & 0xffffu, x1 = bx[j] >> 16, y0 = by[j] & 0xffffu, y1 = by[j] >> 16;
+    for (int ty = y0; ty < y1; ++ty)
+      for (int tx = x0; tx < x1; ++tx) {
+        const int t = ty * tbx + tx;
+        const int pos = s_base[t] + atomicAdd(&s_cnt[t], 1);
+        if ((long long)pos < cap) tile_ranks[pos] = rk[j];
+      }
+  }
+}
+
+// ------------------------------------------------------------------ 5. per-tile bitmap sort + record copy
+__global__ void __launch_bounds__(kSortThreads, 3) tile_sort_pack_kernel(
+    int words /* ceil(G/32) */, int chunk /* bitmap words per thread, odd */, const int* __restrict__ order,
+    const int2* __restrict__ tile_bins, const int* __restrict__ tile_ranks, const int* __restrict__ rank_to_gid,
+    const float4* __restrict__ rec_by_rank, int* __restrict__ gids_sorted, float4* __restrict__ rec) {
+  extern __shared__ unsigned s_bits[];
+  __shared__ int s_warp[33];
+  const int tile = order ? order[blockIdx.x] : (int)blockIdx.x;
+  const int2 range = tile_bins[tile];
+  const int n = range.y - range.x;
+  if (n <= 0) return;  // uniform over the CTA
+  for (int w = threadIdx.x; w < words; w += kSortThreads) s_bits[w] = 0u;
+  __syncthreads();
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kSortThreads) {  // 4 independent loads in flight per thread
+    int r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kSortThreads;
+      r[u] = (i < n) ? tile_ranks[range.x + i] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r[u] >= 0) atomicOr(&s_bits[r[u] >> 5], 1u << (r[u] & 31));
+  }
+  __syncthreads();
+  // thread t owns bitmap words [t*chunk, (t+1)*chunk): odd chunk -> conflict-free shared-memory reads
+  const int w0 = threadIdx.x * chunk, w1 = min(words, w0 + chunk);
+  int cnt = 0;
+  for (int w = w0; w < w1; ++w) cnt += __popc(s_bits[w]);
+  int total;
+  int pos = range.x + block_exclusive_scan(cnt, s_warp, total);
+  for (int w = w0; w < w1; ++w) {  // sorted RANKS, parked in gids_sorted until the copy loop below
+    unsigned m = s_bits[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      gids_sorted[pos++] = w * 32 + b;
+    }
+  }
+  __syncthreads();  // the ranks written above are read back below by other threads of this CTA
+  for (int i0 = threadIdx.x; i0 < n; i0 += kCopyBatch * kSortThreads) {  // kCopyBatch records per thread per round trip
+    int r[kCopyBatch], g[kCopyBatch];
+    float4 q[kCopyBatch][3];
+#pragma unroll
+    for (int u = 0; u < kCopyBatch; ++u) {
+      const int i = i0 + u * kSortThreads;
+      r[u] = (i < n) ? __ldcg(gids_sorted + (size_t)range.x + i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kCopyBatch; ++u) {
+      if (r[u] < 0) continue;
+      g[u] = rank_to_gid[r[u]];
+      const float4* src = rec_by_rank + 3 * (size_t)r[u];
+      q[u][0] = gb::ld_nc_f4(src);
+      q[u][1] = gb::ld_nc_f4(src + 1);
+      q[u][2] = gb::ld_nc_f4(src + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < kCopyBatch; ++u) {
+      if (r[u] < 0) continue;
+      const size_t idx = (size_t)range.x + i0 + u * kSortThreads;
+      gids_sorted[idx] = g[u];
+      rec[3 * idx + 0] = q[u][0];
+      rec[3 * idx + 1] = q[u][1];
+      rec[3 * idx + 2] = q[u][2];
+    }
+  }
+}
+
+struct Layout {
+  size_t counts, hist, zero_bytes, cursor, keys_a, keys_b, vals_a, vals_b, rank_of, rec_by_rank, tile_ranks, total;
+};
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+inline Layout make_layout(int G, int T, int64_t cap) {
+  const int g1 = G > 0 ? G : 1;
+  const size_t ctas = (size_t)gb::cdiv(g1, kRankBlock * rank_items(g1));
+  const size_t g4 = align256((size_t)g1 * 4);
+  Layout l;
+  size_t o = 0;
+  l.counts = o; o += align256((size_t)T * 4);
+  l.hist = o;   o += align256(ctas * kRadix * 4 * kRankPasses);
+  l.zero_bytes = o;                       // [counts | hist] are zeroed with one memset per call
+  l.cursor = o; o += align256((size_t)T * 4);
+  l.keys_a = o; o += g4;
+  l.keys_b = o; o += g4;
+  l.vals_a = o; o += g4;
+  l.vals_b = o; o += g4;
+  l.rank_of = o; o += g4;
+  l.rec_by_rank = o; o += align256((size_t)g1 * 48);
+  l.tile_ranks = o; o += align256((size_t)(cap > 0 ? cap : 1) * 4);
+  l.total = o;
+  return l;
+}
+
+template <int kItems>
+void launch_rank_sort(int G, int ctas, const float* xys, const float* depths, const int32_t* radii, int tbx, int tby,
+                      int block_width, int smem_tiles, unsigned* keys_a, unsigned* keys_b, int* vals_a, int* vals_b,
+                      unsigned* hist, int* counts, int* rank_of, cudaStream_t s) {
+  const size_t hs = (size_t)ctas * kRadix;
+  depth_keys_kernel<kRankBlock * kItems><<<ctas, kGaussBlock, (size_t)smem_tiles * 4, s>>>(
+      G, (const float2*)xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, hist, counts);
+  // pass 0: a -> b (ids = identity), 1: b -> a, 2: a -> b, 3: b -> a (ids only) => rank_to_gid = vals_a
+  rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_a, nullptr, keys_b, vals_b, 0, ctas, hist, hist + hs,
+                                                          nullptr);
+  rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_b, vals_b, keys_a, vals_a, 8, ctas, hist + hs,
+                                                          hist + 2 * hs, nullptr);
+  rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_a, vals_a, keys_b, vals_b, 16, ctas, hist + 2 * hs,
+                                                          hist + 3 * hs, nullptr);
+  rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_b, vals_b, nullptr, vals_a, 24, ctas, hist + 3 * hs,
+                                                          nullptr, rank_of);
+}
+
+// opt in to the large dynamic shared-memory window, once per device and kernel
+template <typename K>
+int opt_in_smem(K kernel, bool* done) {
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBitmapBytes));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// 1 when gb_bin_tiles_pack supports G Gaussians (one tile's rank bitmap must fit in shared memory)
+GB_API int gb_bin_tiles_supported(int G) { return G >= 1 && ((size_t)gb::cdiv(G, 32) * 4 <= (size_t)kMaxBitmapBytes); }
+
+GB_API size_t gb_bin_tiles_workspace_bytes(int G, int num_tiles, int64_t cap) {
+  return make_layout(G, num_tiles, cap).total;
+}
+
+// Binning + record packing of the fused render (see the header of this file).  Outputs: tile_bins [T,2],
+// tile_order [T] (longest list first), gids_sorted [cap], records [cap,12]; n_out (device int32, may be
+// null) receives the true intersection count, *overflow is set to 1 when it exceeds `cap` (the excess is
+// dropped).  Never allocates, never synchronises; capturable in a CUDA graph.
+GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                             const float* colors3, const float* opacity, const float* compensation, int img_h,
+                             int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
+                             int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
+                             void* workspace, void* stream) {
+  if (!gb_bin_tiles_supported(G) || block_width < 1 || cap < 0) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tbx = gb::cdiv(img_w, block_width), tby = gb::cdiv(img_h, block_width);
+  const int T = tbx * tby;
+  if (T < 1 || tbx > 65535 || tby > 65535) return (int)cudaErrorInvalidValue;
+  const Layout l = make_layout(G, T, cap);
+  char* ws = (char*)workspace;
+  int* counts = (int*)(ws + l.counts);
+  unsigned* hist = (unsigned*)(ws + l.hist);
+  int* cursor = (int*)(ws + l.cursor);
+  unsigned* keys_a = (unsigned*)(ws + l.keys_a);
+  unsigned* keys_b = (unsigned*)(ws + l.keys_b);
+  int* vals_a = (int*)(ws + l.vals_a);
+  int* vals_b = (int*)(ws + l.vals_b);
+  int* rank_of = (int*)(ws + l.rank_of);
+  float4* rec_by_rank = (float4*)(ws + l.rec_by_rank);
+  int* tile_ranks = (int*)(ws + l.tile_ranks);
+  const int items = rank_items(G);
+  const int ctas = gb::cdiv(G, kRankBlock * items);
+  const int smem_tiles = (T <= kMaxSmemTiles) ? T : 0;
+  static bool s_opt_k8[64] = {}, s_opt_k16[64] = {}, s_opt_scat[64] = {}, s_opt_sort[64] = {};
+  if ((size_t)smem_tiles * 8 > 40 * 1024) {
+    int e = (items == 8) ? opt_in_smem(depth_keys_kernel<kRankBlock * 8>, s_opt_k8)
+                         : opt_in_smem(depth_keys_kernel<kRankBlock * 16>, s_opt_k16);
+    if (e) return e;
+    e = opt_in_smem(tile_scatter_kernel, s_opt_scat);
+    if (e) return e;
+  }
+
+  GB_CUDA(cudaMemsetAsync(ws, 0, l.zero_bytes, s));
+  if (items == 8)
+    launch_rank_sort<8>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b, vals_a, vals_b,
+                        hist, counts, rank_of, s);
+  else
+    launch_rank_sort<16>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b, vals_a, vals_b,
+                         hist, counts, rank_of, s);
+  tile_scan_kernel<<<1, 1024, 0, s>>>(T, (long long)cap, counts, (int2*)tile_bins, cursor, n_out, overflow);
+  gb::count_launches(6);
+  GB_CHECK_LAUNCH();
+  const int e = gb_tile_order(T, tile_bins, tile_order, stream);
+  if (e) return e;
+  tile_scatter_kernel<<<gb::cdiv(G, kGaussBlock * kScatItems), kGaussBlock, (size_t)smem_tiles * 8, s>>>(
+      G, (const float2*)xys, radii, rank_of, conics, colors3, depths, opacity, compensation, tbx, tby, block_width,
+      (long long)cap, smem_tiles, cursor, tile_ranks, rec_by_rank);
+  const int words = gb::cdiv(G, 32);
+  const int chunk = gb::cdiv(words, kSortThreads) | 1;
+  const size_t smem = (size_t)words * 4;
+  if (smem > 40 * 1024) {
+    const int e2 = opt_in_smem(tile_sort_pack_kernel, s_opt_sort);
+    if (e2) return e2;
+  }
+  tile_sort_pack_kernel<<<T, kSortThreads, smem, s>>>(words, chunk, tile_order, (const int2*)tile_bins, tile_ranks,
+                                                      vals_a, rec_by_rank, gids_sorted, (float4*)records);
+  gb::count_launches(2);
+  GB_CHECK_LAUNCH();
+  return 0;
+}

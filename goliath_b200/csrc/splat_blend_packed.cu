@@ -21,6 +21,7 @@
 //     exchange (12 shuffles instead of 50), accumulated per CTA in shared memory, and flushed with one set
 //     of RED atomics per (tile, Gaussian).
 #include "common.cuh"
+#include "splat_record.cuh"
 
 namespace {
 
@@ -72,21 +73,8 @@ __global__ void __launch_bounds__(256) pack_records_kernel(long long n, const in
   const float2 xy = xys[g];
   const float A = conics[3 * g], B = conics[3 * g + 1], Cc = conics[3 * g + 2];
   const float o = opac[g];
-  // alpha >= 1/255  <=>  sigma <= log(255 * o) =: s.  Box of the ellipse {sigma <= s}: ex = sqrt(2 s cov_xx).
   float ex, ey;
-  // 2x2 determinant with the cancellation error recovered (Kahan): the box must bound the ellipse of THIS conic
-  const float bb = B * B;
-  const float det = fmaf(A, Cc, -bb) + fmaf(-B, B, bb);
-  const float s = __logf(255.f * o) + 1e-3f;  // margin keeps the box conservative w.r.t. ex2.approx / rounding
-  if (!(o >= 0.f) || !(det > 0.f) || !(A > 0.f) || !(Cc > 0.f)) {
-    ex = ey = 3.0e38f;  // malformed conic / opacity: never cull, let the per-pixel test decide
-  } else if (s <= 0.f) {
-    ex = ey = -1.f;     // opacity below 1/255: contributes nowhere
-  } else {
-    const float inv = 1.f / det;
-    ex = sqrtf(2.f * s * Cc * inv) * 1.0005f + 1e-3f;
-    ey = sqrtf(2.f * s * A * inv) * 1.0005f + 1e-3f;
-  }
+  gb::cull_box(A, B, Cc, o, ex, ey);
   float c0, c1, c2, c3 = 0.f;
   if (C == 4) {
     const float4 col = reinterpret_cast<const float4*>(colors)[g];
@@ -113,26 +101,7 @@ __global__ void __launch_bounds__(256) pack_records_fused_kernel(long long n_cap
   const long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;  // count may live on the device (sync-free path)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int g = gids_sorted[i];
-  const float2 xy = xys[g];
-  const float A = conics[3 * g], B = conics[3 * g + 1], Cc = conics[3 * g + 2];
-  const float o = opacity[g] * comp[g];
-  float ex, ey;
-  const float bb = B * B;
-  const float det = fmaf(A, Cc, -bb) + fmaf(-B, B, bb);
-  const float s = __logf(255.f * o) + 1e-3f;
-  if (!(o >= 0.f) || !(det > 0.f) || !(A > 0.f) || !(Cc > 0.f)) {
-    ex = ey = 3.0e38f;
-  } else if (s <= 0.f) {
-    ex = ey = -1.f;
-  } else {
-    const float inv = 1.f / det;
-    ex = sqrtf(2.f * s * Cc * inv) * 1.0005f + 1e-3f;
-    ey = sqrtf(2.f * s * A * inv) * 1.0005f + 1e-3f;
-  }
-  rec[3 * i + 0] = make_float4(xy.x, xy.y, ex, ey);
-  rec[3 * i + 1] = make_float4(A, B, Cc, o);
-  rec[3 * i + 2] = make_float4(colors3[3 * g], colors3[3 * g + 1], colors3[3 * g + 2], depths[g]);
+  gb::pack_record_fused(gids_sorted[i], xys, conics, colors3, depths, opacity, comp, rec + 3 * i);
 }
 
 // Backward glue of the fused render: split the blend's per-Gaussian gradients back into the tensors the projection

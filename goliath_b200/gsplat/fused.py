@@ -4,6 +4,8 @@ Equivalent, output for output, to the reference's call sequence in ca_code/utils
 (project_gaussians, rasterize rgb with opacity * compensation, rasterize depth-as-colour) — same kernels, same
 arithmetic — but without the tensors that sequence materialises between the calls (`opacity * compensation[:, None]`,
 `depths[:, None].expand(-1, 3)`, the second binning) and without their autograd glue in the backward."""
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -13,6 +15,10 @@ from .utils import _tile_bounds, _workspace, bin_and_sort_gaussians, compute_cum
 # sync-free mode: per-device overflow flag (int32 on the device, set by the bin-edges kernel when the intersection
 # count exceeded the capacity of the buffers) — read it with check_overflow() at a point where a sync is acceptable
 _OVERFLOW = {}
+
+# binning of the sync-free path: "buckets" (csrc/splat_bin_tiles.cu) or "keysort" (csrc/splat_bin.cu, the gsplat-shaped
+# pipeline: cumsum -> keys -> radix sort -> bin edges -> pack); identical outputs, the switch exists for A/B timing
+BINNING = os.environ.get("GOLIATH_B200_BINNING", "buckets")
 
 
 def _overflow_flag(dev):
@@ -69,28 +75,41 @@ class _RenderFused(Function):
             if capacity is not None:
                 # ---- sync-free path: the count never visits the host; buffers hold `capacity` intersections
                 cap = int(capacity)
-                cum = torch.empty_like(num_tiles_hit)
-                ws = _workspace(dev, max(L.gb_cumsum_workspace_bytes(G), L.gb_sort_workspace_bytes(cap)))
-                _lib.check(L.gb_cumsum_i32(G, _lib.ptr(num_tiles_hit), _lib.ptr(cum), _lib.ptr(ws), st), "cumsum")
-                n_dev = cum.data_ptr() + 4 * (G - 1)
-                isect = torch.empty(cap, device=dev, dtype=torch.int64)
-                gids_u = torch.empty(cap, **i32)
-                isect_s = torch.empty(cap, device=dev, dtype=torch.int64)
                 gids = torch.empty(cap, **i32)
-                bins = torch.zeros(T, 2, **i32)
                 order = torch.empty(T, **i32)
                 records = torch.empty(cap, 12, **f32)
-                _lib.check(L.gb_map_gaussian_to_intersects_dn(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
-                                                              _lib.ptr(cum), H, W, BW, cap, _lib.ptr(isect),
-                                                              _lib.ptr(gids_u), st), "map_dn")
-                _lib.check(L.gb_sort_intersects_dn(cap, n_dev, _lib.ptr(isect), _lib.ptr(gids_u), _lib.ptr(isect_s),
-                                                   _lib.ptr(gids), key_bits(T), _lib.ptr(ws), st), "sort_dn")
-                _lib.check(L.gb_get_tile_bin_edges_dn(cap, n_dev, _lib.ptr(isect_s), _lib.ptr(bins),
-                                                      _lib.ptr(_overflow_flag(dev)), st), "edges_dn")
-                _lib.check(L.gb_tile_order(T, _lib.ptr(bins), _lib.ptr(order), st), "tile_order")
-                _lib.check(L.gb_pack_records_fused_dn(cap, n_dev, _lib.ptr(gids), _lib.ptr(xys), _lib.ptr(conics),
-                                                      _lib.ptr(colors), _lib.ptr(depths), _lib.ptr(opacity),
-                                                      _lib.ptr(comp), _lib.ptr(records), st), "pack_records_fused_dn")
+                if BINNING == "buckets" and L.gb_bin_tiles_supported(G):
+                    # depth ranks + per-tile buckets ordered by a rank bitmap (csrc/splat_bin_tiles.cu): same bins,
+                    # ids and records as the key sort below, without sorting the intersection keys
+                    bins = torch.empty(T, 2, **i32)
+                    ws = _workspace(dev, L.gb_bin_tiles_workspace_bytes(G, T, cap))
+                    _lib.check(L.gb_bin_tiles_pack(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
+                                                   _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity),
+                                                   _lib.ptr(comp), H, W, BW, cap, _lib.ptr(bins), _lib.ptr(order),
+                                                   _lib.ptr(gids), _lib.ptr(records), None,
+                                                   _lib.ptr(_overflow_flag(dev)), _lib.ptr(ws), st), "bin_tiles_pack")
+                else:
+                    cum = torch.empty_like(num_tiles_hit)
+                    ws = _workspace(dev, max(L.gb_cumsum_workspace_bytes(G), L.gb_sort_workspace_bytes(cap)))
+                    _lib.check(L.gb_cumsum_i32(G, _lib.ptr(num_tiles_hit), _lib.ptr(cum), _lib.ptr(ws), st), "cumsum")
+                    n_dev = cum.data_ptr() + 4 * (G - 1)
+                    isect = torch.empty(cap, device=dev, dtype=torch.int64)
+                    gids_u = torch.empty(cap, **i32)
+                    isect_s = torch.empty(cap, device=dev, dtype=torch.int64)
+                    bins = torch.zeros(T, 2, **i32)
+                    _lib.check(L.gb_map_gaussian_to_intersects_dn(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
+                                                                  _lib.ptr(cum), H, W, BW, cap, _lib.ptr(isect),
+                                                                  _lib.ptr(gids_u), st), "map_dn")
+                    _lib.check(L.gb_sort_intersects_dn(cap, n_dev, _lib.ptr(isect), _lib.ptr(gids_u),
+                                                       _lib.ptr(isect_s), _lib.ptr(gids), key_bits(T), _lib.ptr(ws),
+                                                       st), "sort_dn")
+                    _lib.check(L.gb_get_tile_bin_edges_dn(cap, n_dev, _lib.ptr(isect_s), _lib.ptr(bins),
+                                                          _lib.ptr(_overflow_flag(dev)), st), "edges_dn")
+                    _lib.check(L.gb_tile_order(T, _lib.ptr(bins), _lib.ptr(order), st), "tile_order")
+                    _lib.check(L.gb_pack_records_fused_dn(cap, n_dev, _lib.ptr(gids), _lib.ptr(xys), _lib.ptr(conics),
+                                                          _lib.ptr(colors), _lib.ptr(depths), _lib.ptr(opacity),
+                                                          _lib.ptr(comp), _lib.ptr(records), st),
+                               "pack_records_fused_dn")
                 _lib.check(L.gb_rasterize_packed_fwd(H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records),
                                                      _lib.ptr(bg4), _lib.ptr(out4), _lib.ptr(final_Ts),
                                                      _lib.ptr(final_idx), st), "rasterize_packed_forward")

@@ -135,6 +135,20 @@ int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* g
                              const float* conics, const float* colors3, const float* depths, const float* opacity,
                              const float* compensation, float* records, void* stream);
 
+/* Bucket binning of the fused render (csrc/splat_bin_tiles.cu): replaces, for the fused path, the whole of gsplat
+ * 0.1.11 bin_and_sort_gaussians (compute_cumulative_intersects, map_gaussian_to_intersects, torch.sort,
+ * get_tile_bin_edges — call sites ca_code/utils/render_gsplat.py:65-78,90-104) plus the record packing, with the same
+ * bit-exact outputs: Gaussians are depth-ranked once (G keys), intersections are bucketed per tile with atomics, and
+ * each tile's bucket is ordered with a rank bitmap in shared memory.  Outputs: tile_bins [T,2], tile_order [T],
+ * gids_sorted [cap], records [cap,12]; n_out (device int32, may be NULL) = true intersection count; *overflow = 1
+ * when it exceeds cap (the excess is dropped).  Sync-free, never allocates, capturable in a CUDA graph. */
+int gb_bin_tiles_supported(int G); /* 1 if one tile's G-bit rank bitmap fits in shared memory */
+size_t gb_bin_tiles_workspace_bytes(int G, int num_tiles, int64_t cap);
+int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                      const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
+                      int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int32_t* gids_sorted,
+                      float* records, int32_t* n_out, int32_t* overflow, void* workspace, void* stream);
+
 /* launch order of the tiles, longest list first: order [T] int32 */
 int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
 

@@ -481,3 +481,78 @@ def test_render_views_fused_matches_reference_sequence(cuda):
     assert_close(d1, d0, rtol=1e-6, atol=1e-6, what="normalised depth")
     for k in g0:
         assert_close(g1[k], g0[k], rtol=1e-4, atol=2e-5 * np.abs(g0[k]).max(), frac=0.999, what="grad " + k)
+
+
+@pytest.mark.parametrize("case", ["dense96", "ragged", "bw8", "ties", "tiny_prims", "one_cta", "two_ctas", "big",
+                                  "many_tiles", "too_many_tiles", "sixteen_per_thread"])
+def test_bin_tiles_matches_key_sort(cuda, case):
+    """The bucket binning of the fused render (depth ranks + per-tile bitmap sort, csrc/splat_bin_tiles.cu) returns
+    bit for bit the bins, sorted Gaussian ids and blend records of the key-sort path (csrc/splat_bin.cu + pack)."""
+    from goliath_b200 import _lib
+    from goliath_b200.gsplat import utils as gu
+
+    extra = {
+        "one_cta": (dict(G=4096, img_h=96, img_w=80, seed=3), 16, 10.0),
+        "two_ctas": (dict(G=4097, img_h=96, img_w=80, seed=4, depth_quant=True), 16, 10.0),
+        "big": (dict(G=150_000, img_h=512, img_w=384, seed=13), 16, 6.0),
+        "many_tiles": (dict(G=30_000, img_h=768, img_w=1024, seed=17), 8, 2.0),        # 12288 tiles: opt-in smem
+        "too_many_tiles": (dict(G=20_000, img_h=600, img_w=640, seed=19), 4, 1.5),     # 24000 tiles: global atomics
+        "sixteen_per_thread": (dict(G=400_000, img_h=256, img_w=192, seed=23), 16, 1.5),
+    }
+    kw, bw, mult = CASES[case] if case in CASES else extra[case]
+    s = small_scene(**kw)
+    H, W = s["img_h"], s["img_w"]
+    xys, depths, radii, conics, comp, nth, cov3d = _project_gpu(s, cuda, bw, mult)
+    t = _dev(s, cuda)
+    colors, opacity = t["colors"].contiguous(), t["opacity"].contiguous()
+    G = xys.shape[0]
+    L = _lib.lib()
+    st = _lib.stream_ptr(cuda)
+    # key-sort path
+    n, cum = gu.compute_cumulative_intersects(nth)
+    assert n > 1000
+    tb = gu._tile_bounds(H, W, bw)
+    T = tb[0] * tb[1]
+    _, _, _, gids_ref, bins_ref = gu.bin_and_sort_gaussians(G, n, xys, depths, radii, cum, tb, bw)
+    rec_ref = torch.empty(n, 12, device=cuda)
+    _lib.check(L.gb_pack_records_fused(n, gids_ref.data_ptr(), xys.data_ptr(), conics.data_ptr(), colors.data_ptr(),
+                                       depths.data_ptr(), opacity.data_ptr(), comp.data_ptr(), rec_ref.data_ptr(), st),
+               "pack")
+    # bucket path, twice (the workspace is reused: stale counters must not leak), then with too small a capacity
+    assert L.gb_bin_tiles_supported(G) == 1
+    for cap in (n + 77, n + 77, n, n // 2):
+        ws = torch.empty(L.gb_bin_tiles_workspace_bytes(G, T, cap), dtype=torch.uint8, device=cuda)
+        bins = torch.full((T, 2), -7, dtype=torch.int32, device=cuda)
+        order = torch.full((T,), -7, dtype=torch.int32, device=cuda)
+        gids = torch.full((cap,), -7, dtype=torch.int32, device=cuda)
+        rec = torch.full((cap, 12), float("nan"), device=cuda)
+        n_out = torch.zeros(1, dtype=torch.int32, device=cuda)
+        ovf = torch.zeros(1, dtype=torch.int32, device=cuda)
+        _lib.check(L.gb_bin_tiles_pack(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
+                                       colors.data_ptr(), opacity.data_ptr(), comp.data_ptr(), H, W, bw, cap,
+                                       bins.data_ptr(), order.data_ptr(), gids.data_ptr(), rec.data_ptr(),
+                                       n_out.data_ptr(), ovf.data_ptr(), ws.data_ptr(), st), "bin_tiles_pack")
+        torch.cuda.synchronize()
+        assert int(n_out) == n
+        assert sorted(t2n(order).tolist()) == list(range(T))
+        if cap >= n:
+            assert int(ovf) == 0
+            assert torch.equal(bins, bins_ref)
+            assert torch.equal(gids[:n], gids_ref)
+            assert torch.equal(rec[:n].view(torch.int32), rec_ref.view(torch.int32))
+            assert bool((gids[n:] == -7).all())
+        else:
+            assert int(ovf) == 1
+            b = t2n(bins).astype(np.int64)
+            br = np.minimum(t2n(bins_ref).astype(np.int64), cap)
+            br[br[:, 1] <= br[:, 0]] = 0
+            assert np.array_equal(b, br)
+            # every surviving bucket is a depth-ordered SUBSET of the reference list of its tile
+            g, gr = t2n(gids), t2n(gids_ref)
+            full = t2n(bins_ref)
+            for tile in np.nonzero(b[:, 1] > b[:, 0])[0][:50]:
+                mine = g[b[tile, 0]:b[tile, 1]]
+                ref_list = gr[full[tile, 0]:full[tile, 1]]
+                pos = {v: i for i, v in enumerate(ref_list.tolist())}
+                idx = [pos[v] for v in mine.tolist()]
+                assert idx == sorted(idx) and len(set(idx)) == len(idx)
