@@ -184,19 +184,22 @@ def kernel_roofline(dev, packed, cam, flush):
     st = _lib.stream_ptr(dev)
     T_ = tb[0] * tb[1]
     rec = torch.empty(n, 12, device=dev)
-    order = torch.empty(T_, dtype=torch.int32, device=dev)
-    _lib.check(L.gb_tile_order(T_, bins.data_ptr(), order.data_ptr(), st), "order")
+    sched = 1 if L.gb_get_blend_mode() == 2 else 0  # SM-affine schedule + the kernels that draw tiles from it
+    order = torch.empty(L.gb_tile_schedule_ints(T_), dtype=torch.int32, device=dev)
+    _lib.check((L.gb_tile_schedule if sched else L.gb_tile_order)(T_, bins.data_ptr(), order.data_ptr(), st), "order")
+    ras_fwd = L.gb_rasterize_sched_fwd if sched else L.gb_rasterize_packed_fwd
+    ras_bwd = L.gb_rasterize_sched_bwd if sched else L.gb_rasterize_packed_bwd
 
     def pack():
         _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), colors.data_ptr(),
                                      opac.data_ptr(), rec.data_ptr(), st), "pack")
 
     def fwd():
-        _lib.check(L.gb_rasterize_packed_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(),
+        _lib.check(ras_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(),
                                              out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "fwd")
 
     def bwd():
-        _lib.check(L.gb_rasterize_packed_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(),
+        _lib.check(ras_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(),
                                              rec.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
                                              v_out.data_ptr(), v_a.data_ptr(), gx.data_ptr(), gc.data_ptr(),
                                              gcol.data_ptr(), go.data_ptr(), st), "bwd")
@@ -207,7 +210,7 @@ def kernel_roofline(dev, packed, cam, flush):
     col3, op1 = u["diff_color"].contiguous(), u["opacity"].contiguous()
     ws_b = torch.empty(L.gb_bin_tiles_workspace_bytes(G, T_, cap_b), dtype=torch.uint8, device=dev)
     bins_b = torch.empty(T_, 2, dtype=torch.int32, device=dev)
-    order_b = torch.empty(T_, dtype=torch.int32, device=dev)
+    order_b = torch.empty(L.gb_tile_schedule_ints(T_), dtype=torch.int32, device=dev)
     gids_b = torch.empty(cap_b, dtype=torch.int32, device=dev)
     rec_b = torch.empty(cap_b, 12, device=dev)
     ovf_b = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -215,7 +218,7 @@ def kernel_roofline(dev, packed, cam, flush):
     def bin_tiles():
         _lib.check(L.gb_bin_tiles_pack(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
                                        col3.data_ptr(), op1.data_ptr(), comp.data_ptr(), H, W, BW, cap_b,
-                                       bins_b.data_ptr(), order_b.data_ptr(), gids_b.data_ptr(), rec_b.data_ptr(), None,
+                                       bins_b.data_ptr(), order_b.data_ptr(), sched, gids_b.data_ptr(), rec_b.data_ptr(), None,
                                        ovf_b.data_ptr(), ws_b.data_ptr(), st), "bin_tiles_pack")
 
     bin_tiles()
@@ -252,9 +255,12 @@ def kernel_roofline(dev, packed, cam, flush):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured" if "hbm_gbs" in peaks else "fallback"
+    mode = int(L.gb_get_blend_mode())
+    fwd_name = "blend_fwd_packed_kernel<4>" if mode == 0 else "blend_fwd_pipe_kernel<4>"
+    bwd_name = "blend_bwd_packed_kernel<4>" if mode == 0 else "blend_bwd_pipe_kernel<4>"
     ks = {
-        "blend_fwd_packed_kernel<4>": {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
-        "blend_bwd_packed_kernel<4>": {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
+        fwd_name: {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
+        bwd_name: {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
         "pack_records_kernel<4>": {"ms": t_p, "alg_bytes": bytes_p, "gbs": bytes_p / t_p / 1e6},
         "bin_tiles_pack (9 launches: rank sort, buckets, bitmap sort + pack)": {
             "ms": t_bin, "alg_bytes": bytes_bin, "gbs": bytes_bin / t_bin / 1e6},
@@ -560,6 +566,8 @@ def run_ours(args):
                                  ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
                                                                                  ", step captured in a CUDA graph"))),
                    "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
+                   "blend": ["batch (CTA-synchronous)", "pipe (warp-decoupled)", "affine (warp-decoupled, SM-affine "
+                             "tile schedule)"][int(lib.gb_get_blend_mode())],
                    "intersection_overflow": overflow},
         "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,

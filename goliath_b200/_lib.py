@@ -40,8 +40,14 @@ SIGNATURES = {
     "gb_get_tile_bin_edges_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "gb_bin_tiles_supported": (_i, [_i]),
     "gb_bin_tiles_workspace_bytes": (_sz, [_i, _i, _i64]),
-    "gb_bin_tiles_pack": (_i, [_i] + [_vp] * 7 + [_i, _i, _i, _i64] + [_vp] * 7 + [_vp]),
+    "gb_bin_tiles_pack": (_i, [_i] + [_vp] * 7 + [_i, _i, _i, _i64] + [_vp, _vp, _i] + [_vp] * 5 + [_vp]),
+    "gb_tile_schedule_ints": (_i, [_i]),
+    "gb_tile_schedule": (_i, [_i, _vp, _vp, _vp]),
+    "gb_rasterize_sched_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
+    "gb_rasterize_sched_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
     "gb_splat_grad_unpack": (_i, [_i] + [_vp] * 8 + [_vp]),
+    "gb_get_blend_mode": (_i, []),
+    "gb_set_blend_mode": (None, [_i]),
     "gb_rasterize_packed_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_packed_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
     "gb_compute_raydirs_fwd": (_i, [_i, _i, _i] + [_vp] * 5 + [_f] + [_vp] * 3 + [_vp]),

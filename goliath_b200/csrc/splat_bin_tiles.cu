@@ -38,6 +38,7 @@
 #include "splat_record.cuh"
 
 extern "C" int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
+extern "C" int gb_tile_schedule(int num_tiles, const int32_t* tile_bins, int32_t* sched, void* stream);
 
 namespace {
 
@@ -47,7 +48,7 @@ constexpr int kRankPasses = 4;                        // 32 key bits
 constexpr int kScatItems = 2;                         // Gaussians per thread in tile_scatter_kernel
 constexpr int kSortThreads = 512;
 constexpr int kCopyBatch = 2;                         // records copied per thread per round trip (register budget)
-constexpr int kMaxBitmapBytes = 200 * 1024;           // bitmap of one tile must fit the SM's shared memory
+constexpr int kMaxBitmapBytes = 192 * 1024;           // bitmap of one tile must fit the SM's shared memory
 constexpr int kMaxSmemTiles = 20 * 1024;              // per-CTA tile counters (x2 in the scatter) in shared memory
 
 // keys per thread of the rank sort: 8 (2048 keys per CTA: 147 CTAs at 300k, one per SM) up to ~400k Gaussians,
@@ -165,6 +166,16 @@ __global__ void __launch_bounds__(kRankBlock) rank_scatter_kernel(
   __shared__ int s_scan[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  const int warp_base = blockIdx.x * kTile + warp * (32 * kItems);
+  unsigned k[kItems];  // issued before the table reads below: both sets of loads are in flight together
+  int v[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = warp_base + j * 32 + lane;
+    k[j] = (i < n) ? keys_in[i] : 0xffffffffu;
+    v[j] = (i < n) ? (vals_in ? vals_in[i] : i) : 0;
+  }
+
   // scatter base of (digit d, this CTA): keys with smaller digits anywhere + keys with digit d in earlier CTAs.
   // Column sums of the CTA-major table, cooperatively: thread (g = t / 64, c = t % 64) adds rows g, g+4, ... of
   // the 16-byte column group c, so each thread keeps many independent 16-byte loads in flight (a one-thread-
@@ -197,15 +208,6 @@ __global__ void __launch_bounds__(kRankBlock) rank_scatter_kernel(
   // a digit holding every key makes the pass the identity permutation (typical for the exponent byte)
   const bool copy_only = __syncthreads_or(total == (unsigned)n) != 0;
 
-  const int warp_base = blockIdx.x * kTile + warp * (32 * kItems);
-  unsigned k[kItems];
-  int v[kItems];
-#pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const int i = warp_base + j * 32 + lane;
-    k[j] = (i < n) ? keys_in[i] : 0xffffffffu;
-    v[j] = (i < n) ? (vals_in ? vals_in[i] : i) : 0;
-  }
   if (copy_only) {
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
@@ -490,13 +492,14 @@ GB_API size_t gb_bin_tiles_workspace_bytes(int G, int num_tiles, int64_t cap) {
 }
 
 // Binning + record packing of the fused render (see the header of this file).  Outputs: tile_bins [T,2],
-// tile_order [T] (longest list first), gids_sorted [cap], records [cap,12]; n_out (device int32, may be
+// tile_order [T] (longest list first; with tile_sched = 1 an SM-affine schedule of gb_tile_schedule_ints(T)
+// int32, see gb_tile_schedule), gids_sorted [cap], records [cap,12]; n_out (device int32, may be
 // null) receives the true intersection count, *overflow is set to 1 when it exceeds `cap` (the excess is
 // dropped).  Never allocates, never synchronises; capturable in a CUDA graph.
 GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
                              const float* colors3, const float* opacity, const float* compensation, int img_h,
                              int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
-                             int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
+                             int tile_sched, int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
                              void* workspace, void* stream) {
   if (!gb_bin_tiles_supported(G) || block_width < 1 || cap < 0) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
@@ -537,7 +540,8 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   tile_scan_kernel<<<1, 1024, 0, s>>>(T, (long long)cap, counts, (int2*)tile_bins, cursor, n_out, overflow);
   gb::count_launches(6);
   GB_CHECK_LAUNCH();
-  const int e = gb_tile_order(T, tile_bins, tile_order, stream);
+  const int e = tile_sched ? gb_tile_schedule(T, tile_bins, tile_order, stream)
+                           : gb_tile_order(T, tile_bins, tile_order, stream);
   if (e) return e;
   tile_scatter_kernel<<<gb::cdiv(G, kGaussBlock * kScatItems), kGaussBlock, (size_t)smem_tiles * 8, s>>>(
       G, (const float2*)xys, radii, rank_of, conics, colors3, depths, opacity, compensation, tbx, tby, block_width,

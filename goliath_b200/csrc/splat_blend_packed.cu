@@ -21,44 +21,12 @@
 //     exchange (12 shuffles instead of 50), accumulated per CTA in shared memory, and flushed with one set
 //     of RED atomics per (tile, Gaussian).
 #include "common.cuh"
+#include "splat_blend_common.cuh"
 #include "splat_record.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kBatch = 256;
-constexpr int kRecFloats = 12;  // x y ex ey | A B C opac | c0 c1 c2 c3
-constexpr int kRecBytes = kRecFloats * 4;
-constexpr float kAlphaMaxFwd = 0.999f;
-constexpr float kAlphaMaxBwd = 0.99f;  // gsplat 0.1.x backward constant (oracle: ORC_BWD_ALPHA_CLAMP)
-constexpr float kAlphaMin = 1.f / 255.f;
-constexpr float kTEps = 1e-4f;
-
-// ------------------------------------------------------------------ mbarrier / bulk-copy primitives
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-  } while (!ok);
-}
+using namespace gbblend;
 
 // ------------------------------------------------------------------ record packing
 template <int C>
@@ -124,8 +92,12 @@ __global__ void __launch_bounds__(256) splat_grad_unpack_kernel(int G, const flo
 
 // ------------------------------------------------------------------ LPT tile order (single CTA)
 // order[] = tile ids sorted by descending list length (bucketed, stable); any tile count.
+// With queues = Q > 0 the same array is a SCHEDULE (gb_tile_schedule): position p = k*Q + q is the k-th work item of
+// queue q, the sorted sequence is dealt to the queues boustrophedon-wise (every other group of Q reversed), so the
+// queues carry near-equal sums of list lengths, and Q + 1 draw counters follow at order[T .. T+Q] (zeroed here,
+// restored to zero by every kernel launch that draws from them).
 __global__ void __launch_bounds__(1024) tile_order_kernel(int T, const int2* __restrict__ tile_bins,
-                                                          int* __restrict__ order) {
+                                                          int* __restrict__ order, int queues) {
   constexpr int kBuckets = 1024;
   __shared__ int s_cnt[kBuckets];
   __shared__ int s_warp[33];
@@ -165,9 +137,14 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int T, const int2* __r
   // scatter; order inside a bucket is irrelevant for correctness (any permutation is a valid launch order)
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const int2 r = tile_bins[t];
-    const int pos = atomicAdd(&s_cnt[bucket(r.y - r.x)], 1);
+    int pos = atomicAdd(&s_cnt[bucket(r.y - r.x)], 1);
+    if (queues > 0) {
+      const int grp = pos / queues;
+      if ((grp & 1) && (grp + 1) * queues <= T) pos = grp * queues + (queues - 1 - (pos - grp * queues));
+    }
     order[pos] = t;
   }
+  for (int i = threadIdx.x; i <= queues && queues > 0; i += blockDim.x) order[T + i] = 0;
 }
 
 // ------------------------------------------------------------------ shared helpers
@@ -284,50 +261,6 @@ __global__ void __launch_bounds__(kThreads) blend_fwd_packed_kernel(
 }
 
 // ------------------------------------------------------------------ backward
-// Recursive-halving reduction of 10 per-lane values over the warp: 5+3+2+1+1 = 12 shuffles.
-// On return the lane with index L holds the warp total of slot slot_of(L) in `r` (for lanes with an even
-// index and a valid slot).  Slot mapping: slot = 5*b4 + 3*b3 + 2*b2 + b1 (bits of the lane index), valid
-// when the partial sizes allow it (see slot_valid()).
-__device__ __forceinline__ float reduce10(const float (&v)[10], int lane, int& slot, bool& valid) {
-  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
-  float a[5];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {  // xor 16: low half keeps v[0..4], high half keeps v[5..9]
-    const float send = h4 ? v[i] : v[5 + i];
-    const float keep = h4 ? v[5 + i] : v[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  float b[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {  // xor 8: low keeps a[0..2], high keeps a[3..4] (+ a zero)
-    const float hi_part = (i < 2) ? a[3 + i] : 0.f;
-    const float send = h3 ? a[i] : hi_part;
-    const float keep = h3 ? hi_part : a[i];
-    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  float c[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {  // xor 4: low keeps b[0..1], high keeps b[2] (+ zero)
-    const float hi_part = (i < 1) ? b[2] : 0.f;
-    const float send = h2 ? b[i] : hi_part;
-    const float keep = h2 ? hi_part : b[i];
-    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  float d;
-  {  // xor 2: low keeps c[0], high keeps c[1]
-    const float send = h1 ? c[0] : c[1];
-    const float keep = h1 ? c[1] : c[0];
-    d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  d += __shfl_xor_sync(0xffffffffu, d, 1);
-  // Which slot did this lane end up with?  10 -> (5|5) by b4; 5 -> (3|2) by b3; the (padded) 3 -> (2|1) by b2;
-  // 2 -> (1|1) by b1.  Padding positions carry zeros and are reported invalid.
-  const int off = (h2 ? 2 : 0) + (h1 ? 1 : 0);          // index inside the part selected by b3
-  valid = !(h2 && h1) && (off < (h3 ? 2 : 3));
-  slot = (h4 ? 5 : 0) + (h3 ? 3 : 0) + off;
-  return d;
-}
-
 template <int C>
 __global__ void __launch_bounds__(kThreads) blend_bwd_packed_kernel(
     int img_w, int img_h, int tbx, const int* __restrict__ order, const int* __restrict__ gids_sorted,
@@ -535,7 +468,20 @@ GB_API int gb_splat_grad_unpack(int G, const float* v_colors4, const float* v_op
 // Launch order of the tiles: longest list first.  order: [T] int32.
 GB_API int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream) {
   if (num_tiles <= 0) return 0;
-  tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, (const int2*)tile_bins, order);
+  tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, (const int2*)tile_bins, order, 0);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+// SM-affine schedule of the tiles: `sched` holds gb_tile_schedule_ints(num_tiles) int32.  One queue per SM, filled
+// boustrophedon-wise from the longest-first order so that the queues carry near-equal work; consumed by
+// gb_rasterize_sched_fwd / _bwd, whose CTAs draw from the queue of the SM they run on (csrc/splat_blend_pipe.cu).
+GB_API int gb_tile_schedule_ints(int num_tiles) { return (num_tiles > 0 ? num_tiles : 0) + gbblend::kSchedQueues + 1; }
+GB_API int gb_tile_schedule(int num_tiles, const int32_t* tile_bins, int32_t* sched, void* stream) {
+  if (num_tiles <= 0) return 0;
+  tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(num_tiles, (const int2*)tile_bins, sched,
+                                                          gbblend::kSchedQueues);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;
@@ -549,6 +495,9 @@ GB_API int gb_rasterize_packed_fwd(int img_h, int img_w, int channels, const int
   if (channels != 3 && channels != 4) return (int)cudaErrorInvalidValue;
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   cudaStream_t s = (cudaStream_t)stream;
+  if (gb_get_blend_mode())  // warp-decoupled pipeline (csrc/splat_blend_pipe.cu), identical outputs
+    return gbblend::launch_fwd_pipe(img_h, img_w, channels, tile_bins, tile_order, 0, records, background, out_img,
+                                    final_Ts, final_idx, s);
   if (channels == 3)
     blend_fwd_packed_kernel<3><<<tbx * tby, kThreads, 0, s>>>(img_w, img_h, tbx, tile_order, (const int2*)tile_bins,
                                                               (const float4*)records, background, final_Ts, final_idx, out_img);
@@ -570,6 +519,10 @@ GB_API int gb_rasterize_packed_bwd(int img_h, int img_w, int channels, const int
   if (channels != 3 && channels != 4) return (int)cudaErrorInvalidValue;
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   cudaStream_t s = (cudaStream_t)stream;
+  if (gb_get_blend_mode())
+    return gbblend::launch_bwd_pipe(img_h, img_w, channels, gids_sorted, tile_bins, tile_order, 0, records, background,
+                                    final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity,
+                                    s);
   if (channels == 3)
     blend_bwd_packed_kernel<3><<<tbx * tby, kThreads, 0, s>>>(img_w, img_h, tbx, tile_order, gids_sorted, (const int2*)tile_bins,
                                                               (const float4*)records, background, final_Ts, final_idx,

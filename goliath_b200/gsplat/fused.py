@@ -72,11 +72,13 @@ class _RenderFused(Function):
                 "project_gaussians_forward")
             tb = _tile_bounds(H, W, BW)
             T = tb[0] * tb[1]
+            # blend mode 2: the tile order is an SM-affine schedule and the blend kernels draw their tiles from it
+            sched = 1 if (capacity is not None and L.gb_get_blend_mode() == 2) else 0
             if capacity is not None:
                 # ---- sync-free path: the count never visits the host; buffers hold `capacity` intersections
                 cap = int(capacity)
                 gids = torch.empty(cap, **i32)
-                order = torch.empty(T, **i32)
+                order = torch.empty(L.gb_tile_schedule_ints(T) if sched else T, **i32)
                 records = torch.empty(cap, 12, **f32)
                 if BINNING == "buckets" and L.gb_bin_tiles_supported(G):
                     # depth ranks + per-tile buckets ordered by a rank bitmap (csrc/splat_bin_tiles.cu): same bins,
@@ -86,7 +88,7 @@ class _RenderFused(Function):
                     _lib.check(L.gb_bin_tiles_pack(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii),
                                                    _lib.ptr(conics), _lib.ptr(colors), _lib.ptr(opacity),
                                                    _lib.ptr(comp), H, W, BW, cap, _lib.ptr(bins), _lib.ptr(order),
-                                                   _lib.ptr(gids), _lib.ptr(records), None,
+                                                   sched, _lib.ptr(gids), _lib.ptr(records), None,
                                                    _lib.ptr(_overflow_flag(dev)), _lib.ptr(ws), st), "bin_tiles_pack")
                 else:
                     cum = torch.empty_like(num_tiles_hit)
@@ -105,14 +107,15 @@ class _RenderFused(Function):
                                                        st), "sort_dn")
                     _lib.check(L.gb_get_tile_bin_edges_dn(cap, n_dev, _lib.ptr(isect_s), _lib.ptr(bins),
                                                           _lib.ptr(_overflow_flag(dev)), st), "edges_dn")
-                    _lib.check(L.gb_tile_order(T, _lib.ptr(bins), _lib.ptr(order), st), "tile_order")
+                    _lib.check((L.gb_tile_schedule if sched else L.gb_tile_order)(T, _lib.ptr(bins), _lib.ptr(order), st),
+                               "tile_order")
                     _lib.check(L.gb_pack_records_fused_dn(cap, n_dev, _lib.ptr(gids), _lib.ptr(xys), _lib.ptr(conics),
                                                           _lib.ptr(colors), _lib.ptr(depths), _lib.ptr(opacity),
                                                           _lib.ptr(comp), _lib.ptr(records), st),
                                "pack_records_fused_dn")
-                _lib.check(L.gb_rasterize_packed_fwd(H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records),
-                                                     _lib.ptr(bg4), _lib.ptr(out4), _lib.ptr(final_Ts),
-                                                     _lib.ptr(final_idx), st), "rasterize_packed_forward")
+                _lib.check((L.gb_rasterize_sched_fwd if sched else L.gb_rasterize_packed_fwd)(
+                    H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4), _lib.ptr(out4),
+                    _lib.ptr(final_Ts), _lib.ptr(final_idx), st), "rasterize_packed_forward")
                 num_intersects = cap  # "some": the backward walks the bins, not the count
             else:
                 num_intersects, cum = compute_cumulative_intersects(num_tiles_hit)
@@ -137,7 +140,7 @@ class _RenderFused(Function):
                                                      _lib.ptr(final_idx), st), "rasterize_packed_forward")
         ctx.save_for_backward(means3d, scales, quats, opacity, viewmat, bg4, cov3d, radii, conics, comp, gids, bins, order,
                               records, final_Ts, final_idx)
-        ctx.meta = (G, H, W, num_intersects, float(glob_scale), float(fx), float(fy))
+        ctx.meta = (G, H, W, num_intersects, float(glob_scale), float(fx), float(fy), sched)
         ctx.mark_non_differentiable(radii)
         ctx.set_materialize_grads(False)
         return out4, 1 - final_Ts, radii
@@ -146,7 +149,7 @@ class _RenderFused(Function):
     def backward(ctx, v_out4, v_alpha, _v_radii):
         (means3d, scales, quats, opacity, viewmat, bg4, cov3d, radii, conics, comp, gids, bins, order, records, final_Ts,
          final_idx) = ctx.saved_tensors
-        G, H, W, num_intersects, glob_scale, fx, fy = ctx.meta
+        G, H, W, num_intersects, glob_scale, fx, fy, sched = ctx.meta
         dev = means3d.device
         L = _lib.lib()
         f32 = dict(device=dev, dtype=torch.float32)
@@ -162,7 +165,7 @@ class _RenderFused(Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             if num_intersects >= 1:
-                _lib.check(L.gb_rasterize_packed_bwd(
+                _lib.check((L.gb_rasterize_sched_bwd if sched else L.gb_rasterize_packed_bwd)(
                     H, W, 4, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4),
                     _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out4), _lib.ptr(v_alpha), _lib.ptr(v_xy),
                     _lib.ptr(v_conic), _lib.ptr(v_col4), _lib.ptr(v_opeff), st), "rasterize_packed_backward")

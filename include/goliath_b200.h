@@ -139,18 +139,41 @@ int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* g
  * 0.1.11 bin_and_sort_gaussians (compute_cumulative_intersects, map_gaussian_to_intersects, torch.sort,
  * get_tile_bin_edges — call sites ca_code/utils/render_gsplat.py:65-78,90-104) plus the record packing, with the same
  * bit-exact outputs: Gaussians are depth-ranked once (G keys), intersections are bucketed per tile with atomics, and
- * each tile's bucket is ordered with a rank bitmap in shared memory.  Outputs: tile_bins [T,2], tile_order [T],
+ * each tile's bucket is ordered with a rank bitmap in shared memory.  Outputs: tile_bins [T,2], tile_order [T]
+ * (tile_sched = 1: an SM-affine schedule of gb_tile_schedule_ints(T) int32 instead, see gb_tile_schedule),
  * gids_sorted [cap], records [cap,12]; n_out (device int32, may be NULL) = true intersection count; *overflow = 1
  * when it exceeds cap (the excess is dropped).  Sync-free, never allocates, capturable in a CUDA graph. */
 int gb_bin_tiles_supported(int G); /* 1 if one tile's G-bit rank bitmap fits in shared memory */
 size_t gb_bin_tiles_workspace_bytes(int G, int num_tiles, int64_t cap);
 int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
                       const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
-                      int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int32_t* gids_sorted,
-                      float* records, int32_t* n_out, int32_t* overflow, void* workspace, void* stream);
+                      int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int tile_sched,
+                      int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
+                      void* stream);
 
 /* launch order of the tiles, longest list first: order [T] int32 */
 int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
+
+/* blend formulation: 0 = CTA-synchronous double buffer (csrc/splat_blend_packed.cu), 1 = warp-decoupled mbarrier
+ * pipeline (csrc/splat_blend_pipe.cu), 2 = the pipeline over an SM-affine tile schedule; environment
+ * GOLIATH_B200_BLEND=batch|pipe|affine.  gb_rasterize_packed_fwd/bwd launch the CTA-synchronous kernels in mode 0 and
+ * the pipeline otherwise; callers that build a schedule use gb_rasterize_sched_fwd/bwd in mode 2.  Outputs are
+ * identical in every mode: pixels bit for bit, gradients to atomics order. */
+int gb_get_blend_mode(void);
+void gb_set_blend_mode(int mode);
+
+/* SM-affine schedule of the tiles (one work queue per SM, near-equal sums of list lengths): sched holds
+ * gb_tile_schedule_ints(num_tiles) int32; consumed by gb_rasterize_sched_fwd/bwd, which take the same arguments as
+ * gb_rasterize_packed_fwd/bwd and give the same outputs. */
+int gb_tile_schedule_ints(int num_tiles);
+int gb_tile_schedule(int num_tiles, const int32_t* tile_bins, int32_t* sched, void* stream);
+int gb_rasterize_sched_fwd(int img_h, int img_w, int channels, const int32_t* tile_bins, int32_t* sched,
+                           const float* records, const float* background, float* out_img, float* final_Ts,
+                           int32_t* final_idx, void* stream);
+int gb_rasterize_sched_bwd(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
+                           int32_t* sched, const float* records, const float* background, const float* final_Ts,
+                           const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
+                           float* v_conic, float* v_colors, float* v_opacity, void* stream);
 
 /* blend forward over packed records streamed with cp.async.bulk; tile_order may be NULL */
 int gb_rasterize_packed_fwd(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,

@@ -31,9 +31,12 @@ v_out = torch.ones(H, W, C, device=dev); v_a = torch.zeros(H, W, device=dev)
 gx, gc, gcol, go = torch.zeros(G, 2, device=dev), torch.zeros(G, 3, device=dev), torch.zeros(G, C, device=dev), torch.zeros(G, 1, device=dev)
 L = _lib.lib(); st = _lib.stream_ptr(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-rec = torch.empty(n, 12, device=dev); order = torch.empty(bins.shape[0], dtype=torch.int32, device=dev)
+sched = L.gb_get_blend_mode() == 2
+rec = torch.empty(n, 12, device=dev); order = torch.empty(L.gb_tile_schedule_ints(bins.shape[0]), dtype=torch.int32, device=dev)
 _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), colors.data_ptr(), opac.data_ptr(), rec.data_ptr(), st), "pack")
-_lib.check(L.gb_tile_order(bins.shape[0], bins.data_ptr(), order.data_ptr(), st), "order")
+_lib.check((L.gb_tile_schedule if sched else L.gb_tile_order)(bins.shape[0], bins.data_ptr(), order.data_ptr(), st), "order")
+ras_fwd = L.gb_rasterize_sched_fwd if sched else L.gb_rasterize_packed_fwd
+ras_bwd = L.gb_rasterize_sched_bwd if sched else L.gb_rasterize_packed_bwd
 import time
 def ev(fn, k=10):
     ts = []
@@ -43,9 +46,9 @@ def ev(fn, k=10):
         a.record(); fn(); b.record(); b.synchronize(); ts.append(a.elapsed_time(b))
     return sum(ts) / len(ts) * 1e3
 def pf():
-    _lib.check(L.gb_rasterize_packed_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "pf")
+    _lib.check(ras_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "pf")
 def pb():
-    _lib.check(L.gb_rasterize_packed_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+    _lib.check(ras_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
                                          v_out.data_ptr(), v_a.data_ptr(), gx.data_ptr(), gc.data_ptr(), gcol.data_ptr(), go.data_ptr(), st), "pb")
 def pk():
     _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), colors.data_ptr(), opac.data_ptr(), rec.data_ptr(), st), "pack")

@@ -274,21 +274,38 @@ def test_product_refuses_cpu_tensors(cuda):
                           torch.eye(4)[:3].contiguous(), 10.0, 10.0, 8.0, 8.0, 16, 16, 16)
 
 
+@pytest.fixture(params=["batch", "pipe", "affine"])
+def blend_mode(request):
+    """The formulations of the packed blend: CTA-synchronous double buffer (csrc/splat_blend_packed.cu), warp-decoupled
+    mbarrier pipeline (csrc/splat_blend_pipe.cu), and the pipeline drawing its tiles from an SM-affine schedule."""
+    from goliath_b200 import _lib
+
+    L = _lib.lib()
+    before = L.gb_get_blend_mode()
+    L.gb_set_blend_mode({"batch": 0, "pipe": 1, "affine": 2}[request.param])
+    yield request.param
+    L.gb_set_blend_mode(before)
+
+
 @pytest.mark.parametrize("C", [3, 4])
-@pytest.mark.parametrize("case", ["dense96", "ragged", "ties", "tiny_prims", "big"])
-def test_packed_blend_matches_generic_kernel(orc, cuda, case, C):
-    """The bulk-copy/culling blend (csrc/splat_blend_packed.cu) must give the generic kernel's pixels BIT-exactly
+@pytest.mark.parametrize("case", ["dense96", "ragged", "ties", "tiny_prims", "big", "long_lists"])
+def test_packed_blend_matches_generic_kernel(orc, cuda, case, C, blend_mode):
+    """The bulk-copy/culling blend (both formulations) must give the generic kernel's pixels BIT-exactly
     (same per-pair arithmetic, culled pairs are exactly the alpha<1/255 ones) and its gradients to atomics order."""
     from goliath_b200 import _lib
 
     if case == "big":
         kw, bw, mult = dict(G=60000, img_h=300, img_w=260, seed=21), 16, 3.0
+    elif case == "long_lists":  # few tiles, thousands of records each, mostly transparent: many pipeline laps per tile
+        kw, bw, mult = dict(G=40000, img_h=48, img_w=40, seed=29), 16, 2.0
     else:
         kw, bw, mult = CASES[case]
     s = small_scene(**kw)
     H, W = s["img_h"], s["img_w"]
     rng = np.random.default_rng(7)
     p, b, colors, bg, opac = _blend_inputs(orc, s, bw, mult, C, rng)
+    if case == "long_lists":
+        opac[p["xys"][:, 0] >= 18.0] *= 0.05  # left part saturates early (warps leave the pipeline), right part never
     opac[::97] = 0.001   # below 1/255: culled everywhere
     opac[::89] = 1.0     # exercises the 0.99 / 0.999 clamps
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
@@ -300,42 +317,52 @@ def test_packed_blend_matches_generic_kernel(orc, cuda, case, C):
     st = _lib.stream_ptr(cuda)
     outs = []
     rec = torch.empty(n, 12, device=cuda)
-    order = torch.empty(T, dtype=torch.int32, device=cuda)
+    affine = blend_mode == "affine"
+    order = torch.full((L.gb_tile_schedule_ints(T),), -1, dtype=torch.int32, device=cuda)
     _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), col.data_ptr(),
                                  op.data_ptr(), rec.data_ptr(), st), "pack")
-    _lib.check(L.gb_tile_order(T, bins.data_ptr(), order.data_ptr(), st), "order")
+    _lib.check((L.gb_tile_schedule if affine else L.gb_tile_order)(T, bins.data_ptr(), order.data_ptr(), st), "order")
+    ras_fwd = L.gb_rasterize_sched_fwd if affine else L.gb_rasterize_packed_fwd
+    ras_bwd = L.gb_rasterize_sched_bwd if affine else L.gb_rasterize_packed_bwd
     torch.cuda.synchronize()
-    o = t2n(order)
+    o = t2n(order[:T])
     assert np.array_equal(np.sort(o), np.arange(T)), "tile order must be a permutation"
-    lens = (b["tile_bins"][:, 1] - b["tile_bins"][:, 0])[o]
-    assert np.all(np.diff(lens >> 3) <= 0), "longest lists first"
-    for packed in (False, True):
+    if affine:
+        assert bool((order[T:] == 0).all()), "draw counters of a fresh schedule"
+    else:
+        lens = (b["tile_bins"][:, 1] - b["tile_bins"][:, 0])[o]
+        assert np.all(np.diff(np.minimum(lens >> 3, 1023)) <= 0), "longest lists first"
+        assert bool((order[T:] == -1).all()), "gb_tile_order writes T entries"
+    for packed in (False, True, True):  # the packed kernels twice: a schedule must be reusable launch after launch
         out = torch.empty(H, W, C, device=cuda)
         Ts = torch.empty(H, W, device=cuda)
         fi = torch.empty(H, W, device=cuda, dtype=torch.int32)
         if packed:
-            _lib.check(L.gb_rasterize_packed_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(),
-                                                 bgd.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "pf")
+            _lib.check(ras_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(),
+                               bgd.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "pf")
         else:
             _lib.check(L.gb_rasterize_fwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(),
                                           conics.data_ptr(), col.data_ptr(), op.data_ptr(), bgd.data_ptr(),
                                           out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "gf")
         torch.cuda.synchronize()
         outs.append((out, Ts, fi))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for k in (1, 2):
+        assert all(torch.equal(outs[0][i], outs[k][i]) for i in range(3)), "packed pixels != generic kernel (pass %d)" % k
+    if affine:
+        assert bool((order[T:] == 0).all()), "draw counters must be back to zero after a launch"
     v_out = d(rng.standard_normal((H, W, C)).astype(np.float32))
     v_alpha = d(rng.standard_normal((H, W)).astype(np.float32))
     G = len(opac)
     grads = []
-    for packed in (False, True):
+    for packed in (False, True, True):
         g = [torch.zeros(G, 2, device=cuda), torch.zeros(G, 3, device=cuda), torch.zeros(G, C, device=cuda),
              torch.zeros(G, 1, device=cuda)]
         Ts, fi = outs[0][1], outs[0][2]
         if packed:
-            _lib.check(L.gb_rasterize_packed_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(),
-                                                 rec.data_ptr(), bgd.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
-                                                 v_out.data_ptr(), v_alpha.data_ptr(), g[0].data_ptr(), g[1].data_ptr(),
-                                                 g[2].data_ptr(), g[3].data_ptr(), st), "pb")
+            _lib.check(ras_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(),
+                               rec.data_ptr(), bgd.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+                               v_out.data_ptr(), v_alpha.data_ptr(), g[0].data_ptr(), g[1].data_ptr(),
+                               g[2].data_ptr(), g[3].data_ptr(), st), "pb")
         else:
             _lib.check(L.gb_rasterize_bwd(H, W, bw, C, gids.data_ptr(), bins.data_ptr(), xys.data_ptr(),
                                           conics.data_ptr(), col.data_ptr(), op.data_ptr(), bgd.data_ptr(),
@@ -343,8 +370,9 @@ def test_packed_blend_matches_generic_kernel(orc, cuda, case, C):
                                           g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), st), "gb")
         torch.cuda.synchronize()
         grads.append([t2n(x) for x in g])
-    for name, x, y in zip(("v_xy", "v_conic", "v_colors", "v_opacity"), grads[1], grads[0]):
-        assert_close(x, y, rtol=2e-5, atol=2e-5 * np.abs(y).max(), what=name + " packed vs generic")
+    for k in (1, 2):
+        for name, x, y in zip(("v_xy", "v_conic", "v_colors", "v_opacity"), grads[k], grads[0]):
+            assert_close(x, y, rtol=2e-5, atol=2e-5 * np.abs(y).max(), what=name + " packed vs generic (pass %d)" % k)
     # and against the oracle
     ref = orc.rasterize_bwd(H, W, bw, b["gaussian_ids_sorted"], b["tile_bins"], p["xys"], p["conics"], colors, opac,
                             bg, t2n(outs[0][1]), t2n(outs[0][2]), t2n(v_out), t2n(v_alpha))
@@ -402,7 +430,7 @@ def test_fused_render_equals_two_pass_and_bin_cache(cuda):
     assert L.gb_launch_count() > 6, "binning must be recomputed when depths changed"
 
 
-def test_sync_free_render_and_cuda_graph(cuda):
+def test_sync_free_render_and_cuda_graph(cuda, blend_mode):
     """capacity=N: no host sync, same pixels and gradients as the exact path; overflow is detected; the whole
     forward+backward can be captured in a CUDA graph and replayed on new inputs."""
     from goliath_b200.gsplat.fused import check_overflow
@@ -530,7 +558,7 @@ def test_bin_tiles_matches_key_sort(cuda, case):
         ovf = torch.zeros(1, dtype=torch.int32, device=cuda)
         _lib.check(L.gb_bin_tiles_pack(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
                                        colors.data_ptr(), opacity.data_ptr(), comp.data_ptr(), H, W, bw, cap,
-                                       bins.data_ptr(), order.data_ptr(), gids.data_ptr(), rec.data_ptr(),
+                                       bins.data_ptr(), order.data_ptr(), 0, gids.data_ptr(), rec.data_ptr(),
                                        n_out.data_ptr(), ovf.data_ptr(), ws.data_ptr(), st), "bin_tiles_pack")
         torch.cuda.synchronize()
         assert int(n_out) == n
