@@ -130,6 +130,48 @@ def test_binning_invariants(orc):
     assert np.array_equal(a[np.lexsort(a.T[::-1])], c[np.lexsort(c.T[::-1])])
 
 
+@pytest.mark.parametrize("quant", [False, True])
+def test_bucket_binning_is_equivalent_to_the_key_sort(orc, quant):
+    """The premise of csrc/splat_bin_tiles.cu, checked on the CPU against the oracle's key sort: rank the Gaussians once
+    by (depth bits, id), bucket the (Gaussian, tile) pairs per tile in ANY order, then order every bucket by setting
+    bits in a G-bit bitmap and reading them back — this reproduces gaussian_ids_sorted and tile_bins exactly, depth
+    ties included (a tile holds a Gaussian at most once, so its ranks are unique)."""
+    s = small_scene(G=4000, depth_quant=quant, seed=13)
+    bw = 16
+    p = orc.project_fwd(s["means3d"], s["scales"] * np.float32(8.0), 1.0, s["quats"], s["viewmat"], s["fx"], s["fy"],
+                        s["cx"], s["cy"], s["img_h"], s["img_w"], bw, 0.1)
+    b = orc.bin_and_sort(p["xys"], p["depths"], p["radii"], p["num_tiles_hit"], s["img_h"], s["img_w"], bw)
+    G = len(p["radii"])
+    tbx, tby = (s["img_w"] + bw - 1) // bw, (s["img_h"] + bw - 1) // bw
+    # 1. depth ranks: stable sort of the 32 depth bits, emission order = ascending id
+    order = np.argsort(p["depths"].view(np.uint32), kind="stable")
+    rank_of = np.empty(G, np.int64)
+    rank_of[order] = np.arange(G)
+    # 2. buckets, filled in a scrambled order (the kernel claims slots with atomics)
+    tiles_of = b["isect_ids"] >> 32
+    perm = np.random.default_rng(5).permutation(len(tiles_of))
+    buckets = {}
+    for t, g in zip(tiles_of[perm], b["gaussian_ids"][perm]):
+        buckets.setdefault(int(t), []).append(int(rank_of[g]))
+    # 3. bitmap sort per tile, bins from the counts
+    gids, bins, start = [], np.zeros((tbx * tby, 2), np.int32), 0
+    for t in range(tbx * tby):
+        ranks = buckets.get(t, [])
+        if not ranks:
+            continue
+        bitmap = np.zeros(G, bool)
+        bitmap[ranks] = True
+        assert bitmap.sum() == len(ranks), "a tile holds every Gaussian at most once"
+        gids.append(order[np.nonzero(bitmap)[0]])
+        bins[t] = (start, start + len(ranks))
+        start += len(ranks)
+    assert start == b["num_intersects"] > 1000
+    assert np.array_equal(bins, b["tile_bins"])
+    assert np.array_equal(np.concatenate(gids).astype(np.int32), b["gaussian_ids_sorted"])
+    if quant:
+        assert (np.diff(b["isect_ids_sorted"]) == 0).sum() > 0, "the scene must contain exact depth ties"
+
+
 def torch_blend(H, W, bw, gids_sorted, tile_bins, xys, conics, colors, opac, bg, alpha_max=0.999):
     """float64 differentiable restatement of the per-pixel front-to-back blend (python loop over the list)."""
     tbx = (W + bw - 1) // bw
