@@ -268,13 +268,16 @@ def kernel_roofline(dev, packed, cam, flush):
     dom = max((k for k in ks if k.startswith("blend")), key=lambda k: ks[k]["ms"])
     # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the same scene
     # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); not measurable live
-    traffic = None
+    traffic, ncu_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][dom]["dram_bytes"]
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][dom]
+        traffic = cap["dram_bytes"]
+        # the blend is not HBM-bound at this operating point: what the same capture says binds it
+        ncu_note = {k: cap[k] for k in ("issue_active_pct", "sm_cycles_active_over_elapsed", "top_stalls") if k in cap}
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": ks[dom]["gbs"] / peak, "traffic": traffic, "peak_source": which, "intersections": int(I),
+            "frac": ks[dom]["gbs"] / peak, "traffic": traffic, "ncu": ncu_note, "peak_source": which, "intersections": int(I),
             "kernels": ks}
     return roof
 
