@@ -10,7 +10,7 @@
 //                            intersection COUNT of every visible Gaussian.  Counts are privatised per CTA in
 //                            shared memory and flushed with one RED per (CTA, non-empty tile): the hot tiles
 //                            of a head scene take ~2000 hits each, which serialise on the L2 atomic unit when
-//                            issued one by one (measured: 118 us -> see profiles/).
+//                            issued one by one (measured: 118 us with one global RED per pair, 8 us privatised).
 //   2. rank_scatter_kernel   x4: stable LSD radix sort of the G depth keys (8-bit digits).  One kernel per
 //                            pass: a CTA derives its own scatter bases from the per-CTA histogram table
 //                            (column prefix read from L2) and accumulates the NEXT pass's table with global

@@ -22,6 +22,10 @@
 //
 // Pixels are bit-identical to the CTA-synchronous kernels (per pixel the records are visited in the same
 // order); gradients agree to the order of the floating-point atomics.
+//
+// Both kernels can also draw their tile from an SM-affine schedule (gb_tile_schedule, draw_tile below) instead of
+// taking order[blockIdx.x]; measured on the bench scene this does not beat the plain longest-first launch order
+// (DESIGN.md section 4), so it is an option (GOLIATH_B200_BLEND=affine), not the default.
 #include <stdlib.h>
 #include <string.h>
 
