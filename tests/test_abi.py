@@ -57,3 +57,31 @@ def test_product_fails_loudly_without_library(monkeypatch, tmp_path):
         assert "no CPU fallback" in str(e) or "not built" in str(e)
     else:
         raise AssertionError("expected GoliathB200Error")
+
+
+def test_host_side_sizing_functions():
+    """Pure host functions of the C ABI (no device work): sizing of the bucket binning, schedule length, blend-mode
+    switch.  They decide buffer sizes on the Python side, so their contract is pinned here."""
+    from goliath_b200 import _lib
+
+    L = _lib.lib()
+    assert L.gb_bin_tiles_supported(1) == 1 and L.gb_bin_tiles_supported(300_000) == 1
+    assert L.gb_bin_tiles_supported(1_048_576) == 1          # native RGCA size: 128 KB bitmap
+    assert L.gb_bin_tiles_supported(0) == 0 and L.gb_bin_tiles_supported(4_000_000) == 0  # bitmap > shared memory
+    T = 42 * 64
+    small = L.gb_bin_tiles_workspace_bytes(300_000, T, 1 << 20)
+    big = L.gb_bin_tiles_workspace_bytes(300_000, T, 1 << 22)
+    assert big - small == ((1 << 22) - (1 << 20)) * 4       # one int32 rank per intersection slot
+    assert small >= 300_000 * (5 * 4 + 48)                   # keys/ids ping-pong + rank_of + by-rank records
+    assert small % 256 == 0
+    assert L.gb_tile_schedule_ints(T) == T + 148 + 1         # one queue per SM + the draw counter
+    before = L.gb_get_blend_mode()
+    try:
+        for m in (0, 1, 2):
+            L.gb_set_blend_mode(m)
+            assert L.gb_get_blend_mode() == m
+        L.gb_set_blend_mode(7)
+        assert L.gb_get_blend_mode() == 2
+    finally:
+        L.gb_set_blend_mode(before)
+    assert before in (0, 1, 2)
