@@ -8,14 +8,19 @@ from torch import Tensor
 from .. import _lib
 
 _WS = {}
+_WS_RETIRED = {}  # outgrown buffers stay allocated: a captured CUDA graph may still hold their addresses
 _DEBUG_ASSUME_N = [None]
 
 
 def _workspace(dev, nbytes: int) -> Tensor:
-    """Grow-only per-device scratch buffer (the C ABI never allocates)."""
+    """Grow-only per-device scratch buffer (the C ABI never allocates).  A buffer that is outgrown is retired, not
+    freed — kernels already captured in a CUDA graph keep pointing into it (sizes grow by at least 25 % per step, so the
+    retired buffers together stay below four times the live one)."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _WS_RETIRED.setdefault(key, []).append(buf)
         buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=dev)
         _WS[key] = buf
     return buf
