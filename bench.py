@@ -550,6 +550,10 @@ def run_ours(args):
                 cpu["decoder_shade"] = cpu_decoder_shade(args.lights)
             except Exception as e:  # the headline line must not depend on this extra
                 cpu["decoder_shade"] = {"error": str(e)[:200]}
+            try:
+                cpu["mesh_vae_decoder"] = cpu_mesh_vae_decoder()
+            except Exception as e:
+                cpu["mesh_vae_decoder"] = {"error": str(e)[:200]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -702,6 +706,30 @@ def cpu_decoder_shade(lights=32, slab=1024):
             "gaussians_decoded_shaded_per_s": G / dt,
             "what": "PyTorch CPU decoder towers + head math (oracle restatement of rgca.py:506-546) + C-oracle SG shade, "
                     "1 frame, native size, random weights"}
+
+
+def cpu_mesh_vae_decoder(frames=3):
+    """BASELINE.json configs[0] / SURVEY.md §8 row R9: the reference's body decoder (mesh_vae.ConvDecoder, 58.7 M
+    parameters, mesh_vae_example.yml) forward for one frame on the host cores — pure PyTorch, the case the reference
+    itself can run without a GPU.  Timed on the restatement oracle/mesh_vae_oracle.py, which is pinned to the reference
+    class by tests/golden/mesh_vae_ref.npz (identical outputs on identical weights).  Bounded: 1 warm-up + `frames`."""
+    from oracle import mesh_vae_oracle as mo
+
+    th = torch
+    th.set_num_threads(os.cpu_count() or 1)
+    dec = mo.seeded_fill(mo.ConvDecoder(mo.synthetic_masks(), mo.identity_resample, mo.uv_vertex_gather()))
+    pose, embs, face = mo.seeded_inputs()
+    ts = []
+    with th.no_grad():
+        dec(pose, embs, face)
+        for _ in range(frames):
+            t0 = time.perf_counter()
+            dec(pose, embs, face)
+            ts.append(time.perf_counter() - t0)
+    return {"s_per_frame": float(np.median(ts)), "frames": frames, "params_M": sum(p.numel() for p in dec.parameters()) / 1e6,
+            "cores": os.cpu_count() or 1, "torch_threads": th.get_num_threads(),
+            "what": "mesh_vae.ConvDecoder forward, 1 frame, uv 1024 (mesh_vae_example.yml), PyTorch CPU, random weights; "
+                    "seam sampler / from_uv replaced by bilinear gathers of the same shapes"}
 
 
 def run_reference(args):
