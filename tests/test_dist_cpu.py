@@ -75,3 +75,16 @@ def test_view_shard_broadcast_and_grad_allreduce():
     assert t0 == t1 and t0 != 0.0, "both ranks must hold the owner's table after the broadcast"
     assert c0 != c1, "ranks render different views"
     assert abs(tot0 - tot1) < 1e-3 * abs(tot0) and abs(tot0 - (g0 + g1)) < 1e-3 * abs(tot0), "all-reduce(sum) of grads"
+
+
+def test_view_partition_of_the_baseline_configs():
+    """BASELINE.json configs[2] / configs[4]: 16 views over 8 GPUs -> 2 per rank; 150 cameras over
+    8 GPUs -> 19 on six ranks, 18 on two; every view exactly once."""
+    from goliath_b200.dist import views_of_rank
+
+    parts = [views_of_rank(r, 8, 16) for r in range(8)]
+    assert all(len(p) == 2 for p in parts) and sorted(sum(parts, [])) == list(range(16))
+    parts = [views_of_rank(r, 8, 150) for r in range(8)]
+    assert sorted(len(p) for p in parts) == [18, 18, 19, 19, 19, 19, 19, 19]
+    assert sorted(sum(parts, [])) == list(range(150))
+    assert views_of_rank(0, 1, 5) == [0, 1, 2, 3, 4] and views_of_rank(3, 4, 2) == []
