@@ -112,6 +112,15 @@ int launch_bwd_pipe(int img_h, int img_w, int channels, const int32_t* gids_sort
                     const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
                     float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s);
 
+// host-side launchers of the hit-ILP forward / transposed-reduction backward (csrc/splat_blend_mom.cu)
+int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+                   const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
+                   cudaStream_t s);
+int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
+                   const int32_t* tile_order, const float* records, const float* background, const float* final_Ts,
+                   const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
+                   float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s);
+
 }  // namespace gbblend
 
 GB_API int gb_get_blend_mode(void);

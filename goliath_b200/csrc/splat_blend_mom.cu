@@ -1,0 +1,526 @@
+// goliath_b200/csrc/splat_blend_mom.cu — third formulation of the packed blend (sm_100a), blend mode 3 (default).
+//
+// Same records, same per-(pixel, Gaussian) arithmetic in the forward and the same gradients as
+// csrc/splat_blend_pipe.cu (gsplat 0.1.11 rasterize_forward / rasterize_backward_kernel, call sites
+// ca_code/utils/render_gsplat.py:65-78,90-104).  Round-1 ncu/SASS of the pipeline kernels (profiles/
+// r01_blend_pipe_ncu.txt) showed both directions bound by the per-warp issue rate on the
+// heaviest tile: ~0.125 IPC per warp on a dependent chain of LDS -> FMA -> ex2 -> shuffles -> shared-memory CAS
+// atomics, 163 instructions per footprint hit in the backward.  What changes here:
+//
+//  cull      the 32-lane record test is the exact minimum of the Gaussian's quadratic form over the warp's 8x4
+//            pixel rectangle (a convex QP on a box: the minimiser lies on one of the two faces visible from the
+//            centre), compared with log(255 * opacity); the axis-aligned box of round 1 passed 10-45 % false hits.
+//  forward   footprint hits are blended four at a time: the four alphas (loads, quadratic form, ex2) are
+//            independent and issue back to back, only the transmittance recurrence is serial.  Pixels stay
+//            bit-identical to the other formulations (same operations in the same order per pixel).
+//  backward  TRANSPOSED reduction.  Hits are compacted into a per-warp list of entries (a copy of the record plus
+//            its sorted index).  For a chunk of 16 entries, phase A runs with lanes = pixels: the serial
+//            transmittance / colour-buffer recurrence, writing (fac, v_sigma) of every (hit, pixel) pair into a
+//            16 x 32 shared-memory matrix (odd row stride).  Phase B runs with lanes = (hit, half of the
+//            footprint): a lane reads ITS hit's row and accumulates v_colour = sum fac * v_out and the image
+//            moments S0, Si, Sj, Sii, Sij of v_sigma over the pixels (pixel offsets are compile-time constants),
+//            from which v_conic, v_xy and v_opacity follow in closed form (dx = u - i, dy = v - j).  One xor-16
+//            shuffle of the 10 sums replaces the 12-shuffle recursive halving PER HIT of round 1, and the lane
+//            that owns the hit adds it to the global gradient arrays with RED (vector RED for the colours): no
+//            shared-memory float atomics (CAS loops in SASS), no per-stage accumulators, no flush tickets.
+//            1 / (1 - alpha) uses rcp.approx (gradients have a 1e-4 bar, not bit parity).
+//
+// Stages are recycled as in the pipeline kernels (mbarrier ring, cp.async.bulk), but a warp has finished with a
+// stage as soon as it has culled it — the entries carry what phases A and B need.
+#include "common.cuh"
+#include "splat_blend_common.cuh"
+
+namespace {
+
+using namespace gbblend;
+
+constexpr int kPixelWarps = 8;
+constexpr int kStageRecs = 128;  // records per pipeline stage (6 KB)
+constexpr int kFwdStages = 4;
+constexpr int kFwdThreads = (kPixelWarps + 1) * 32;
+constexpr int kBwdStages = 3;
+constexpr int kBwdThreads = kPixelWarps * 32;
+constexpr int kChunk = 16;            // hits per transposed-reduction chunk
+constexpr int kEntryCap = 48;         // pending entries per warp: < kChunk left over + up to 32 new
+constexpr int kMStride = 33;          // float2 row stride of the (hit, pixel) matrix: odd -> conflict-free both ways
+constexpr float kCullMargin = 2e-3f;  // slack of the exact cull test (ex2.approx / lg2.approx / rounding)
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Does the record (centre (x, y), conic (A, B, Cc), opacity o) reach alpha >= 1/255 anywhere on the rectangle of pixel
+// centres [fx0, fx1] x [fy0, fy1]?  d = centre - pixel ranges over [x - fx1, x - fx0] x [y - fy1, y - fy0]; sigma(d) is
+// a positive-definite quadratic with its minimum at d = 0.  If 0 is outside the rectangle the minimiser lies on a face
+// from which the segment to 0 leaves the rectangle, i.e. on the line d.x = ex0 or d.y = ey0 (ex0, ey0 = the
+// coordinates of the rectangle nearest to 0); on each line the 1-D minimiser is clamped to the face.  Both candidates
+// are feasible points, so min(f1, f2) >= the true minimum, and one of them attains it.  (ex, ey) is the round-1 box
+// (kept as a cheap pre-test and as the "never cull" marker 3e38 for malformed conics).
+__device__ __forceinline__ bool footprint_hit(const float4 q0, const float4* __restrict__ q1p, float fx0, float fx1,
+                                              float fy0, float fy1) {
+  if (!((q0.x + q0.z >= fx0) && (q0.x - q0.z <= fx1) && (q0.y + q0.w >= fy0) && (q0.y - q0.w <= fy1))) return false;
+  if (q0.z > 1e30f) return true;  // malformed conic / opacity: the per-pixel test decides
+  const float4 q1 = *q1p;         // A B C o
+  const float dxlo = q0.x - fx1, dxhi = q0.x - fx0, dylo = q0.y - fy1, dyhi = q0.y - fy0;
+  const float ex0 = fminf(fmaxf(0.f, dxlo), dxhi), ey0 = fminf(fmaxf(0.f, dylo), dyhi);
+  const float dy1 = fminf(fmaxf(-q1.y * ex0 * rcp_approx(q1.z), dylo), dyhi);
+  const float dx2 = fminf(fmaxf(-q1.y * ey0 * rcp_approx(q1.x), dxlo), dxhi);
+  const float f1 = 0.5f * (q1.x * ex0 * ex0 + q1.z * dy1 * dy1) + q1.y * ex0 * dy1;
+  const float f2 = 0.5f * (q1.x * dx2 * dx2 + q1.z * ey0 * ey0) + q1.y * dx2 * ey0;
+  const float s = __logf(255.f * q1.w);
+  return fminf(f1, f2) <= s + kCullMargin + 1e-4f * fabsf(s);
+}
+
+struct Tile {
+  int tile_id, tx, ty;
+};
+__device__ __forceinline__ Tile make_tile(int tile_id, int tbx) {
+  Tile t;
+  t.tile_id = tile_id;
+  t.ty = tile_id / tbx;
+  t.tx = tile_id - t.ty * tbx;
+  return t;
+}
+
+// ------------------------------------------------------------------ forward
+template <int C>
+__global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
+    int img_w, int img_h, int tbx, const int* __restrict__ order, const int2* __restrict__ tile_bins,
+    const float4* __restrict__ rec, const float* __restrict__ background, float* __restrict__ final_Ts,
+    int* __restrict__ final_idx, float* __restrict__ out_img) {
+  __shared__ __align__(128) float4 s_rec[kFwdStages][kStageRecs * 3];
+  __shared__ __align__(8) unsigned long long s_full[kFwdStages];
+  __shared__ __align__(8) unsigned long long s_empty[kFwdStages];
+  __shared__ int s_ndone;  // pixel warps whose 32 pixels are saturated
+
+  const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+  if (tr == 0) {
+#pragma unroll
+    for (int s = 0; s < kFwdStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kPixelWarps);
+    }
+    s_ndone = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier of this kernel
+  const Tile tl = make_tile(order ? order[blockIdx.x] : (int)blockIdx.x, tbx);
+  const int2 range = tile_bins[tl.tile_id];
+  const int num_batches = (range.y - range.x + kStageRecs - 1) / kStageRecs;
+
+  if (warp == kPixelWarps) {  // ------------------------------ producer warp (one lane)
+    if (lane != 0) return;
+    volatile int* ndone = &s_ndone;
+    int issued = 0;
+    for (int b = 0; b < num_batches; ++b) {
+      const int s = b % kFwdStages;
+      if (b >= kFwdStages) {
+        const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
+        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
+        }
+        if (*ndone >= kPixelWarps) break;  // every pixel of the tile is saturated: nothing more to fetch
+      }
+      const int start = range.x + b * kStageRecs;
+      const unsigned bytes = (unsigned)min(kStageRecs, range.y - start) * kRecBytes;
+      mbar_expect_tx(&s_full[s], bytes);
+      bulk_g2s(&s_rec[s][0], rec + (size_t)start * 3, bytes, &s_full[s]);
+      issued = b + 1;
+    }
+    for (int b = max(0, issued - kFwdStages); b < issued; ++b)  // every issued copy lands before the CTA retires
+      mbar_wait(&s_full[b % kFwdStages], (unsigned)((b / kFwdStages) & 1));
+    return;
+  }
+
+  const int wx0 = tl.tx * 16 + ((warp & 1) << 3), wy0 = tl.ty * 16 + ((warp >> 1) << 2);
+  const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+  const bool inside = (pxi < img_w) && (pyi < img_h);
+  const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+  const float fx0 = (float)wx0 + 0.5f, fx1 = (float)wx0 + 7.5f, fy0 = (float)wy0 + 0.5f, fy1 = (float)wy0 + 3.5f;
+
+  bool done = !inside;
+  float T = 1.f;
+  int cur_idx = 0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  bool counted = false;
+  for (int b = 0; b < num_batches; ++b) {
+    const bool all_done = __all_sync(0xffffffffu, done);
+    if (all_done && !counted) {
+      counted = true;
+      if (lane == 0) atomicAdd(&s_ndone, 1);
+    }
+    const int s = b % kFwdStages;
+    const unsigned par = (unsigned)((b / kFwdStages) & 1);
+    int st = 0;
+    if (lane == 0) {
+      volatile int* ndone = &s_ndone;
+      for (;;) {
+        if (mbar_try(&s_full[s], par)) { st = 1; break; }
+        if (all_done && *ndone >= kPixelWarps) { st = 2; break; }
+      }
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st == 2) break;  // tile finished
+    if (all_done) {      // saturated warp: release the stage untouched, keep the barrier phases aligned
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      continue;
+    }
+    mbar_wait(&s_full[s], par);
+    const float4* sr = s_rec[s];
+    const int batch_start = range.x + b * kStageRecs;
+    const int batch_size = min(kStageRecs, range.y - batch_start);
+    for (int c0 = 0; c0 < batch_size; c0 += 32) {
+      const int ti = c0 + lane;
+      bool hit = false;
+      if (ti < batch_size) hit = footprint_hit(sr[ti * 3], &sr[ti * 3 + 1], fx0, fx1, fy0, fy1);
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        // up to four hits per round: independent alphas, serial transmittance
+        int t[4];
+        bool live[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          live[u] = mask != 0;
+          t[u] = live[u] ? c0 + __ffs(mask) - 1 : t[0];
+          mask &= mask - 1;  // 0 & anything == 0
+        }
+        float alpha[4], sig[4];
+        float4 col[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 q0 = sr[t[u] * 3], q1 = sr[t[u] * 3 + 1];
+          col[u] = sr[t[u] * 3 + 2];
+          const float dx = q0.x - px, dy = q0.y - py;
+          sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+          alpha[u] = fminf(kAlphaMaxFwd, q1.w * __expf(-sig[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
+          const float next_T = T * (1.f - alpha[u]);
+          const bool stop = ok && (next_T <= kTEps);
+          const bool take = ok && !stop;
+          done = done || stop;
+          if (take) {
+            const float vis = alpha[u] * T;
+            acc[0] += col[u].x * vis;
+            acc[1] += col[u].y * vis;
+            acc[2] += col[u].z * vis;
+            if (C == 4) acc[3] += col[u].w * vis;
+            T = next_T;
+            cur_idx = batch_start + t[u];
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+  if (inside) {
+    const size_t pix = (size_t)pyi * img_w + pxi;
+    final_Ts[pix] = T;
+    final_idx[pix] = cur_idx;
+    if (C == 4) {
+      reinterpret_cast<float4*>(out_img)[pix] =
+          make_float4(acc[0] + T * background[0], acc[1] + T * background[1], acc[2] + T * background[2],
+                      acc[3] + T * background[3]);
+    } else {
+      out_img[pix * 3 + 0] = acc[0] + T * background[0];
+      out_img[pix * 3 + 1] = acc[1] + T * background[1];
+      out_img[pix * 3 + 2] = acc[2] + T * background[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward
+// dynamic shared memory layout (bytes): records ring | per-warp entries | per-warp (hit, pixel) matrix | per-warp v_out
+constexpr int kSmRec = kBwdStages * kStageRecs * kRecBytes;                 // 18432
+constexpr int kSmEntries = kPixelWarps * kEntryCap * 48;                    // 18432
+constexpr int kSmM = kPixelWarps * kChunk * kMStride * 8;                   // 33792
+constexpr int kSmVo = kPixelWarps * 32 * 16;                                // 4096
+constexpr int kBwdSmem = kSmRec + kSmEntries + kSmM + kSmVo;                // 74752
+
+template <int C>
+__global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
+    int img_w, int img_h, int tbx, const int* __restrict__ order, const int* __restrict__ gids_sorted,
+    const int2* __restrict__ tile_bins, const float4* __restrict__ rec, const float* __restrict__ background,
+    const float* __restrict__ final_Ts, const int* __restrict__ final_idx, const float* __restrict__ v_output,
+    const float* __restrict__ v_output_alpha, float* __restrict__ v_xy, float* __restrict__ v_conic,
+    float* __restrict__ v_colors, float* __restrict__ v_opacity) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* s_rec = reinterpret_cast<float4*>(smem);
+  __shared__ __align__(8) unsigned long long s_full[kBwdStages];
+  __shared__ int s_ticket[kBwdStages];  // warps that have finished culling the stage's current batch
+  __shared__ int s_cta_final;
+
+  const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+  float4* E = reinterpret_cast<float4*>(smem + kSmRec) + warp * kEntryCap * 3;           // pending entries
+  float2* M = reinterpret_cast<float2*>(smem + kSmRec + kSmEntries) + warp * kChunk * kMStride;
+  float4* VO = reinterpret_cast<float4*>(smem + kSmRec + kSmEntries + kSmM) + warp * 32;
+
+  const Tile tl = make_tile(order ? order[blockIdx.x] : (int)blockIdx.x, tbx);
+  const int2 range = tile_bins[tl.tile_id];
+  if (range.y <= range.x) return;
+  const int wx0 = tl.tx * 16 + ((warp & 1) << 3), wy0 = tl.ty * 16 + ((warp >> 1) << 2);
+  const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+  const bool inside = (pxi < img_w) && (pyi < img_h);
+  const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+  const float fx0 = (float)wx0 + 0.5f, fx1 = (float)wx0 + 7.5f, fy0 = (float)wy0 + 0.5f, fy1 = (float)wy0 + 3.5f;
+  const size_t pix = inside ? ((size_t)pyi * img_w + pxi) : 0;
+
+  const float T_final = inside ? final_Ts[pix] : 1.f;
+  float T = T_final;
+  float buffer[4] = {0.f, 0.f, 0.f, 0.f};
+  const int bin_final = inside ? final_idx[pix] : -1;
+  float vo[4] = {0.f, 0.f, 0.f, 0.f};
+  float voa = 0.f;
+  if (inside) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) vo[c] = v_output[pix * C + c];
+    voa = v_output_alpha[pix];
+  }
+  VO[lane] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+  float bgdot = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) bgdot += background[c] * vo[c];
+  const float tfc = T_final * (voa - bgdot);  // the two T_final * ra terms of v_alpha share it
+
+  int warp_bin_final = bin_final;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
+  if (tr == 0) {
+    s_cta_final = -1;
+#pragma unroll
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      s_ticket[s] = 0;
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_cta_final, warp_bin_final);
+  __syncthreads();
+  // the walk starts at the last index any pixel of the tile needs and goes down to range.x
+  const int last = min(s_cta_final, range.y - 1);
+  if (last < range.x) return;  // no pixel of this tile blended anything (CTA-uniform: nothing is in flight yet)
+  const int num_batches = (last - range.x + kStageRecs) / kStageRecs;
+  auto issue = [&](int k) {  // one lane; batch k covers indices [hi_k - size_k + 1, hi_k], hi_k = last - k*kStageRecs
+    const int s = k % kBwdStages;
+    const int hi = last - k * kStageRecs;
+    const int lo = max(range.x, hi - kStageRecs + 1);
+    const unsigned bytes = (unsigned)(hi - lo + 1) * kRecBytes;
+    mbar_expect_tx(&s_full[s], bytes);
+    bulk_g2s(s_rec + s * kStageRecs * 3, rec + (size_t)lo * 3, bytes, &s_full[s]);
+  };
+  if (tr == 0)
+    for (int k = 0; k < min(kBwdStages, num_batches); ++k) issue(k);
+  // no CTA-wide barrier below this line
+
+  // ---- one chunk of n <= 16 pending entries starting at entry `base`: phase A (lanes = pixels), phase B (lanes = hits)
+  auto chunk = [&](int base, int n) {
+    unsigned anymask = 0;  // bit h: some pixel of the footprint took a gradient from hit h
+#pragma unroll 1
+    for (int h0 = 0; h0 < n; h0 += 4) {
+      float al[4], ov[4], ra[4];
+      float4 col[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int h = min(h0 + u, n - 1);
+        const float4 a0 = E[(base + h) * 3], a1 = E[(base + h) * 3 + 1];  // x y A B | C o idx -
+        col[u] = E[(base + h) * 3 + 2];
+        const float dx = a0.x - px, dy = a0.y - py;
+        const float sigma = 0.5f * (a0.z * dx * dx + a1.x * dy * dy) + a0.w * dx * dy;
+        const float vis = __expf(-sigma);
+        const float alpha = fminf(kAlphaMaxBwd, a1.y * vis);
+        const bool valid = inside && (h0 + u < n) && (__float_as_int(a1.z) <= bin_final) && !(sigma < 0.f) &&
+                           !(alpha < kAlphaMin);
+        al[u] = valid ? alpha : 0.f;
+        ov[u] = valid ? a1.y * vis : 0.f;
+        ra[u] = rcp_approx(1.f - al[u]);  // exactly 1 for the pairs that do not take part
+        if (__ballot_sync(0xffffffffu, valid)) anymask |= 1u << (h0 + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        T *= ra[u];
+        const float fac = al[u] * T;
+        const float cc[4] = {col[u].x, col[u].y, col[u].z, col[u].w};
+        float v_alpha = tfc * ra[u];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          v_alpha += (cc[c] * T - buffer[c] * ra[u]) * vo[c];
+          buffer[c] += cc[c] * fac;
+        }
+        M[(h0 + u) * kMStride + lane] = make_float2(fac, -ov[u] * v_alpha);  // (fac, v_sigma); zeros when not valid
+      }
+    }
+    __syncwarp();
+    {
+      const int hh = lane & 15, half = lane >> 4;
+      const int he = min(hh, n - 1);
+      const float4 a0 = E[(base + he) * 3], a1 = E[(base + he) * 3 + 1];
+      const float2* Mrow = M + hh * kMStride + half * 16;
+      const float4* V = VO + half * 16;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f, sii = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 m = Mrow[q];
+        const float4 v = V[q];
+        const float fi = (float)(q & 7);
+        g[0] += m.x * v.x;
+        g[1] += m.x * v.y;
+        g[2] += m.x * v.z;
+        if (C == 4) g[3] += m.x * v.w;
+        if (q < 8) {
+          r00 += m.y;
+          r10 += m.y * fi;
+        } else {
+          r01 += m.y;
+          r11 += m.y * fi;
+        }
+        sii += m.y * (fi * fi);
+      }
+      // pixel (i, j) of this half: dx = u - i, dy = v - j with j in {0, 1}
+      const float u_ = a0.x - fx0, v_ = a0.y - (fy0 + (float)(2 * half));
+      const float S0 = r00 + r01, Sj = r01, Si = r10 + r11, Sij = r11;
+      const float sx = u_ * S0 - Si, sy = v_ * S0 - Sj;                      // sum v_sigma * dx, * dy
+      const float sxx = u_ * (u_ * S0 - 2.f * Si) + sii;                     // sum v_sigma * dx^2
+      const float sxy = u_ * (v_ * S0 - Sj) - v_ * Si + Sij;                 // sum v_sigma * dx * dy
+      const float syy = v_ * (v_ * S0 - 2.f * Sj) + Sj;                      // sum v_sigma * dy^2  (j^2 == j)
+      float o[10];
+      o[0] = g[0]; o[1] = g[1]; o[2] = g[2]; o[3] = g[3];
+      o[4] = 0.5f * sxx; o[5] = sxy; o[6] = 0.5f * syy;
+      o[7] = a0.z * sx + a0.w * sy;   // v_xy.x = A sx + B sy
+      o[8] = a0.w * sx + a1.x * sy;   // v_xy.y = B sx + C sy
+      o[9] = S0;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+      if (half == 0 && hh < n && ((anymask >> hh) & 1u)) {
+        const int g_id = gids_sorted[__float_as_int(a1.z)];
+        if (C == 4) {
+          gb::red_add_v4(v_colors + 4 * (size_t)g_id, o[0], o[1], o[2], o[3]);
+        } else {
+          gb::red_add(v_colors + 3 * (size_t)g_id + 0, o[0]);
+          gb::red_add(v_colors + 3 * (size_t)g_id + 1, o[1]);
+          gb::red_add(v_colors + 3 * (size_t)g_id + 2, o[2]);
+        }
+        gb::red_add(v_conic + 3 * (size_t)g_id + 0, o[4]);
+        gb::red_add(v_conic + 3 * (size_t)g_id + 1, o[5]);
+        gb::red_add(v_conic + 3 * (size_t)g_id + 2, o[6]);
+        gb::red_add_v2(v_xy + 2 * (size_t)g_id, o[7], o[8]);
+        // v_opacity = sum vis * v_alpha = -sum v_sigma / o   (o >= 1/255 wherever a pair was valid)
+        gb::red_add(v_opacity + g_id, -o[9] * rcp_approx(a1.y));
+      }
+    }
+    __syncwarp();  // phase B's reads of M / E are complete before the next chunk or the compaction overwrites them
+  };
+
+  int cnt = 0;  // pending entries of this warp (warp-uniform)
+  for (int k = 0; k < num_batches; ++k) {
+    const int s = k % kBwdStages;
+    const int hi = last - k * kStageRecs;
+    const int lo = max(range.x, hi - kStageRecs + 1);
+    const int batch_size = hi - lo + 1;
+    mbar_wait(&s_full[s], (unsigned)((k / kBwdStages) & 1));
+    const float4* sr = s_rec + s * kStageRecs * 3;
+    // slot j of the stage holds sorted index lo + j; walk j downwards, 32 at a time
+    const int j_top = min(batch_size - 1, warp_bin_final - lo);  // nothing above this index matters to the warp
+    for (int c1 = (j_top & ~31); c1 >= 0 && j_top >= 0; c1 -= 32) {
+      const int tj = c1 + lane;
+      bool hit = false;
+      if (tj <= j_top) hit = footprint_hit(sr[tj * 3], &sr[tj * 3 + 1], fx0, fx1, fy0, fy1);
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (mask == 0) continue;
+      if (hit) {  // back to front: the hit with the highest index goes first
+        const int pos = cnt + __popc(mask & ~((2u << lane) - 1u));
+        const float4 q0 = sr[tj * 3], q1 = sr[tj * 3 + 1], q2 = sr[tj * 3 + 2];
+        E[pos * 3 + 0] = make_float4(q0.x, q0.y, q1.x, q1.y);
+        E[pos * 3 + 1] = make_float4(q1.z, q1.w, __int_as_float(lo + tj), 0.f);
+        E[pos * 3 + 2] = q2;
+      }
+      cnt += __popc(mask);
+      __syncwarp();
+      if (cnt >= kChunk) {
+        int base = 0;
+        while (cnt - base >= kChunk) {
+          chunk(base, kChunk);
+          base += kChunk;
+        }
+        const int left = cnt - base;  // < 16, source entries [base, cnt) with base >= 16: disjoint from [0, left)
+        if (lane < left) {
+          const float4 e0 = E[(base + lane) * 3], e1 = E[(base + lane) * 3 + 1], e2 = E[(base + lane) * 3 + 2];
+          E[lane * 3 + 0] = e0;
+          E[lane * 3 + 1] = e1;
+          E[lane * 3 + 2] = e2;
+        }
+        cnt = left;
+        __syncwarp();
+      }
+    }
+    // this warp is finished with the stage: the last of the 8 through recycles it
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();  // release this warp's reads of the stage
+      const int ticket = atomicAdd(&s_ticket[s], 1);
+      if (ticket == kPixelWarps - 1) {
+        __threadfence_block();
+        s_ticket[s] = 0;
+        if (k + kBwdStages < num_batches) issue(k + kBwdStages);
+      }
+    }
+  }
+  if (cnt > 0) chunk(0, cnt);
+}
+
+bool g_attr_set[64] = {};  // per device: the > 48 KB dynamic shared memory opt-in of the backward kernel
+
+}  // namespace
+
+namespace gbblend {
+
+int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+                   const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
+                   cudaStream_t s) {
+  const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
+  if (channels == 3)
+    blend_fwd_ilp_kernel<3><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, (const int2*)tile_bins,
+                                                              (const float4*)records, background, final_Ts, final_idx,
+                                                              out_img);
+  else
+    blend_fwd_ilp_kernel<4><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, (const int2*)tile_bins,
+                                                              (const float4*)records, background, final_Ts, final_idx,
+                                                              out_img);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
+                   const int32_t* tile_order, const float* records, const float* background, const float* final_Ts,
+                   const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
+                   float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s) {
+  const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !g_attr_set[dev]) {
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
+  }
+  if (channels == 3)
+    blend_bwd_mom_kernel<3><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(
+        img_w, img_h, tbx, tile_order, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
+        final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+  else
+    blend_bwd_mom_kernel<4><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(
+        img_w, img_h, tbx, tile_order, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
+        final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gbblend

@@ -410,25 +410,31 @@ __global__ void __launch_bounds__(kBwdThreads, 4) blend_bwd_pipe_kernel(
   }
 }
 
-constexpr int kDefaultBlendMode = 1;  // measured: the SM-affine schedule (2) does not beat plain longest-first launch order, see DESIGN.md §4
-int g_blend_mode = -1;  // 0: CTA-synchronous (splat_blend_packed.cu), 1: warp-decoupled pipeline, 2: + SM-affine schedule
+constexpr int kDefaultBlendMode = 3;  // round 2: hit-ILP forward + transposed-reduction backward (splat_blend_mom.cu)
+int g_blend_mode = -1;  // 0: CTA-synchronous (splat_blend_packed.cu), 1: warp-decoupled pipeline, 2: + SM-affine schedule,
+                        // 3: exact cull + 4-hit ILP forward + transposed (moment) backward (splat_blend_mom.cu)
 
 }  // namespace
 
 // Blend formulation: 0 = CTA-synchronous double buffer, 1 = warp-decoupled pipeline, 2 = warp-decoupled pipeline
-// over an SM-affine schedule.  gb_rasterize_packed_fwd/bwd launch the CTA-synchronous kernels in mode 0 and the
-// pipeline otherwise; callers that can provide a schedule (gb_tile_schedule: the fused render, bench.py) use
-// gb_rasterize_sched_fwd/bwd in mode 2.  Default from the environment (GOLIATH_B200_BLEND=batch|pipe|affine).
-// Outputs are identical (pixels bit for bit, gradients to atomics order); the switch exists for A/B timing and
-// the parity tests.
+// over an SM-affine schedule, 3 = exact cull + hit-ILP forward + transposed-reduction backward (default).
+// gb_rasterize_packed_fwd/bwd dispatch on it; callers that can provide a schedule (gb_tile_schedule: the fused
+// render, bench.py) use gb_rasterize_sched_fwd/bwd in mode 2.  Default from the environment
+// (GOLIATH_B200_BLEND=batch|pipe|affine|mom).  Pixels are identical bit for bit in every mode; gradients agree to
+// the order of the atomics in modes 0-2 and to fp32 re-association (1e-5 relative) in mode 3.  The switch exists
+// for A/B timing and the parity tests.
 GB_API int gb_get_blend_mode(void) {
   if (g_blend_mode < 0) {
     const char* e = getenv("GOLIATH_B200_BLEND");
-    g_blend_mode = !e ? kDefaultBlendMode : strcmp(e, "batch") == 0 ? 0 : strcmp(e, "pipe") == 0 ? 1 : 2;
+    g_blend_mode = !e ? kDefaultBlendMode
+                   : strcmp(e, "batch") == 0 ? 0
+                   : strcmp(e, "pipe") == 0  ? 1
+                   : strcmp(e, "affine") == 0 ? 2
+                                              : 3;
   }
   return g_blend_mode;
 }
-GB_API void gb_set_blend_mode(int mode) { g_blend_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+GB_API void gb_set_blend_mode(int mode) { g_blend_mode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 // Blend over an SM-affine schedule (gb_tile_schedule): the warp-decoupled kernels, each CTA drawing its tile from
 // the queue of the SM it runs on.  Same arguments and outputs as gb_rasterize_packed_fwd / _bwd.
