@@ -184,7 +184,7 @@ def kernel_roofline(dev, packed, cam, flush):
     st = _lib.stream_ptr(dev)
     T_ = tb[0] * tb[1]
     rec = torch.empty(n, 12, device=dev)
-    sched = 1 if L.gb_get_blend_mode() == 2 else 0  # SM-affine schedule + the kernels that draw tiles from it
+    sched = 1 if L.gb_get_blend_mode() in (2, 4) else 0  # SM-affine schedule + the kernels that draw tiles from it
     order = torch.empty(L.gb_tile_schedule_ints(T_), dtype=torch.int32, device=dev)
     _lib.check((L.gb_tile_schedule if sched else L.gb_tile_order)(T_, bins.data_ptr(), order.data_ptr(), st), "order")
     ras_fwd = L.gb_rasterize_sched_fwd if sched else L.gb_rasterize_packed_fwd
@@ -256,8 +256,10 @@ def kernel_roofline(dev, packed, cam, flush):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured" if "hbm_gbs" in peaks else "fallback"
     mode = int(L.gb_get_blend_mode())
-    fwd_name = "blend_fwd_packed_kernel<4>" if mode == 0 else "blend_fwd_pipe_kernel<4>"
-    bwd_name = "blend_bwd_packed_kernel<4>" if mode == 0 else "blend_bwd_pipe_kernel<4>"
+    fwd_name = ("blend_fwd_packed_kernel<4>", "blend_fwd_pipe_kernel<4>", "blend_fwd_pipe_kernel<4>",
+                "blend_fwd_ilp_kernel<4>", "blend_fwd_ilp_kernel<4>")[mode]
+    bwd_name = ("blend_bwd_packed_kernel<4>", "blend_bwd_pipe_kernel<4>", "blend_bwd_pipe_kernel<4>",
+                "blend_bwd_mom_kernel<4>", "blend_bwd_mom_kernel<4>")[mode]
     ks = {
         fwd_name: {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
         bwd_name: {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
@@ -574,7 +576,8 @@ def run_ours(args):
                                                                                  ", step captured in a CUDA graph"))),
                    "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
                    "blend": ["batch (CTA-synchronous)", "pipe (warp-decoupled)", "affine (warp-decoupled, SM-affine "
-                             "tile schedule)"][int(lib.gb_get_blend_mode())],
+                             "tile schedule)", "mom (exact cull, 4-hit ILP forward, transposed-reduction backward)",
+                             "mom-affine (mom over the SM-affine tile schedule)"][int(lib.gb_get_blend_mode())],
                    "intersection_overflow": overflow},
         "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,

@@ -7,7 +7,8 @@
 // One thread per texel / Gaussian g = y*W + x.  The decoder's outputs are read directly as NCHW planes
 // (plane c of batch b at [b][c][g]: every load is a fully coalesced 128-byte warp request), the 3x81 light SH
 // table of the batch item sits in shared memory, and the 13 per-Gaussian results are written once in the [B,G,*]
-// layouts the rest of the path consumes.  Pure HBM kernel: 129 planes * 4 B + 36 B in, ~130 B out per Gaussian
+// layouts the rest of the path consumes.  An optional second light-SH table (the training-mode random back light of
+// rgca.py:590-618) is evaluated in the same pass (shsum2 = diff_color_rand before the clamp).  Pure HBM kernel: 129 planes * 4 B + 36 B in, ~130 B out per Gaussian
 // (~680 B vs ~5-6 KB of traffic in the eager formulation).  Backward mirrors it: one pass that writes the 129
 // gradient planes coalesced.
 #include "common.cuh"
@@ -30,6 +31,11 @@ struct HeadsArgs {
   const float *g_primpos, *g_primqvec, *g_primscale, *g_primscale_preclip, *g_opacity, *g_sigma, *g_spec_vis,
       *g_spec_dnml, *g_spec_nml, *g_diff_color, *g_ref_dirs, *g_primnmlbase;
   float *g_f_vnocond, *g_f_vcond, *g_postex, *g_tn, *g_albedo;  // g_albedo [B,G,3] (summed over B by the caller)
+  // optional second light-SH table [B,3,81] (training-mode random back light, rgca.py:590-618): its SH sums come out
+  // of the same pass over the 113 diffuse planes (shsum2 [B,G,3], no albedo); g_shsum2 is their upstream gradient
+  const float* light_sh2;
+  float* shsum2;
+  const float* g_shsum2;
 };
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus
@@ -37,10 +43,15 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 __device__ __forceinline__ void st3(float* p, size_t i, float a, float b, float c) { p[3 * i] = a; p[3 * i + 1] = b; p[3 * i + 2] = c; }
 __device__ __forceinline__ float3 ld3n(const float* p, size_t i) { return p ? make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]) : make_float3(0.f, 0.f, 0.f); }
 
+template <bool SECOND>
 __global__ void __launch_bounds__(kBlock) heads_fwd_kernel(HeadsArgs a) {
   __shared__ float s_L[3 * 81];
+  __shared__ float s_L2[SECOND ? 3 * 81 : 1];
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 243; i += kBlock) s_L[i] = a.light_sh[(size_t)b * 243 + i];
+  for (int i = threadIdx.x; i < 243; i += kBlock) {
+    s_L[i] = a.light_sh[(size_t)b * 243 + i];
+    if (SECOND) s_L2[i] = a.light_sh2[(size_t)b * 243 + i];
+  }
   __syncthreads();
   const int g = blockIdx.x * kBlock + threadIdx.x;
   if (g >= a.G) return;
@@ -50,11 +61,15 @@ __global__ void __launch_bounds__(kBlock) heads_fwd_kernel(HeadsArgs a) {
   const size_t o = (size_t)b * G + g;
 
   // ---- SH diffuse: S_c = sum_{k<16} sh[c*16+k] L[c][k] + sum_{16<=k<81} sh[48+k-16] L[c][k]
-  float S[3] = {0.f, 0.f, 0.f};
+  float S[3] = {0.f, 0.f, 0.f}, S2[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll 8
-    for (int k = 0; k < NCOL; ++k) S[c] += fn[(size_t)(c * NCOL + k) * G] * s_L[c * 81 + k];
+    for (int k = 0; k < NCOL; ++k) {
+      const float v = fn[(size_t)(c * NCOL + k) * G];
+      S[c] += v * s_L[c * 81 + k];
+      if (SECOND) S2[c] += v * s_L2[c * 81 + k];
+    }
   }
 #pragma unroll 5
   for (int k = 0; k < NMONO; ++k) {
@@ -62,7 +77,13 @@ __global__ void __launch_bounds__(kBlock) heads_fwd_kernel(HeadsArgs a) {
     S[0] += v * s_L[NCOL + k];
     S[1] += v * s_L[81 + NCOL + k];
     S[2] += v * s_L[162 + NCOL + k];
+    if (SECOND) {
+      S2[0] += v * s_L2[NCOL + k];
+      S2[1] += v * s_L2[81 + NCOL + k];
+      S2[2] += v * s_L2[162 + NCOL + k];
+    }
   }
+  if (SECOND) st3(a.shsum2, (size_t)b * G + g, S2[0], S2[1], S2[2]);
   const float al0 = a.albedo[3 * (size_t)g], al1 = a.albedo[3 * (size_t)g + 1], al2 = a.albedo[3 * (size_t)g + 2];
   st3(a.diff_color, o, al0 * S[0], al1 * S[1], al2 * S[2]);
   st3(a.shsum, o, S[0], S[1], S[2]);
@@ -100,10 +121,15 @@ __global__ void __launch_bounds__(kBlock) heads_fwd_kernel(HeadsArgs a) {
   st3(a.ref_dirs, o, v0 - 2.f * s * m0, v1 - 2.f * s * m1, v2 - 2.f * s * m2);
 }
 
+template <bool SECOND>
 __global__ void __launch_bounds__(kBlock) heads_bwd_kernel(HeadsArgs a) {
   __shared__ float s_L[3 * 81];
+  __shared__ float s_L2[SECOND ? 3 * 81 : 1];
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 243; i += kBlock) s_L[i] = a.light_sh[(size_t)b * 243 + i];
+  for (int i = threadIdx.x; i < 243; i += kBlock) {
+    s_L[i] = a.light_sh[(size_t)b * 243 + i];
+    if (SECOND) s_L2[i] = a.light_sh2[(size_t)b * 243 + i];
+  }
   __syncthreads();
   const int g = blockIdx.x * kBlock + threadIdx.x;
   if (g >= a.G) return;
@@ -120,14 +146,23 @@ __global__ void __launch_bounds__(kBlock) heads_bwd_kernel(HeadsArgs a) {
   const float S0 = a.shsum[3 * o], S1 = a.shsum[3 * o + 1], S2 = a.shsum[3 * o + 2];
   st3(a.g_albedo, o, gdiff.x * S0, gdiff.y * S1, gdiff.z * S2);
   const float gS[3] = {gdiff.x * al0, gdiff.y * al1, gdiff.z * al2};
+  const float3 g2v = SECOND ? ld3n(a.g_shsum2, o) : make_float3(0.f, 0.f, 0.f);
+  const float g2[3] = {g2v.x, g2v.y, g2v.z};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll 8
-    for (int k = 0; k < NCOL; ++k) gn[(size_t)(c * NCOL + k) * G] = gS[c] * s_L[c * 81 + k];
+    for (int k = 0; k < NCOL; ++k) {
+      float v = gS[c] * s_L[c * 81 + k];
+      if (SECOND) v += g2[c] * s_L2[c * 81 + k];
+      gn[(size_t)(c * NCOL + k) * G] = v;
+    }
   }
 #pragma unroll 5
-  for (int k = 0; k < NMONO; ++k)
-    gn[(size_t)(3 * NCOL + k) * G] = gS[0] * s_L[NCOL + k] + gS[1] * s_L[81 + NCOL + k] + gS[2] * s_L[162 + NCOL + k];
+  for (int k = 0; k < NMONO; ++k) {
+    float v = gS[0] * s_L[NCOL + k] + gS[1] * s_L[81 + NCOL + k] + gS[2] * s_L[162 + NCOL + k];
+    if (SECOND) v += g2[0] * s_L2[NCOL + k] + g2[1] * s_L2[81 + NCOL + k] + g2[2] * s_L2[162 + NCOL + k];
+    gn[(size_t)(3 * NCOL + k) * G] = v;
+  }
 
   // ---- recompute the forward quantities needed below
   const float* fg = fn + (size_t)NDIFF * G;
@@ -219,7 +254,7 @@ GB_API int gb_rgca_heads_fwd(int B, int G, const float* f_vnocond, const float* 
                              float scale_lo, float scale_hi, float* primpos, float* primqvec, float* primscale,
                              float* primscale_preclip, float* opacity, float* sigma, float* spec_vis, float* spec_dnml,
                              float* spec_nml, float* diff_color, float* ref_dirs, float* primnmlbase, float* shsum,
-                             void* stream) {
+                             const float* light_sh2, float* shsum2, void* stream) {
   if (B <= 0 || G <= 0) return 0;
   HeadsArgs a = {};
   a.B = B; a.G = G; a.f_vnocond = f_vnocond; a.f_vcond = f_vcond; a.postex = postex; a.tn = tn; a.albedo = albedo;
@@ -227,7 +262,12 @@ GB_API int gb_rgca_heads_fwd(int B, int G, const float* f_vnocond, const float* 
   a.primqvec = primqvec; a.primscale = primscale; a.primscale_preclip = primscale_preclip; a.opacity = opacity;
   a.sigma = sigma; a.spec_vis = spec_vis; a.spec_dnml = spec_dnml; a.spec_nml = spec_nml; a.diff_color = diff_color;
   a.ref_dirs = ref_dirs; a.primnmlbase = primnmlbase; a.shsum = shsum;
-  heads_fwd_kernel<<<dim3(gb::cdiv(G, kBlock), B), kBlock, 0, (cudaStream_t)stream>>>(a);
+  a.light_sh2 = light_sh2; a.shsum2 = shsum2;
+  if ((light_sh2 == nullptr) != (shsum2 == nullptr)) return (int)cudaErrorInvalidValue;
+  if (light_sh2)
+    heads_fwd_kernel<true><<<dim3(gb::cdiv(G, kBlock), B), kBlock, 0, (cudaStream_t)stream>>>(a);
+  else
+    heads_fwd_kernel<false><<<dim3(gb::cdiv(G, kBlock), B), kBlock, 0, (cudaStream_t)stream>>>(a);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;
@@ -242,7 +282,8 @@ GB_API int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* 
                              const float* g_opacity, const float* g_sigma, const float* g_spec_vis,
                              const float* g_spec_dnml, const float* g_spec_nml, const float* g_diff_color,
                              const float* g_ref_dirs, const float* g_primnmlbase, float* g_f_vnocond, float* g_f_vcond,
-                             float* g_postex, float* g_tn, float* g_albedo, void* stream) {
+                             float* g_postex, float* g_tn, float* g_albedo, const float* light_sh2, const float* g_shsum2,
+                             void* stream) {
   if (B <= 0 || G <= 0) return 0;
   HeadsArgs a = {};
   a.B = B; a.G = G; a.f_vnocond = f_vnocond; a.f_vcond = f_vcond; a.postex = postex; a.tn = tn; a.albedo = albedo;
@@ -253,7 +294,11 @@ GB_API int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* 
   a.g_spec_dnml = g_spec_dnml; a.g_spec_nml = g_spec_nml; a.g_diff_color = g_diff_color; a.g_ref_dirs = g_ref_dirs;
   a.g_primnmlbase = g_primnmlbase; a.g_f_vnocond = g_f_vnocond; a.g_f_vcond = g_f_vcond; a.g_postex = g_postex;
   a.g_tn = g_tn; a.g_albedo = g_albedo;
-  heads_bwd_kernel<<<dim3(gb::cdiv(G, kBlock), B), kBlock, 0, (cudaStream_t)stream>>>(a);
+  a.light_sh2 = light_sh2; a.g_shsum2 = g_shsum2;
+  if (light_sh2 && g_shsum2)
+    heads_bwd_kernel<true><<<dim3(gb::cdiv(G, kBlock), B), kBlock, 0, (cudaStream_t)stream>>>(a);
+  else
+    heads_bwd_kernel<false><<<dim3(gb::cdiv(G, kBlock), B), kBlock, 0, (cudaStream_t)stream>>>(a);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;

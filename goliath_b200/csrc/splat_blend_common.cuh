@@ -102,6 +102,39 @@ __device__ __forceinline__ float reduce10(const float (&v)[10], int lane, int& s
 }
 
 
+// Which tile does this CTA blend?  (one thread calls this.)
+//  sched == 0: the launch order, order[blockIdx.x] (longest list first) or row-major when order is null.
+//  sched == 1: `order` is a schedule written by gb_tile_schedule: position k*Q + q is the k-th item of queue q
+//  (Q = kSchedQueues = SM count), Q draw counters and a draw count follow at order[T ..].  The CTA draws the
+//  next item of the queue of the SM it runs on, so an SM blends the tiles of ITS queue whatever the block
+//  scheduler does, and the queues were filled with near-equal work (ncu on the launch-order kernels:
+//  sm__cycles_active.avg is only ~70 % of the elapsed cycles, the SMs finish far apart).  A CTA whose queue
+//  is exhausted takes from the following queues (a grid of T CTAs draws exactly T items, one scan finds
+//  one), and the launch's last draw puts the counters back to zero for the next launch on this schedule.
+__device__ __forceinline__ int draw_tile(const int* order, int sched, int T) {
+  if (!sched) return order ? order[blockIdx.x] : (int)blockIdx.x;
+  int* cursors = const_cast<int*>(order) + T;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  int q = (int)(smid % (unsigned)kSchedQueues);
+  int tile = -1;
+  for (int i = 0; i < kSchedQueues; ++i, q = (q + 1 == kSchedQueues) ? 0 : q + 1) {
+    const int cnt = (T > q) ? (T - q + kSchedQueues - 1) / kSchedQueues : 0;
+    if (cnt == 0 || *(volatile int*)&cursors[q] >= cnt) continue;  // empty or exhausted queue
+    const int slot = atomicAdd(&cursors[q], 1);
+    if (slot < cnt) {
+      tile = order[slot * kSchedQueues + q];
+      break;
+    }
+  }
+  __threadfence();
+  if (atomicAdd(&cursors[kSchedQueues], 1) == (int)gridDim.x - 1) {  // every CTA of the launch has drawn
+    __threadfence();
+    for (int i = 0; i <= kSchedQueues; ++i) cursors[i] = 0;
+  }
+  return tile;
+}
+
 // host-side launchers of the warp-decoupled kernels (csrc/splat_blend_pipe.cu)
 // `sched` = 1: tile_order is a schedule written by gb_tile_schedule (CTAs draw their tile from per-SM queues)
 int launch_fwd_pipe(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
@@ -113,11 +146,11 @@ int launch_bwd_pipe(int img_h, int img_w, int channels, const int32_t* gids_sort
                     float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s);
 
 // host-side launchers of the hit-ILP forward / transposed-reduction backward (csrc/splat_blend_mom.cu)
-int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
                    const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
                    cudaStream_t s);
 int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
-                   const int32_t* tile_order, const float* records, const float* background, const float* final_Ts,
+                   const int32_t* tile_order, int sched, const float* records, const float* background, const float* final_Ts,
                    const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
                    float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s);
 

@@ -87,16 +87,18 @@ __device__ __forceinline__ Tile make_tile(int tile_id, int tbx) {
 // ------------------------------------------------------------------ forward
 template <int C>
 __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
-    int img_w, int img_h, int tbx, const int* __restrict__ order, const int2* __restrict__ tile_bins,
+    int img_w, int img_h, int tbx, const int* order, int sched, const int2* __restrict__ tile_bins,
     const float4* __restrict__ rec, const float* __restrict__ background, float* __restrict__ final_Ts,
     int* __restrict__ final_idx, float* __restrict__ out_img) {
   __shared__ __align__(128) float4 s_rec[kFwdStages][kStageRecs * 3];
   __shared__ __align__(8) unsigned long long s_full[kFwdStages];
   __shared__ __align__(8) unsigned long long s_empty[kFwdStages];
   __shared__ int s_ndone;  // pixel warps whose 32 pixels are saturated
+  __shared__ int s_tile;
 
   const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
   if (tr == 0) {
+    s_tile = draw_tile(order, sched, tbx * ((img_h + 15) >> 4));
 #pragma unroll
     for (int s = 0; s < kFwdStages; ++s) {
       mbar_init(&s_full[s], 1);
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
     fence_mbar_init();
   }
   __syncthreads();  // the only CTA-wide barrier of this kernel
-  const Tile tl = make_tile(order ? order[blockIdx.x] : (int)blockIdx.x, tbx);
+  if (s_tile < 0) return;
+  const Tile tl = make_tile(s_tile, tbx);
   const int2 range = tile_bins[tl.tile_id];
   const int num_batches = (range.y - range.x + kStageRecs - 1) / kStageRecs;
 
@@ -245,7 +248,7 @@ constexpr int kBwdSmem = kSmRec + kSmEntries + kSmM + kSmVo;                // 7
 
 template <int C>
 __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
-    int img_w, int img_h, int tbx, const int* __restrict__ order, const int* __restrict__ gids_sorted,
+    int img_w, int img_h, int tbx, const int* order, int sched, const int* __restrict__ gids_sorted,
     const int2* __restrict__ tile_bins, const float4* __restrict__ rec, const float* __restrict__ background,
     const float* __restrict__ final_Ts, const int* __restrict__ final_idx, const float* __restrict__ v_output,
     const float* __restrict__ v_output_alpha, float* __restrict__ v_xy, float* __restrict__ v_conic,
@@ -255,13 +258,17 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
   __shared__ __align__(8) unsigned long long s_full[kBwdStages];
   __shared__ int s_ticket[kBwdStages];  // warps that have finished culling the stage's current batch
   __shared__ int s_cta_final;
+  __shared__ int s_tile;
 
   const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+  if (tr == 0) s_tile = draw_tile(order, sched, tbx * ((img_h + 15) >> 4));
+  __syncthreads();
+  if (s_tile < 0) return;
   float4* E = reinterpret_cast<float4*>(smem + kSmRec) + warp * kEntryCap * 3;           // pending entries
   float2* M = reinterpret_cast<float2*>(smem + kSmRec + kSmEntries) + warp * kChunk * kMStride;
   float4* VO = reinterpret_cast<float4*>(smem + kSmRec + kSmEntries + kSmM) + warp * 32;
 
-  const Tile tl = make_tile(order ? order[blockIdx.x] : (int)blockIdx.x, tbx);
+  const Tile tl = make_tile(s_tile, tbx);
   const int2 range = tile_bins[tl.tile_id];
   if (range.y <= range.x) return;
   const int wx0 = tl.tx * 16 + ((warp & 1) << 3), wy0 = tl.ty * 16 + ((warp >> 1) << 2);
@@ -320,39 +327,40 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
   // no CTA-wide barrier below this line
 
   // ---- one chunk of n <= 16 pending entries starting at entry `base`: phase A (lanes = pixels), phase B (lanes = hits)
+  // (entries [base, base + n) with n rounded up to a multiple of 4 by invalid padding entries, see pad4 below)
   auto chunk = [&](int base, int n) {
-    unsigned anymask = 0;  // bit h: some pixel of the footprint took a gradient from hit h
 #pragma unroll 1
     for (int h0 = 0; h0 < n; h0 += 4) {
       float al[4], ov[4], ra[4];
       float4 col[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int h = min(h0 + u, n - 1);
+        const int h = h0 + u;
         const float4 a0 = E[(base + h) * 3], a1 = E[(base + h) * 3 + 1];  // x y A B | C o idx -
         col[u] = E[(base + h) * 3 + 2];
         const float dx = a0.x - px, dy = a0.y - py;
         const float sigma = 0.5f * (a0.z * dx * dx + a1.x * dy * dy) + a0.w * dx * dy;
         const float vis = __expf(-sigma);
         const float alpha = fminf(kAlphaMaxBwd, a1.y * vis);
-        const bool valid = inside && (h0 + u < n) && (__float_as_int(a1.z) <= bin_final) && !(sigma < 0.f) &&
-                           !(alpha < kAlphaMin);
+        // pixels outside the image have bin_final = -1, padding entries have idx = INT_MAX
+        const bool valid = (__float_as_int(a1.z) <= bin_final) && !(sigma < 0.f) && !(alpha < kAlphaMin);
         al[u] = valid ? alpha : 0.f;
         ov[u] = valid ? a1.y * vis : 0.f;
         ra[u] = rcp_approx(1.f - al[u]);  // exactly 1 for the pairs that do not take part
-        if (__ballot_sync(0xffffffffu, valid)) anymask |= 1u << (h0 + u);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        // v_alpha = sum_c (c_c T' - buffer_c ra) v_out_c + T_final ra (v_out_alpha - bg.v_out) with T' = T ra:
+        // the common factor ra is applied once
+        const float cc[4] = {col[u].x, col[u].y, col[u].z, col[u].w};
+        float v_alpha = tfc;
+#pragma unroll
+        for (int c = 0; c < C; ++c) v_alpha += (cc[c] * T - buffer[c]) * vo[c];
+        v_alpha *= ra[u];
         T *= ra[u];
         const float fac = al[u] * T;
-        const float cc[4] = {col[u].x, col[u].y, col[u].z, col[u].w};
-        float v_alpha = tfc * ra[u];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          v_alpha += (cc[c] * T - buffer[c] * ra[u]) * vo[c];
-          buffer[c] += cc[c] * fac;
-        }
+        for (int c = 0; c < C; ++c) buffer[c] += cc[c] * fac;
         M[(h0 + u) * kMStride + lane] = make_float2(fac, -ov[u] * v_alpha);  // (fac, v_sigma); zeros when not valid
       }
     }
@@ -361,15 +369,20 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
       const int hh = lane & 15, half = lane >> 4;
       const int he = min(hh, n - 1);
       const float4 a0 = E[(base + he) * 3], a1 = E[(base + he) * 3 + 1];
+      // the Gaussian id is only needed by the REDs at the end: start its load now (padding entries: index 0)
+      const int e_idx = __float_as_int(a1.z);
+      const int g_id = gids_sorted[e_idx == 0x7fffffff ? 0 : e_idx];
       const float2* Mrow = M + hh * kMStride + half * 16;
       const float4* V = VO + half * 16;
       float g[4] = {0.f, 0.f, 0.f, 0.f};
       float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f, sii = 0.f;
+      float facmax = 0.f;  // fac = alpha * T > 0 exactly for the (hit, pixel) pairs that took a gradient
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const float2 m = Mrow[q];
         const float4 v = V[q];
         const float fi = (float)(q & 7);
+        facmax = fmaxf(facmax, m.x);
         g[0] += m.x * v.x;
         g[1] += m.x * v.y;
         g[2] += m.x * v.z;
@@ -398,8 +411,8 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
       o[9] = S0;
 #pragma unroll
       for (int i = 0; i < 10; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
-      if (half == 0 && hh < n && ((anymask >> hh) & 1u)) {
-        const int g_id = gids_sorted[__float_as_int(a1.z)];
+      facmax = fmaxf(facmax, __shfl_xor_sync(0xffffffffu, facmax, 16));
+      if (half == 0 && hh < n && facmax > 0.f) {  // false hits (no valid pixel) add nothing
         if (C == 4) {
           gb::red_add_v4(v_colors + 4 * (size_t)g_id, o[0], o[1], o[2], o[3]);
         } else {
@@ -418,13 +431,24 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
     __syncwarp();  // phase B's reads of M / E are complete before the next chunk or the compaction overwrites them
   };
 
+  // pad the entry list [0, cnt) to a multiple of 4 with entries no pixel accepts (idx = INT_MAX)
+  auto pad4 = [&](int cnt_) {
+    const int padded = (cnt_ + 3) & ~3;
+    if (lane < padded - cnt_) {
+      E[(cnt_ + lane) * 3 + 0] = make_float4(0.f, 0.f, 1.f, 0.f);
+      E[(cnt_ + lane) * 3 + 1] = make_float4(1.f, 0.f, __int_as_float(0x7fffffff), 0.f);
+      E[(cnt_ + lane) * 3 + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    return padded;
+  };
   int cnt = 0;  // pending entries of this warp (warp-uniform)
   for (int k = 0; k < num_batches; ++k) {
     const int s = k % kBwdStages;
     const int hi = last - k * kStageRecs;
     const int lo = max(range.x, hi - kStageRecs + 1);
     const int batch_size = hi - lo + 1;
-    mbar_wait(&s_full[s], (unsigned)((k / kBwdStages) & 1));
+    while (!mbar_try(&s_full[s], (unsigned)((k / kBwdStages) & 1))) __nanosleep(64);  // warps far ahead park cheaply
     const float4* sr = s_rec + s * kStageRecs * 3;
     // slot j of the stage holds sorted index lo + j; walk j downwards, 32 at a time
     const int j_top = min(batch_size - 1, warp_bin_final - lo);  // nothing above this index matters to the warp
@@ -472,7 +496,7 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
       }
     }
   }
-  if (cnt > 0) chunk(0, cnt);
+  if (cnt > 0) chunk(0, pad4(cnt));
 }
 
 bool g_attr_set[64] = {};  // per device: the > 48 KB dynamic shared memory opt-in of the backward kernel
@@ -481,16 +505,17 @@ bool g_attr_set[64] = {};  // per device: the > 48 KB dynamic shared memory opt-
 
 namespace gbblend {
 
-int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
                    const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
                    cudaStream_t s) {
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
+  if (sched && !tile_order) return (int)cudaErrorInvalidValue;
   if (channels == 3)
-    blend_fwd_ilp_kernel<3><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, (const int2*)tile_bins,
+    blend_fwd_ilp_kernel<3><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched, (const int2*)tile_bins,
                                                               (const float4*)records, background, final_Ts, final_idx,
                                                               out_img);
   else
-    blend_fwd_ilp_kernel<4><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, (const int2*)tile_bins,
+    blend_fwd_ilp_kernel<4><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched, (const int2*)tile_bins,
                                                               (const float4*)records, background, final_Ts, final_idx,
                                                               out_img);
   gb::count_launches(1);
@@ -499,10 +524,11 @@ int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins,
 }
 
 int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
-                   const int32_t* tile_order, const float* records, const float* background, const float* final_Ts,
+                   const int32_t* tile_order, int sched, const float* records, const float* background, const float* final_Ts,
                    const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
                    float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s) {
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
+  if (sched && !tile_order) return (int)cudaErrorInvalidValue;
   int dev = 0;
   GB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !g_attr_set[dev]) {
@@ -512,11 +538,11 @@ int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorte
   }
   if (channels == 3)
     blend_bwd_mom_kernel<3><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(
-        img_w, img_h, tbx, tile_order, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
+        img_w, img_h, tbx, tile_order, sched, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
         final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
   else
     blend_bwd_mom_kernel<4><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(
-        img_w, img_h, tbx, tile_order, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
+        img_w, img_h, tbx, tile_order, sched, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
         final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();

@@ -495,8 +495,8 @@ GB_API int gb_rasterize_packed_fwd(int img_h, int img_w, int channels, const int
   if (channels != 3 && channels != 4) return (int)cudaErrorInvalidValue;
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   cudaStream_t s = (cudaStream_t)stream;
-  if (gb_get_blend_mode() == 3)  // exact cull + hit-ILP forward (csrc/splat_blend_mom.cu), identical pixels
-    return gbblend::launch_fwd_mom(img_h, img_w, channels, tile_bins, tile_order, records, background, out_img, final_Ts,
+  if (gb_get_blend_mode() >= 3)  // exact cull + hit-ILP forward (csrc/splat_blend_mom.cu), identical pixels
+    return gbblend::launch_fwd_mom(img_h, img_w, channels, tile_bins, tile_order, 0, records, background, out_img, final_Ts,
                                    final_idx, s);
   if (gb_get_blend_mode())  // warp-decoupled pipeline (csrc/splat_blend_pipe.cu), identical outputs
     return gbblend::launch_fwd_pipe(img_h, img_w, channels, tile_bins, tile_order, 0, records, background, out_img,
@@ -522,8 +522,8 @@ GB_API int gb_rasterize_packed_bwd(int img_h, int img_w, int channels, const int
   if (channels != 3 && channels != 4) return (int)cudaErrorInvalidValue;
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   cudaStream_t s = (cudaStream_t)stream;
-  if (gb_get_blend_mode() == 3)  // transposed-reduction backward (csrc/splat_blend_mom.cu)
-    return gbblend::launch_bwd_mom(img_h, img_w, channels, gids_sorted, tile_bins, tile_order, records, background,
+  if (gb_get_blend_mode() >= 3)  // transposed-reduction backward (csrc/splat_blend_mom.cu)
+    return gbblend::launch_bwd_mom(img_h, img_w, channels, gids_sorted, tile_bins, tile_order, 0, records, background,
                                    final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity, s);
   if (gb_get_blend_mode())
     return gbblend::launch_bwd_pipe(img_h, img_w, channels, gids_sorted, tile_bins, tile_order, 0, records, background,

@@ -54,39 +54,6 @@ __device__ __forceinline__ Tile make_tile(int tile_id, int tbx) {
   return t;
 }
 
-// Which tile does this CTA blend?  (one thread calls this.)
-//  sched == 0: the launch order, order[blockIdx.x] (longest list first) or row-major when order is null.
-//  sched == 1: `order` is a schedule written by gb_tile_schedule: position k*Q + q is the k-th item of queue q
-//  (Q = kSchedQueues = SM count), Q draw counters and a draw count follow at order[T ..].  The CTA draws the
-//  next item of the queue of the SM it runs on, so an SM blends the tiles of ITS queue whatever the block
-//  scheduler does, and the queues were filled with near-equal work (ncu on the launch-order kernels:
-//  sm__cycles_active.avg is only ~70 % of the elapsed cycles, the SMs finish far apart).  A CTA whose queue
-//  is exhausted takes from the following queues (a grid of T CTAs draws exactly T items, one scan finds
-//  one), and the launch's last draw puts the counters back to zero for the next launch on this schedule.
-__device__ __forceinline__ int draw_tile(const int* order, int sched, int T) {
-  if (!sched) return order ? order[blockIdx.x] : (int)blockIdx.x;
-  int* cursors = const_cast<int*>(order) + T;
-  unsigned smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  int q = (int)(smid % (unsigned)kSchedQueues);
-  int tile = -1;
-  for (int i = 0; i < kSchedQueues; ++i, q = (q + 1 == kSchedQueues) ? 0 : q + 1) {
-    const int cnt = (T > q) ? (T - q + kSchedQueues - 1) / kSchedQueues : 0;
-    if (cnt == 0 || *(volatile int*)&cursors[q] >= cnt) continue;  // empty or exhausted queue
-    const int slot = atomicAdd(&cursors[q], 1);
-    if (slot < cnt) {
-      tile = order[slot * kSchedQueues + q];
-      break;
-    }
-  }
-  __threadfence();
-  if (atomicAdd(&cursors[kSchedQueues], 1) == (int)gridDim.x - 1) {  // every CTA of the launch has drawn
-    __threadfence();
-    for (int i = 0; i <= kSchedQueues; ++i) cursors[i] = 0;
-  }
-  return tile;
-}
-
 // ------------------------------------------------------------------ forward
 template <int C>
 __global__ void __launch_bounds__(kFwdThreads) blend_fwd_pipe_kernel(
@@ -412,7 +379,8 @@ __global__ void __launch_bounds__(kBwdThreads, 4) blend_bwd_pipe_kernel(
 
 constexpr int kDefaultBlendMode = 3;  // round 2: hit-ILP forward + transposed-reduction backward (splat_blend_mom.cu)
 int g_blend_mode = -1;  // 0: CTA-synchronous (splat_blend_packed.cu), 1: warp-decoupled pipeline, 2: + SM-affine schedule,
-                        // 3: exact cull + 4-hit ILP forward + transposed (moment) backward (splat_blend_mom.cu)
+                        // 3: exact cull + 4-hit ILP forward + transposed (moment) backward (splat_blend_mom.cu),
+                        // 4: mode 3 drawing its tiles from the SM-affine schedule
 
 }  // namespace
 
@@ -430,11 +398,12 @@ GB_API int gb_get_blend_mode(void) {
                    : strcmp(e, "batch") == 0 ? 0
                    : strcmp(e, "pipe") == 0  ? 1
                    : strcmp(e, "affine") == 0 ? 2
-                                              : 3;
+                   : strcmp(e, "mom") == 0    ? 3
+                                              : 4;  // "mom-affine"
   }
   return g_blend_mode;
 }
-GB_API void gb_set_blend_mode(int mode) { g_blend_mode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
+GB_API void gb_set_blend_mode(int mode) { g_blend_mode = mode < 0 ? 0 : (mode > 4 ? 4 : mode); }
 
 // Blend over an SM-affine schedule (gb_tile_schedule): the warp-decoupled kernels, each CTA drawing its tile from
 // the queue of the SM it runs on.  Same arguments and outputs as gb_rasterize_packed_fwd / _bwd.
@@ -443,6 +412,9 @@ GB_API int gb_rasterize_sched_fwd(int img_h, int img_w, int channels, const int3
                                   int32_t* final_idx, void* stream) {
   if (img_h <= 0 || img_w <= 0) return 0;
   if (channels != 3 && channels != 4) return (int)cudaErrorInvalidValue;
+  if (gb_get_blend_mode() >= 3)
+    return gbblend::launch_fwd_mom(img_h, img_w, channels, tile_bins, sched, 1, records, background, out_img, final_Ts,
+                                   final_idx, (cudaStream_t)stream);
   return gbblend::launch_fwd_pipe(img_h, img_w, channels, tile_bins, sched, 1, records, background, out_img, final_Ts,
                                   final_idx, (cudaStream_t)stream);
 }
@@ -453,6 +425,10 @@ GB_API int gb_rasterize_sched_bwd(int img_h, int img_w, int channels, const int3
                                   float* v_colors, float* v_opacity, void* stream) {
   if (img_h <= 0 || img_w <= 0) return 0;
   if (channels != 3 && channels != 4) return (int)cudaErrorInvalidValue;
+  if (gb_get_blend_mode() >= 3)
+    return gbblend::launch_bwd_mom(img_h, img_w, channels, gids_sorted, tile_bins, sched, 1, records, background,
+                                   final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity,
+                                   (cudaStream_t)stream);
   return gbblend::launch_bwd_pipe(img_h, img_w, channels, gids_sorted, tile_bins, sched, 1, records, background,
                                   final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity,
                                   (cudaStream_t)stream);

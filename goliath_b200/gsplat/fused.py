@@ -72,8 +72,8 @@ class _RenderFused(Function):
                 "project_gaussians_forward")
             tb = _tile_bounds(H, W, BW)
             T = tb[0] * tb[1]
-            # blend mode 2: the tile order is an SM-affine schedule and the blend kernels draw their tiles from it
-            sched = 1 if (capacity is not None and L.gb_get_blend_mode() == 2) else 0
+            # blend modes 2 and 4: the tile order is an SM-affine schedule and the blend kernels draw their tiles from it
+            sched = 1 if (capacity is not None and L.gb_get_blend_mode() in (2, 4)) else 0
             if capacity is not None:
                 # ---- sync-free path: the count never visits the host; buffers hold `capacity` intersections
                 cap = int(capacity)

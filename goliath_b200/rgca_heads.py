@@ -19,7 +19,7 @@ _OUT = ("primpos", "primqvec", "primscale", "primscale_preclip", "opacity", "sig
 
 class _GaussianHeads(Function):
     @staticmethod
-    def forward(ctx, f_vnocond, f_vcond, postex, tn, albedo, light_sh, campos, scale_lo, scale_hi):
+    def forward(ctx, f_vnocond, f_vcond, postex, tn, albedo, light_sh, campos, scale_lo, scale_hi, light_sh2=None):
         ins = [t.contiguous() for t in (f_vnocond, f_vcond, postex, tn, albedo, light_sh, campos)]
         names = ("f_vnocond", "f_vcond", "postex", "tn", "albedo", "light_sh", "campos")
         for t, n in zip(ins, names):
@@ -36,18 +36,29 @@ class _GaussianHeads(Function):
                     opacity=e(B, G, 1), sigma=e(B, G), spec_vis=e(B, G, 1), spec_dnml=e(B, G, 3), spec_nml=e(B, G, 3),
                     diff_color=e(B, G, 3), ref_dirs=e(B, G, 3), primnmlbase=e(B, G, 3))
         shsum = e(B, G, 3)
+        shsum2 = None
+        if light_sh2 is not None:  # second light-SH table evaluated in the same pass (rgca.py:590-616)
+            light_sh2 = light_sh2.contiguous()
+            _lib.check_input(light_sh2, "light_sh2")
+            if light_sh2.shape != light_sh.shape:
+                raise RuntimeError("light_sh2 must have the shape of light_sh [B,3,81]")
+            shsum2 = e(B, G, 3)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gb_rgca_heads_fwd(
                 B, G, *[_lib.ptr(t) for t in ins], float(scale_lo), float(scale_hi),
-                *[_lib.ptr(outs[k]) for k in _OUT], _lib.ptr(shsum), _lib.stream_ptr(dev)), "rgca_heads_fwd")
+                *[_lib.ptr(outs[k]) for k in _OUT], _lib.ptr(shsum), _lib.ptr(light_sh2), _lib.ptr(shsum2),
+                _lib.stream_ptr(dev)), "rgca_heads_fwd")
         ctx.save_for_backward(*ins, shsum)
+        ctx.light_sh2 = light_sh2  # constant (no gradient): built under no_grad upstream
         ctx.scale = (float(scale_lo), float(scale_hi))
         ctx.shape = (B, C, H, W)
         ctx.set_materialize_grads(False)
-        return tuple(outs[k] for k in _OUT)
+        return tuple(outs[k] for k in _OUT) + (shsum2,)
 
     @staticmethod
     def backward(ctx, *gouts):
+        g_shsum2 = gouts[-1]
+        gouts = gouts[:-1]
         f_vnocond, f_vcond, postex, tn, albedo, light_sh, campos, shsum = ctx.saved_tensors
         B, C, H, W = ctx.shape
         G = H * W
@@ -63,19 +74,26 @@ class _GaussianHeads(Function):
                 B, G, _lib.ptr(f_vnocond), _lib.ptr(f_vcond), _lib.ptr(postex), _lib.ptr(tn), _lib.ptr(albedo),
                 _lib.ptr(light_sh), _lib.ptr(campos), ctx.scale[0], ctx.scale[1], _lib.ptr(shsum),
                 *[_lib.ptr(g) for g in gouts], _lib.ptr(g_fn), _lib.ptr(g_fv), _lib.ptr(g_pt), _lib.ptr(g_tn),
-                _lib.ptr(g_al), _lib.stream_ptr(dev)), "rgca_heads_bwd")
+                _lib.ptr(g_al), _lib.ptr(ctx.light_sh2 if g_shsum2 is not None else None),
+                _lib.ptr(None if g_shsum2 is None or ctx.light_sh2 is None else g_shsum2.contiguous()),
+                _lib.stream_ptr(dev)), "rgca_heads_bwd")
         g_albedo = g_al.sum(0, keepdim=True).view_as(albedo) if ctx.needs_input_grad[4] else None
-        return g_fn, g_fv, g_pt, g_tn, g_albedo, None, None, None, None
+        return g_fn, g_fv, g_pt, g_tn, g_albedo, None, None, None, None, None
 
 
 def gaussian_heads(f_vnocond, f_vcond, postex, tn, albedo, headrel_light_sh, headrel_campos,
-                   primscale_range=PRIMSCALE_RANGE) -> Dict[str, torch.Tensor]:
+                   primscale_range=PRIMSCALE_RANGE, rand_light_sh=None) -> Dict[str, torch.Tensor]:
     """f_vnocond [B,125,H,W] and f_vcond [B,4,H,W] are the decoder towers' raw outputs (rgca.py:495,503), postex the UV
     position map, tn the UNIT normal map (rgca.py:483-491), albedo the [1,H*W,3] parameter, headrel_light_sh [B,3,81],
-    headrel_campos [B,3].  Returns the reference's per-Gaussian tensors plus `ref_dirs`."""
+    headrel_campos [B,3].  Returns the reference's per-Gaussian tensors plus `ref_dirs`.  With `rand_light_sh`
+    [B,3,81] (the training-mode random back light, rgca.py:590-616) the result also holds `diff_color_rand` [B,G,3] =
+    (diff_shs * rand_light_sh[:, None]).sum(-1), computed in the same pass over the 113 diffuse planes."""
     outs = _GaussianHeads.apply(f_vnocond, f_vcond, postex, tn, albedo, headrel_light_sh, headrel_campos,
-                                primscale_range[0], primscale_range[1])
-    return dict(zip(_OUT, outs))
+                                primscale_range[0], primscale_range[1], rand_light_sh)
+    d = dict(zip(_OUT, outs[:-1]))
+    if rand_light_sh is not None:
+        d["diff_color_rand"] = outs[-1]
+    return d
 
 
 class _ShadeCompose(Function):

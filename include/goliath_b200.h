@@ -239,16 +239,36 @@ int gb_rgca_heads_fwd(int B, int G, const float* f_vnocond, const float* f_vcond
                       const float* albedo, const float* light_sh, const float* campos, float scale_lo, float scale_hi,
                       float* primpos, float* primqvec, float* primscale, float* primscale_preclip, float* opacity,
                       float* sigma, float* spec_vis, float* spec_dnml, float* spec_nml, float* diff_color,
-                      float* ref_dirs, float* primnmlbase, float* shsum, void* stream);
+                      float* ref_dirs, float* primnmlbase, float* shsum, const float* light_sh2, float* shsum2,
+                      void* stream);
+/* light_sh2 [B,3,81] / shsum2 [B,G,3] (both NULL or both set): a second light-SH table evaluated in the same pass over the
+ * 113 diffuse planes — the training-mode random back light `diff_color_rand` of rgca.py:590-616 (no albedo, unclamped). */
 
-/* backward of the above; upstream gradients may be NULL; g_albedo is [B,G,3] (summed over B by the caller). */
+/* backward of the above; upstream gradients may be NULL; g_albedo is [B,G,3] (summed over B by the caller);
+ * light_sh2 / g_shsum2: the second table and the upstream gradient of shsum2 (both NULL when unused). */
 int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* f_vcond, const float* postex, const float* tn,
                       const float* albedo, const float* light_sh, const float* campos, float scale_lo, float scale_hi,
                       const float* shsum, const float* g_primpos, const float* g_primqvec, const float* g_primscale,
                       const float* g_primscale_preclip, const float* g_opacity, const float* g_sigma,
                       const float* g_spec_vis, const float* g_spec_dnml, const float* g_spec_nml,
                       const float* g_diff_color, const float* g_ref_dirs, const float* g_primnmlbase, float* g_f_vnocond,
-                      float* g_f_vcond, float* g_postex, float* g_tn, float* g_albedo, void* stream);
+                      float* g_f_vcond, float* g_postex, float* g_tn, float* g_albedo, const float* light_sh2,
+                      const float* g_shsum2, void* stream);
+
+/* replaces the environment-map specular branch of rgca.PrimDecoder.forward (ca_code/models/rgca.py:548-556):
+ * einsum("bxy,bny->bnx", lightrot, ref_dirs) -> dir2uv (ca_code/utils/envmap.py:284-292) -> mipmap_grid_sample of the
+ * pre-convolved pyramid at level sigma * level_scale (ca_code/utils/mipmap_sampler.py:13-66: bilinear, border padding,
+ * align_corners=False, two adjacent levels blended by the fractional level) -> clamp(max=1) * spec_vis.
+ * levels: q (1..8) device pointers to [B,3,H_l,W_l] fp32 (the array itself in HOST memory); level_hw: q (H, W) pairs
+ * (host).  ref_dirs [B,G,3], sigma [B,G], spec_vis [B,G], lightrot [B,3,3] -> spec [B,G,3]. */
+int gb_envmap_spec_fwd(int B, int G, int q, const float* const* levels, const int32_t* level_hw, const float* ref_dirs,
+                       const float* sigma, const float* spec_vis, const float* lightrot, float level_scale, float* spec,
+                       void* stream);
+/* g_spec [B,G,3] -> g_ref_dirs [B,G,3], g_spec_vis [B,G] (overwritten); no gradient for sigma (the level is picked
+ * under no_grad upstream) nor for the environment map. */
+int gb_envmap_spec_bwd(int B, int G, int q, const float* const* levels, const int32_t* level_hw, const float* ref_dirs,
+                       const float* sigma, const float* spec_vis, const float* lightrot, float level_scale,
+                       const float* g_spec, float* g_ref_dirs, float* g_spec_vis, void* stream);
 
 /* replaces the per-view post-processing of rgca.AutoEncoder.render (ca_code/models/rgca.py:136-151, with
  * render_gsplat.py:79-108): colour HWC -> CHW, alpha = 1 - final_T (detached), depth / alpha.clamp(0.05, 1).

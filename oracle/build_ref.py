@@ -7,6 +7,11 @@ into the repo) with the reference's own flags (setup.py of each extension: -use_
 oracle and the product kernels (tests/test_ref_witness_gpu.py) and bench.py times them as the reference arm of
 the extension-level ratios.  gsplat is third-party and absent: it cannot be built here.
 
+It also byte-compiles the reference's L1 PYTHON wrappers (extensions/*/X.py and ca_code/utils/render_gsplat.py: the
+`autograd.Function`s that call into the pybind modules) to sourceless .pyc files under oracle/_ref/pyc/ — compiled
+artefacts like the .so files, no source text enters the repo — so that tests/test_dropins.py can run the reference's
+OWN wrappers, unchanged, over `goliath_b200.install_dropins()` on the GPU box (where /root/reference does not exist).
+
 Usage: python oracle/build_ref.py [sgutilslib utilslib mvpraymarchlib]
 """
 import os
@@ -71,13 +76,37 @@ def build_one(name):
     return so
 
 
+WRAPPERS = {  # module name under oracle/_ref/pyc -> reference file
+    "ref_sgutils": "/root/reference/extensions/sgutils/sgutils.py",
+    "ref_utils": "/root/reference/extensions/utils/utils.py",
+    "ref_mvpraymarch": "/root/reference/extensions/mvpraymarch/mvpraymarch.py",
+    "ref_render_gsplat": "/root/reference/ca_code/utils/render_gsplat.py",
+}
+
+
+def build_wrappers():
+    """py_compile the reference's L1 wrappers (unchanged) into oracle/_ref/pyc/<name>.pyc."""
+    import py_compile
+
+    out = os.path.join(OUT, "pyc")
+    os.makedirs(out, exist_ok=True)
+    done = []
+    for name, src in WRAPPERS.items():
+        if os.path.exists(src):
+            done.append(py_compile.compile(src, cfile=os.path.join(out, name + ".pyc"), doraise=True))
+    return done
+
+
 def build(names=None):
     if not os.path.isdir(REF):
         return []  # GPU box: use the prebuilt files
     names = names or list(EXTS)
     with ThreadPoolExecutor(max_workers=3) as ex:
-        return list(ex.map(build_one, names))
+        return list(ex.map(build_one, names)) + build_wrappers()
 
 
 if __name__ == "__main__":
-    print(build(sys.argv[1:] or None))
+    if sys.argv[1:] == ["wrappers"]:
+        print(build_wrappers())
+    else:
+        print(build(sys.argv[1:] or None))

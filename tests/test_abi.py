@@ -77,11 +77,11 @@ def test_host_side_sizing_functions():
     assert L.gb_tile_schedule_ints(T) == T + 148 + 1         # one queue per SM + the draw counter
     before = L.gb_get_blend_mode()
     try:
-        for m in (0, 1, 2, 3):
+        for m in (0, 1, 2, 3, 4):
             L.gb_set_blend_mode(m)
             assert L.gb_get_blend_mode() == m
         L.gb_set_blend_mode(7)
-        assert L.gb_get_blend_mode() == 3
+        assert L.gb_get_blend_mode() == 4
     finally:
         L.gb_set_blend_mode(before)
-    assert before in (0, 1, 2, 3)
+    assert before in (0, 1, 2, 3, 4)

@@ -274,7 +274,7 @@ def test_product_refuses_cpu_tensors(cuda):
                           torch.eye(4)[:3].contiguous(), 10.0, 10.0, 8.0, 8.0, 16, 16, 16)
 
 
-@pytest.fixture(params=["batch", "pipe", "affine", "mom"])
+@pytest.fixture(params=["batch", "pipe", "affine", "mom", "mom-affine"])
 def blend_mode(request):
     """The formulations of the packed blend: CTA-synchronous double buffer (csrc/splat_blend_packed.cu), warp-decoupled
     mbarrier pipeline (csrc/splat_blend_pipe.cu), the pipeline drawing its tiles from an SM-affine schedule, and the
@@ -283,7 +283,7 @@ def blend_mode(request):
 
     L = _lib.lib()
     before = L.gb_get_blend_mode()
-    L.gb_set_blend_mode({"batch": 0, "pipe": 1, "affine": 2, "mom": 3}[request.param])
+    L.gb_set_blend_mode({"batch": 0, "pipe": 1, "affine": 2, "mom": 3, "mom-affine": 4}[request.param])
     yield request.param
     L.gb_set_blend_mode(before)
 
@@ -318,7 +318,7 @@ def test_packed_blend_matches_generic_kernel(orc, cuda, case, C, blend_mode):
     st = _lib.stream_ptr(cuda)
     outs = []
     rec = torch.empty(n, 12, device=cuda)
-    affine = blend_mode == "affine"
+    affine = blend_mode in ("affine", "mom-affine")
     order = torch.full((L.gb_tile_schedule_ints(T),), -1, dtype=torch.int32, device=cuda)
     _lib.check(L.gb_pack_records(n, C, gids.data_ptr(), xys.data_ptr(), conics.data_ptr(), col.data_ptr(),
                                  op.data_ptr(), rec.data_ptr(), st), "pack")
@@ -375,7 +375,7 @@ def test_packed_blend_matches_generic_kernel(orc, cuda, case, C, blend_mode):
         for name, x, y in zip(("v_xy", "v_conic", "v_colors", "v_opacity"), grads[k], grads[0]):
             # modes 0-2 differ from the generic kernel only in the order of the atomics; mode 3 re-associates the sums
             # over the pixels (image moments) and uses rcp.approx: same 1e-4 bar as against the oracle
-            tol = dict(rtol=1e-4, atol=1e-5 * np.abs(y).max(), frac=0.999) if blend_mode == "mom" else \
+            tol = dict(rtol=1e-4, atol=1e-5 * np.abs(y).max(), frac=0.999) if blend_mode.startswith("mom") else \
                 dict(rtol=2e-5, atol=2e-5 * np.abs(y).max())
             assert_close(x, y, what=name + " packed vs generic (pass %d)" % k, **tol)
     # and against the oracle
