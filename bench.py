@@ -4,13 +4,15 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
   python bench.py --impl reference ...                     CPU restatement of the same path on the host cores
 
-One "step" = one pass of the hot path over one view per rank of the BASELINE.json configs[1] workload
-(300k Gaussians, 1 view 1024x667, L=32 point lights): SG specular shade + colour compose -> EWA projection ->
-tile bin/sort -> alpha blend rgb -> alpha blend depth, forward AND backward (v_out = 1), through the
-reference-shaped Python surface (goliath_b200.sgutils.evaluate_gaussian, goliath_b200.render.render_views).
+One "step" (default --config head) = one pass of the hot path over one view per rank of the BASELINE.json configs[1]
+workload (300k Gaussians, 1 view 1024x667, L=32 point lights): SG specular shade + colour compose -> EWA projection ->
+tile bin/sort -> alpha blend rgb + depth, forward AND backward (v_out = 1), through the reference-shaped Python surface
+(goliath_b200.rgca_heads.shade_compose, goliath_b200.render.render_views).
 `value` = views*H*W/1e6 / time with inputs resident in HBM; `e2e` = same through HOST buffers (H2D of the decoded
-Gaussians + D2H of images and gradients inside the timed region).  N>1: one view per rank (weak scaling), the
-frame owner (rank 0) broadcasts the decoded Gaussians and gradients are all-reduced, both inside the timed region.
+Gaussians from pinned memory + D2H of the rendered images inside the timed region; the gradients stay on the device
+for the optimiser).  N>1: one view per rank (weak scaling), the frame owner (rank 0) broadcasts the decoded Gaussians
+and gradients are all-reduced (goliath_b200.dist.FrameExchange), both inside the timed region.
+--config olat | hand_mvp | mvp_full run BASELINE configs[2..4] with the same JSON schema.
 """
 import argparse
 import json
@@ -33,8 +35,13 @@ NCOL = 19  # packed decoded Gaussian: pos3 quat4 scale3 opacity1 diff3 lobe3 sig
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 for --config head, fewer for the heavier configs)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (at least 3 are always run)")
+    ap.add_argument("--config", default="head", choices=["head", "olat", "hand_mvp", "mvp_full"],
+                    help="head = BASELINE configs[1] (the headline metric); olat = configs[2] (32 OLAT conditions x 16 views); "
+                         "hand_mvp = configs[3] (4096 primitives, 8 cameras, decode + raymarch fwd+bwd); mvp_full = configs[4] "
+                         "(256k primitives, 150 cameras)")
+    ap.add_argument("--no-decoder", action="store_true", help="skip the `decoder` sub-object of the headline line")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=300_000)
     ap.add_argument("--lights", type=int, default=32)
@@ -284,6 +291,115 @@ def kernel_roofline(dev, packed, cam, flush):
     return roof
 
 
+# ------------------------------------------------------------------------------------------ RGCA workloads (configs 2, 3)
+def _count_intersections(packed, Rts, intrs):
+    """(tile, Gaussian) intersections summed over the given views (one host sync; reporting only)."""
+    from goliath_b200.gsplat import project_gaussians
+
+    u = unpack(packed.detach())
+    total = 0
+    for Rt, (fx, fy, cx, cy) in zip(Rts, intrs):
+        nth = project_gaussians(u["primpos"].contiguous(), u["primscale"].contiguous(), 1.0, u["primqvec"].contiguous(), Rt,
+                                fx, fy, cx, cy, H, W, BW, 0.1)[5]
+        total += int(nth.sum().item())
+    return total
+
+
+class HeadWorkload:
+    """BASELINE configs[1]: 300k Gaussians, ONE view 1024x667 per rank (weak scaling), L = 32 point lights."""
+    key, scaling = "head", "weak"
+
+    def __init__(self, args, rank, world, dev):
+        from goliath_b200 import synthetic
+
+        self.args, self.rank, self.world, self.dev = args, rank, world, dev
+        self.G = args.gaussians
+        self.li = {k: v.to(dev) for k, v in synthetic.lights(args.lights).items()}
+        c = synthetic.ring_camera(rank % 16, img_h=H, img_w=W)
+        self.cam = dict(Rt=c["viewmat"][None].to(dev), intr=(c["fx"], c["fy"], c["cx"], c["cy"]))
+        self.cap = None if args.eager_sync else max(8 * self.G, 1 << 20)
+        self.views_local, self.images_per_view = 1, 1
+        self.mp_per_step = world * H * W / 1e6
+        self.metric = "rendered megapixels/sec (fwd+bwd) RGCA head 300k Gaussians"
+        self.workload = ("rgca_example.yml head: %d Gaussians, 1 view %dx%d per GPU, L=%d lights, shade+project+bin/sort+"
+                         "blend(rgb)+blend(depth) fwd+bwd" % (self.G, H, W, args.lights))
+        self.extra = {"views_per_gpu": 1, "lights": args.lights}
+
+    def intersections(self, packed):
+        return _count_intersections(packed, [self.cam["Rt"][0]], [self.cam["intr"]])
+
+    def compute(self, packed):
+        """forward + backward of one view from the flat decoded buffer; returns ([rgb, alpha, depth], flat grad)."""
+        leaves = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
+        rgb, alpha, depth = gpu_step(leaves, self.cam, self.li, capacity=self.cap)
+        grad = torch.cat([leaves[k].grad.reshape(-1) for k, _ in FIELDS])  # flat dL/d(decoded), same layout
+        return [rgb, alpha, depth], grad
+
+
+class OlatWorkload:
+    """BASELINE configs[2]: 300k Gaussians x 32 OLAT lighting conditions x 16 views, views sharded over the ranks (strong
+    scaling: the frame is fixed).  Per view: ONE projection + ONE tile binning, 32 x (L=1 shade -> blend) against the shared
+    bins (goliath_b200.gsplat.olat), forward and backward; the decoded table is broadcast, its gradient all-reduced."""
+    key, scaling = "olat", "strong"
+    N_VIEWS, N_COND = 16, 32
+
+    def __init__(self, args, rank, world, dev):
+        from goliath_b200 import synthetic
+        from goliath_b200.dist import views_of_rank
+
+        self.args, self.rank, self.world, self.dev = args, rank, world, dev
+        self.G = args.gaussians
+        li = synthetic.lights(self.N_COND)
+        self.lint = [li["light_intensity"][:, c:c + 1].contiguous().to(dev) for c in range(self.N_COND)]
+        self.lpos = [li["light_pos"][:, c:c + 1].contiguous().to(dev) for c in range(self.N_COND)]
+        self.one = torch.ones(1, dtype=torch.int32, device=dev)
+        self.views = views_of_rank(rank, world, self.N_VIEWS)
+        cams = [synthetic.ring_camera(v, img_h=H, img_w=W) for v in self.views]
+        self.Rt = torch.stack([c["viewmat"] for c in cams]).to(dev) if cams else torch.zeros(0, 3, 4, device=dev)
+        self.intr = [(c["fx"], c["fy"], c["cx"], c["cy"]) for c in cams]
+        self.cap = max(8 * self.G, 1 << 20)
+        self.views_local, self.images_per_view = len(self.views), self.N_COND
+        self.mp_per_step = self.N_VIEWS * self.N_COND * H * W / 1e6
+        self.metric = "rendered megapixels/sec (fwd+bwd) RGCA OLAT relighting 300k Gaussians x 32 lights x 16 views"
+        self.workload = ("RGCA relighting: %d Gaussians x %d OLAT lighting conditions x %d views (%dx%d) sharded over the "
+                         "ranks; per view one projection + one tile binning, %d x (L=1 shade + blend) fwd+bwd"
+                         % (self.G, self.N_COND, self.N_VIEWS, H, W, self.N_COND))
+        self.extra = {"views_total": self.N_VIEWS, "views_this_rank": len(self.views), "conditions": self.N_COND}
+
+    def intersections(self, packed):
+        return _count_intersections(packed, list(self.Rt), self.intr)
+
+    def compute(self, packed):
+        from goliath_b200.gsplat.olat import render_views_shared
+        from goliath_b200.rgca_heads import shade_compose
+
+        u = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
+        V = len(self.views)
+        cols = [shade_compose(u["lobe_dirs"][None], u["sigma"][None], self.lint[c], self.lpos[c], u["primpos"][None], self.one,
+                              u["diff_color"][None], u["spec_vis"][None])[0] for c in range(self.N_COND)]
+        colors = torch.stack(cols)                                             # [C,G,3]
+        geom = {k: u[k][None].expand(V, *u[k].shape) for k in ("primpos", "primqvec", "primscale", "opacity")}
+        rgb, alpha, depth = render_views_shared(W, H, self.Rt, geom, colors[None].expand(V, *colors.shape), self.intr,
+                                                capacity=self.cap)
+        torch.autograd.backward([rgb, depth], [torch.ones_like(rgb), torch.ones_like(depth)])
+        grad = torch.cat([u[k].grad.reshape(-1) for k, _ in FIELDS])
+        return [rgb, alpha, depth], grad
+
+
+def _timeit_events(fn, reps, flush=None):
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return ts
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -294,31 +410,25 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from goliath_b200 import _lib, synthetic
+    from goliath_b200 import _lib
+    from goliath_b200.dist import FrameExchange
 
     lib = _lib.lib()
-    G = args.gaussians
+    wl = (OlatWorkload if args.config == "olat" else HeadWorkload)(args, rank, world, dev)
+    G = wl.G
+    steps = args.steps if args.steps is not None else (200 if wl.key == "head" else 10)
+    warmup = args.warmup if args.warmup is not None else (10 if wl.key == "head" else 3)
+    warmup = max(3, warmup)
     host_packed = packed_scene(G).pin_memory()
-    li_h = synthetic.lights(args.lights)
-    li = {k: v.to(dev) for k, v in li_h.items()}
-    c = synthetic.ring_camera(rank % 16, img_h=H, img_w=W)
-    cam = dict(Rt=c["viewmat"][None].to(dev), intr=(c["fx"], c["fy"], c["cx"], c["cy"]))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def flush():
         flush_buf.fill_(1)  # > 126 MB L2
 
     resident = host_packed.to(dev)
-    cap = None if args.eager_sync else max(8 * G, 1 << 20)   # sync-free capacity (intersections); None = exact + host sync
+    cap = wl.cap
     static_in = torch.empty_like(resident)                    # the graph's input buffer (field-major decoded Gaussians)
     state = {"graph": None, "outs": None}
-
-    def compute(packed):
-        """forward + backward of one view from the flat decoded buffer; returns (rgb, alpha, depth, flat grad)."""
-        leaves = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
-        rgb, alpha, depth = gpu_step(leaves, cam, li, capacity=cap)
-        grad = torch.cat([leaves[k].grad.reshape(-1) for k, _ in FIELDS])  # flat dL/d(decoded), same layout
-        return rgb, alpha, depth, grad
 
     def build_graph():
         """Capture compute(static_in) once (sync-free path), after side-stream warm-up as torch requires."""
@@ -326,144 +436,123 @@ def run_ours(args):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
-                compute(static_in)
+                wl.compute(static_in)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            outs = compute(static_in)
+            outs = wl.compute(static_in)
         state["graph"], state["outs"] = g, outs
 
-    def one_step(e2e):
-        src = host_packed if e2e else resident
-        static_in.copy_(src, non_blocking=True)     # e2e: pinned host -> device inside the timed region
-        if world > 1:
-            dist.broadcast(static_in, src=0)        # decoded Gaussians of the frame, owner = rank 0
+    def run_step():
         if state["graph"] is not None:
             state["graph"].replay()
-            rgb, alpha, depth, grad = state["outs"]
-        else:
-            rgb, alpha, depth, grad = compute(static_in)
-        if world > 1:
-            dist.all_reduce(grad)                   # dL/d(decoded) summed over the views
-        if e2e:
-            # the step's result as a caller consumes it: the rendered rgb / alpha / depth images go back to the host;
-            # dL/d(decoded) stays on the device for the optimiser, as in the reference's training loop
-            for dst, src_t in zip(host_out, (rgb, alpha, depth)):
-                dst.copy_(src_t, non_blocking=True)
-        return None
+            return state["outs"]
+        return wl.compute(static_in)
 
-    host_out = [torch.empty(1, 3, H, W).pin_memory(), torch.empty(1, 1, H, W).pin_memory(), torch.empty(1, 1, H, W).pin_memory()]
     # one eager step to count this library's launches per step, then capture
     static_in.copy_(resident)
-    compute(static_in)
+    outs0, _ = wl.compute(static_in)
     torch.cuda.synchronize()
     lib.gb_launch_count_reset()
-    compute(static_in)
+    wl.compute(static_in)
     torch.cuda.synchronize()
     launches_per_step = int(lib.gb_launch_count())
+    host_out = [torch.empty(t.shape).pin_memory() for t in outs0]
+    host_out2 = [torch.empty(t.shape).pin_memory() for t in outs0]
+    d2h = sum(t.numel() * 4 for t in outs0)
+    del outs0
     if cap is not None and not args.no_graph:
         build_graph()
 
-    def timed_resident(steps, warmup):
-        """`value` arm: inputs resident in HBM.  With N > 1 the two exchange steps run on a communication stream:
-        the broadcast of frame i+1's decoded table overlaps step i's graph, the all-reduce of step i's gradient overlaps
-        step i+1 (double-buffered staging); whatever is NOT hidden shows up as a wait inside the per-step event pair."""
-        main = torch.cuda.current_stream()
-        if world == 1:
-            return timed(False, steps, warmup)
-        comm = torch.cuda.Stream()
-        next_in = [torch.empty_like(resident) for _ in range(2)]
-        grad_stage = [torch.empty_like(resident) for _ in range(2)]
-        ev = lambda: [torch.cuda.Event() for _ in range(2)]
-        bc_done, in_free, g_ready, g_free = ev(), ev(), ev(), ev()
+    # ---------------------------------------------------------------- N = 1 paths
+    def timed_single(e2e, n_steps, n_warm):
+        """per-step event pairs; e2e: the table comes from pinned host memory and the images go back, serially."""
+        def one():
+            static_in.copy_(host_packed if e2e else resident, non_blocking=True)
+            imgs, _ = run_step()
+            if e2e:
+                for dst, src_t in zip(host_out, imgs):
+                    dst.copy_(src_t, non_blocking=True)
+        for _ in range(n_warm):
+            one()
+        torch.cuda.synchronize()
+        lib.gb_launch_count_reset()
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            one()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        return sum(per_step), per_step, time.perf_counter() - t0
 
-        def bcast(i):
-            k = i & 1
-            with torch.cuda.stream(comm):
-                if i >= 2:
-                    comm.wait_event(in_free[k])
-                next_in[k].copy_(resident, non_blocking=True)   # stands for the owner's decoder output of frame i
-                dist.broadcast(next_in[k], src=0)
-                bc_done[k].record(comm)
+    # ---------------------------------------------------------------- N > 1: the exchange steps (goliath_b200.dist)
+    def timed_exchange(e2e, n_steps, n_warm):
+        """The frame owner (rank 0) broadcasts frame i+1's decoded table and every rank's gradient of frame i is
+        all-reduced, both on FrameExchange's communication stream under the neighbouring renders.  e2e: the OWNER's table
+        comes from pinned host memory (the other ranks receive it over NVLink and copy nothing in), every rank's images go
+        back to its pinned host buffers on a copy stream."""
+        ex = FrameExchange(resident.numel(), dev, owner=0)
+        src = (host_packed if e2e else resident) if rank == 0 else None
+        s_out = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        stage_out = [[torch.empty_like(t) for t in state["outs"][0]] for _ in range(2)] if e2e else None
+        hosts = [host_out, host_out2]
+        out_ready = [torch.cuda.Event() for _ in range(2)]
+        out_free = [torch.cuda.Event() for _ in range(2)]
 
         def run(n, evs):
-            bcast(0)
+            ex.post_input(0, src)
             for i in range(n):
                 k = i & 1
                 flush()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                main.wait_event(bc_done[k])
-                static_in.copy_(next_in[k], non_blocking=True)
-                in_free[k].record(main)
+                ex.take_input(i, static_in)
                 if i + 1 < n:
-                    bcast(i + 1)
-                state["graph"].replay() if state["graph"] is not None else None
-                grad = state["outs"][3] if state["graph"] is not None else compute(static_in)[3]
-                if i >= 2:
-                    main.wait_event(g_free[k])
-                grad_stage[k].copy_(grad, non_blocking=True)
-                g_ready[k].record(main)
-                with torch.cuda.stream(comm):
-                    comm.wait_event(g_ready[k])
-                    dist.all_reduce(grad_stage[k])              # dL/d(decoded) summed over the views
-                    g_free[k].record(comm)
+                    ex.post_input(i + 1, src)
+                imgs, grad = run_step()
+                ex.post_grad(i, grad)
+                if e2e:
+                    if i >= 2:
+                        main.wait_event(out_free[k])
+                    for dst, src_t in zip(stage_out[k], imgs):
+                        dst.copy_(src_t, non_blocking=True)
+                    out_ready[k].record(main)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(out_ready[k])
+                        for dst, src_t in zip(hosts[k], stage_out[k]):
+                            dst.copy_(src_t, non_blocking=True)
+                        out_free[k].record(s_out)
                 if i + 1 == n:
-                    main.wait_stream(comm)
+                    ex.finish()
+                    main.wait_stream(s_out)
                 b.record()
                 evs.append((a, b))
 
-        run(warmup, [])
+        run(n_warm, [])
         torch.cuda.synchronize()
         dist.barrier()
         evs = []
         t0 = time.perf_counter()
-        run(steps, evs)
+        run(n_steps, evs)
         torch.cuda.synchronize()
         dist.barrier()
         wall = time.perf_counter() - t0
-        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches_per_step * steps, wall
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        return sum(per_step), per_step, wall, ex.bytes_h2d
 
-    def timed(e2e, steps, warmup):
-        for _ in range(warmup):
-            one_step(e2e)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        lib.gb_launch_count_reset()
-        evs = []
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            flush()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            one_step(e2e)
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        launches = launches_per_step * steps
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, wall
-
-    def timed_e2e(steps, warmup):
-        """End to end, streamed: every step's decoded-Gaussian table comes from pinned host memory and its images go back
-        to pinned host memory, with the H2D copy of step i+1 and the D2H copy of step i-1 running on their own streams
-        under step i's graph (double-buffered staging on both sides).  One device-side event pair around all K steps."""
+    def timed_e2e_streamed_single(n_steps, n_warm):
+        """N = 1, streamed: H2D of step i+1 and D2H of step i-1 on their own streams under step i's graph."""
         main = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         stage_in = [torch.empty_like(resident) for _ in range(2)]
-        stage_out = [[torch.empty(1, 3, H, W, device=dev), torch.empty(1, 1, H, W, device=dev),
-                      torch.empty(1, 1, H, W, device=dev)] for _ in range(2)]
-        hosts = [host_out, [torch.empty_like(t).pin_memory() for t in host_out]]
-        stage_grad = [torch.empty_like(resident) for _ in range(2)] if world > 1 else None
+        stage_out = [[torch.empty_like(t) for t in state["outs"][0]] for _ in range(2)] if state["outs"] else None
+        hosts = [host_out, host_out2]
         ev = lambda: [torch.cuda.Event() for _ in range(2)]
         in_ready, in_free, out_ready, out_free = ev(), ev(), ev(), ev()
 
@@ -473,8 +562,6 @@ def run_ours(args):
                 if i >= 2:
                     s_in.wait_event(in_free[k])
                 stage_in[k].copy_(host_packed, non_blocking=True)
-                if world > 1:
-                    dist.broadcast(stage_in[k], src=0)          # decoded Gaussians of the frame, owner = rank 0
                 in_ready[k].record(s_in)
 
         def run(n):
@@ -487,67 +574,94 @@ def run_ours(args):
                 main.wait_event(in_ready[k])
                 static_in.copy_(stage_in[k], non_blocking=True)
                 in_free[k].record(main)
-                if state["graph"] is not None:
-                    state["graph"].replay()
-                    rgb, alpha, depth, grad = state["outs"]
-                else:
-                    rgb, alpha, depth, grad = compute(static_in)
+                imgs, _ = run_step()
+                if stage_out is None:
+                    for dst, src_t in zip(hosts[k], imgs):
+                        dst.copy_(src_t, non_blocking=True)
+                    continue
                 if i >= 2:
                     main.wait_event(out_free[k])
-                for dst, src_t in zip(stage_out[k], (rgb, alpha, depth)):
+                for dst, src_t in zip(stage_out[k], imgs):
                     dst.copy_(src_t, non_blocking=True)
-                if world > 1:
-                    stage_grad[k].copy_(grad, non_blocking=True)
                 out_ready[k].record(main)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(out_ready[k])
-                    if world > 1:
-                        dist.all_reduce(stage_grad[k])          # dL/d(decoded) summed over the views
                     for dst, src_t in zip(hosts[k], stage_out[k]):
                         dst.copy_(src_t, non_blocking=True)
                     out_free[k].record(s_out)
             main.wait_stream(s_out)
 
-        run(warmup)
+        run(n_warm)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        run(steps)
+        run(n_steps)
         b.record()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        return a.elapsed_time(b)
+
+    def rank_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def rank_gather(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     proc = path = None
     if rank == 0:
         proc, path = sample_clocks_start(local)
-    ms_total, launches, wall = timed_resident(args.steps, args.warmup)
-    ms_e2e_serial, _, _ = timed(True, max(20, args.steps // 4), 3)
-    ms_e2e_serial *= args.steps / max(20, args.steps // 4)
-    ms_e2e = timed_e2e(args.steps, max(3, args.warmup))
+    e2e_steps = max(min(steps, 20), steps // 4)
+    collectives = None
+    if world == 1:
+        ms_total, per_step, wall = timed_single(False, steps, warmup)
+        ms_e2e_serial = timed_single(True, e2e_steps, 3)[0] * steps / e2e_steps
+        ms_e2e = timed_e2e_streamed_single(steps, warmup)
+        h2d_rank = host_packed.numel() * 4
+    else:
+        ms_total, per_step, wall, _ = timed_exchange(False, steps, warmup)
+        ms_e2e, _, _, h2d_bytes = timed_exchange(True, steps, warmup)
+        ms_e2e_serial = None
+        h2d_rank = h2d_bytes // max(steps + warmup, 1)
+        # the exchange steps alone (no render), on an idle machine: what has to be hidden under a step
+        ex_t = resident.clone()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_bc = float(np.median(_timeit_events(lambda: dist.broadcast(ex_t, src=0), 10)))
+        t_ar = float(np.median(_timeit_events(lambda: dist.all_reduce(ex_t), 10)))
+        collectives = {"broadcast_ms_alone": rank_max(t_bc), "allreduce_ms_alone": rank_max(t_ar),
+                       "bytes": ex_t.numel() * 4}
+    per_rank_isect = rank_gather(float(wl.intersections(resident)))
+    own_ms = float(np.sum(per_step))
+    ms_total = rank_max(ms_total)
+    ms_e2e = rank_max(ms_e2e)
+    per_rank_ms = rank_gather(own_ms / steps)
+    h2d_per_rank = rank_gather(float(h2d_rank))
+    # the render alone on this rank (no exchange, no copies): view heterogeneity vs collective cost
+    torch.cuda.synchronize()
+    render_only = float(np.mean(_timeit_events(lambda: run_step(), 10, flush)))
+    per_rank_render = rank_gather(render_only)
     clocks = sample_clocks_stop(proc, path) if rank == 0 else None
 
-    mp_per_step = world * H * W / 1e6
-    value = mp_per_step * args.steps / (ms_total / 1e3)
-    e2e_v = mp_per_step * args.steps / (ms_e2e / 1e3)
-    h2d = host_packed.numel() * 4
-    d2h = (H * W * 3 + H * W + H * W) * 4
+    mp_per_step = wl.mp_per_step
+    value = mp_per_step * steps / (ms_total / 1e3)
+    e2e_v = mp_per_step * steps / (ms_e2e / 1e3)
 
     overflow = False
     if cap is not None:
         from goliath_b200.gsplat.fused import check_overflow
         overflow = check_overflow(dev)
-    roof = cpu = None
-    if rank == 0:
-        roof = kernel_roofline(dev, resident, cam, flush)
+    roof = cpu = dec = None
+    if rank == 0 and wl.key == "head":
+        roof = kernel_roofline(dev, resident, wl.cam, flush)
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(args, steps=1, warmup=0)
+            cpu = cpu_baseline(args, steps=3, warmup=3)
             try:
                 cpu["decoder_shade"] = cpu_decoder_shade(args.lights)
             except Exception as e:  # the headline line must not depend on this extra
@@ -556,38 +670,388 @@ def run_ours(args):
                 cpu["mesh_vae_decoder"] = cpu_mesh_vae_decoder()
             except Exception as e:
                 cpu["mesh_vae_decoder"] = {"error": str(e)[:200]}
+        if world == 1 and not args.no_decoder:
+            try:
+                dec = decoder_summary(args, dev)
+            except Exception as e:
+                dec = {"error": str(e)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
     line = {
-        "metric": "rendered megapixels/sec (fwd+bwd) RGCA head 300k Gaussians", "value": value, "unit": "MP/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "rgca_example.yml head: %d Gaussians, 1 view %dx%d per GPU, L=%d lights, shade+project+"
-                               "bin/sort+blend(rgb)+blend(depth) fwd+bwd" % (G, H, W, args.lights),
-                   "gaussians": G, "views_per_gpu": 1, "lights": args.lights, "block_width": BW,
-                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world,
-                   "collectives": (None if world == 1 else "NCCL broadcast of frame i+1's decoded table and all-reduce of "
-                                   "step i's gradient on a communication stream, overlapped with the neighbouring steps"),
-                   "host_path": ("eager, exact buffers, 1 host sync/view" if cap is None else
-                                 ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
-                                                                                 ", step captured in a CUDA graph"))),
-                   "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
-                   "blend": ["batch (CTA-synchronous)", "pipe (warp-decoupled)", "affine (warp-decoupled, SM-affine "
-                             "tile schedule)", "mom (exact cull, 4-hit ILP forward, transposed-reduction backward)",
-                             "mom-affine (mom over the SM-affine tile schedule)"][int(lib.gb_get_blend_mode())],
-                   "intersection_overflow": overflow},
-        "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps,
-                "how": "streamed: H2D of step i+1 and D2H of step i-1 on copy streams under step i's graph; the timed "
-                       "region (one event pair around all steps) includes the per-step 256 MiB L2 flush",
-                "serial_ms_per_step": ms_e2e_serial / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "metric": wl.metric, "value": value, "unit": "MP/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+        "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict({"workload": wl.workload, "name": wl.key, "gaussians": G, "block_width": BW,
+                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world,
+                        "collectives": (None if world == 1 else "goliath_b200.dist.FrameExchange: NCCL broadcast of frame "
+                                        "i+1's decoded table from its owner and all-reduce of frame i's gradient on a "
+                                        "communication stream under the neighbouring renders; only the owner reads its source"),
+                        "host_path": ("eager, exact buffers, 1 host sync/view" if cap is None else
+                                      ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
+                                                                                      ", step captured in a CUDA graph"))),
+                        "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
+                        "rank_sort": ["cooperative (one launch, varying key bits only)", "4 radix passes"][int(lib.gb_get_rank_sort_mode())],
+                        "blend": ["batch (CTA-synchronous)", "pipe (warp-decoupled)", "affine (warp-decoupled, SM-affine "
+                                  "tile schedule)", "mom (exact cull, 4-hit ILP forward, transposed-reduction backward)",
+                                  "mom-affine (mom over the SM-affine tile schedule)"][int(lib.gb_get_blend_mode())],
+                        "intersection_overflow": overflow}, **wl.extra),
+        "e2e": {"value": e2e_v, "unit": "MP/s", "h2d_bytes_per_step": int(sum(h2d_per_rank)), "d2h_bytes_per_step": d2h * world,
+                "ms_per_step": ms_e2e / steps,
+                "how": ("streamed: H2D of step i+1 and D2H of step i-1 on copy streams under step i's graph; rendered images "
+                        "(not gradients: they stay on the device for the optimiser) go back to pinned host memory; the timed "
+                        "region includes the per-step 256 MiB L2 flush" if world == 1 else
+                        "owner-only H2D of the decoded table, NCCL broadcast, render, gradient all-reduce, D2H of every "
+                        "rank's images, double-buffered on communication / copy streams; per-step event pairs, max over ranks"),
+                "serial_ms_per_step": None if ms_e2e_serial is None else ms_e2e_serial / steps,
+                "h2d_bytes_per_rank": [int(x) for x in h2d_per_rank]},
+        "gpu_launches": launches_per_step * steps, "clocks": clocks, "roofline": roof,
+        "per_rank": {"ms_per_step": per_rank_ms, "render_only_ms": per_rank_render,
+                     "intersections": [int(x) for x in per_rank_isect], "collectives": collectives},
     }
+    if dec is not None:
+        line["decoder"] = dec
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ MVP workloads (configs 4, 5)
+def _mvp_dist_setup():
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local, dev
+
+
+def _ref_ext(name):
+    import importlib.util
+
+    so = os.path.join(ROOT, "oracle", "_ref", name + ".so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location(name, so)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _raymarch_kernels_alone(dev, raypos, raydir, tminmax, transf, template, step, reps=5):
+    """forward / backward raymarch kernels alone through the extension-module API (ours and, when oracle/_ref holds it,
+    the reference's mvpraymarchlib rebuilt for sm_100a) on the same tensors: the extension-level ratio of north_star."""
+    from goliath_b200 import mvpraymarchlib
+    from goliath_b200.mvpraymarch import _fixedorder_topology
+
+    N, Hh, Ww = raypos.shape[:3]
+    K = transf[0].shape[1]
+    sid, ch, par = _fixedorder_topology(N, K, dev)
+    aabb = torch.empty(N, 2 * K - 1, 2, 3, device=dev)
+    rgba = torch.empty(N, Hh, Ww, 4, device=dev)
+    sat = torch.empty(N, Hh, Ww, 3, device=dev)
+    grgba = torch.ones(N, Hh, Ww, 4, device=dev)
+    gp, gr, gsc = (torch.zeros_like(t) for t in transf)
+    gt = torch.zeros_like(template)
+    res = {}
+    for tag, lib in (("ours", mvpraymarchlib), ("reference", _ref_ext("mvpraymarchlib"))):
+        if lib is None:
+            continue
+        lib.compute_aabb(*transf, sid, ch, par, aabb, 0)
+
+        def fwd():
+            sat.fill_(-1.0)
+            lib.raymarch_forward(raypos, raydir, step, tminmax, sid, ch, aabb, *transf, template, None, rgba, sat, None, None, 0,
+                                 False, 512, True, True, 8.0, 8.0, 0, 0.99, 3, 8, 16)
+
+        def bwd():
+            lib.raymarch_backward(raypos, raydir, step, tminmax, sid, ch, aabb, transf[0], gp, transf[1], gr, transf[2], gsc,
+                                  template, gt, None, None, rgba, grgba, sat, None, 0, False, 512, True, True, 8.0, 8.0, 0, 0.99,
+                                  3, 8, 16)
+
+        fwd(); bwd()
+        res["raymarch_fwd_ms_" + tag] = float(np.median(_timeit_events(fwd, reps)))
+        res["raymarch_bwd_ms_" + tag] = float(np.median(_timeit_events(bwd, reps)))
+        res["alpha_mean_" + tag] = float(rgba[..., 3].mean())
+    if "raymarch_fwd_ms_reference" in res:
+        res["ours_over_reference_fwd_bwd"] = ((res["raymarch_fwd_ms_reference"] + res["raymarch_bwd_ms_reference"])
+                                              / (res["raymarch_fwd_ms_ours"] + res["raymarch_bwd_ms_ours"]))
+    return res
+
+
+def _mvp_roofline(N, K, T, P, ms_fwd, ms_bwd):
+    """raymarch fwd bytes = N*(K*TD*TH*TW*16 + K*60 + (2K-1)*24) + N*P*(32 + 16 + 12); the backward
+    adds the template-gradient RMW (K*TD*TH*TW*16*2) and reads the forward's outputs.  L2/latency-bound by design: the
+    HBM fraction is reported, it is not the target."""
+    vox = K * T[0] * T[1] * T[2]
+    b_f = N * (vox * 16 + K * 60 + (2 * K - 1) * 24) + N * P * (32 + 16 + 12)
+    b_b = N * (vox * 16 * 3 + K * 60 * 2 + (2 * K - 1) * 24) + N * P * (32 + 16 + 12 + 16)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ks = {"raymarch_fwd_kernel": {"ms": ms_fwd, "alg_bytes": b_f, "gbs": b_f / ms_fwd / 1e6},
+          "raymarch_bwd_kernel": {"ms": ms_bwd, "alg_bytes": b_b, "gbs": b_b / ms_bwd / 1e6}}
+    dom = max(ks, key=lambda k: ks[k]["ms"])
+    return {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": ks[dom]["gbs"] / peak, "traffic": None, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+            "note": "the march is L2/latency-bound (SURVEY.md section 8d): HBM fraction reported, not the target",
+            "kernels": ks}
+
+
+def run_hand_mvp(args):
+    """BASELINE configs[3]: hand_mvp_example.yml — 4096 volumetric primitives (64x64 UV grid, 8x16x16 voxels each), 8 cameras
+    1024x667, one step = PoseEncoder -> TransDecoder + alpha / rgb slab decoders -> primitive transforms -> slab->primitive
+    re-layout -> ray generation -> mvpraymarch, forward + backward (loss = sum of the rendered rgba), as
+    ca_code/models/hand_mvp.py:205-268 runs it (mesh/LBS front end replaced by a synthetic base frame)."""
+    import torch.distributed as dist
+
+    world, rank, local, dev = _mvp_dist_setup()
+    from goliath_b200 import _lib, synthetic
+    from goliath_b200 import mvpraymarch as mvr
+    from goliath_b200 import utils as gutils
+    from goliath_b200.dist import views_of_rank
+    from goliath_b200.hand_mvp import DeconvContentDecoder, PoseEncoder, TransDecoder, prim_transforms, slabs_to_primrgba
+
+    lib = _lib.lib()
+    steps = args.steps if args.steps is not None else 10
+    warmup = max(3, args.warmup if args.warmup is not None else 3)
+    NCAM, K, T = 8, 4096, (8, 16, 16)
+    cams = views_of_rank(rank, world, NCAM)
+    B = len(cams)
+    torch.manual_seed(4096)
+    s = synthetic.mvp_scene(N=NCAM, side=64, T=(1, 1, 1), img_h=H, img_w=W, density=1.0)  # geometry + cameras only
+    sel = torch.tensor(cams, dtype=torch.long)
+    posbase = s["primpos"][sel].to(dev).contiguous()
+    rotbase = s["primrot"][sel].to(dev).contiguous()
+    cam = {k: s[k][sel].to(dev).contiguous() for k in ("viewpos", "viewrot", "focal", "princpt")}
+    penc = PoseEncoder(54, 64, 64).to(dev)
+    tdec = TransDecoder(64).to(dev)
+    adec, rdec = DeconvContentDecoder(8, 64, 1).to(dev), DeconvContentDecoder(8, 66, 3).to(dev)
+    with torch.no_grad():  # random-init weights; output biases set so the volume is semi-transparent and coloured
+        adec.texbranch[-1].bias.fill_(float(args.mvp_density))
+        rdec.texbranch[-1].bias.fill_(2.0)
+    params = [p for m in (penc, tdec, adec, rdec) for p in m.parameters()]
+    gen = torch.Generator().manual_seed(54)
+    host_pose = torch.randn(NCAM, 60, generator=gen)[sel].contiguous().pin_memory()
+    host_cond = torch.rand(NCAM, 2, 64, 64, generator=gen)[sel].contiguous().pin_memory()  # view_cos_uv, ambient occlusion
+    pose_d, cond_d = host_pose.to(dev), host_cond.to(dev)
+    step_sz = 1.0 / 2000.0
+    host_img = torch.empty(B, H, W, 4).pin_memory()
+
+    def forward(pose, cond):
+        joint = penc(pose)
+        primpos, primrot, primscale = prim_transforms(tdec.raw(joint), posbase, rotbase, prim_scale=56.0)
+        alpha_raw = adec(joint).view(B, 8, 1, 1024, 1024)
+        rgb_raw = rdec(torch.cat([joint, cond], 1)).view(B, 8, 3, 1024, 1024)
+        tpl = slabs_to_primrgba(rgb_raw, alpha_raw, (16, 16, 8), valid_prims=None, raw=True)
+        raypos, raydir, tminmax = gutils.compute_raydirs(cam["viewpos"], cam["viewrot"], cam["focal"], cam["princpt"], (W, H), 1.0)
+        out = mvr.mvpraymarch(raypos, raydir, step_sz, tminmax, (primpos, primrot, primscale), tpl, None)
+        return out, (raypos, raydir, tminmax, primpos, primrot, primscale, tpl)
+
+    def step(e2e):
+        if e2e:
+            pose_d.copy_(host_pose, non_blocking=True)
+            cond_d.copy_(host_cond, non_blocking=True)
+        out, _ = forward(pose_d, cond_d)
+        out.backward(_ones_like(out))
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        if e2e:
+            host_img.copy_(out.detach(), non_blocking=True)
+        for p in params:
+            p.grad = None
+
+    def timed(e2e, n, w):
+        for _ in range(w):
+            step(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        lib.gb_launch_count_reset()
+        evs = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(e2e); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        launches = int(lib.gb_launch_count())
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    proc = path = None
+    if rank == 0:
+        proc, path = sample_clocks_start(local)
+    ms_total, launches = timed(False, steps, warmup)
+    ms_e2e, _ = timed(True, steps, 3)
+    clocks = sample_clocks_stop(proc, path) if rank == 0 else None
+    ext = roof = None
+    if rank == 0:
+        with torch.no_grad():
+            out, (raypos, raydir, tminmax, primpos, primrot, primscale, tpl) = forward(pose_d, cond_d)
+        ext = _raymarch_kernels_alone(dev, raypos, raydir, tminmax, (primpos.contiguous(), primrot.contiguous(),
+                                                                     primscale.contiguous()), tpl.contiguous(), step_sz)
+        roof = _mvp_roofline(B, K, T, H * W, ext["raymarch_fwd_ms_ours"], ext["raymarch_bwd_ms_ours"])
+        ext["alpha_mean_rendered"] = float(out[..., 3].mean())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    mp = NCAM * H * W / 1e6
+    line = {
+        "metric": "rendered megapixels/sec (fwd+bwd) hand-MVP 4096 primitives, 8 cameras", "value": mp * steps / (ms_total / 1e3),
+        "unit": "MP/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "hand_mvp_example.yml: 4096 volumetric primitives (8x16x16 voxels), 8 cameras %dx%d, decode "
+                               "(PoseEncoder, TransDecoder, alpha/rgb slab decoders) + slab->primitive + raydirs + mvpraymarch "
+                               "fwd+bwd, stepsize 1/2000" % (H, W),
+                   "name": "hand_mvp", "cameras": NCAM, "cameras_this_rank": B, "primitives": K, "template": list(T),
+                   "l2": "inputs regenerated every step (1.07 GB of templates per 8 cameras: larger than L2)",
+                   "parallelism": "camera-shard x%d" % world, "alpha_bias": args.mvp_density},
+        "e2e": {"value": mp * steps / (ms_e2e / 1e3), "unit": "MP/s", "h2d_bytes_per_step": NCAM * (60 + 2 * 64 * 64) * 4,
+                "d2h_bytes_per_step": NCAM * H * W * 4 * 4, "ms_per_step": ms_e2e / steps,
+                "how": "pose + conditioning maps from pinned host memory, rendered rgba images back to pinned host memory, "
+                       "serial inside each step; parameter gradients stay on the device"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "reference_extension": ext,
+    }
+    print(json.dumps(line))
+
+
+def run_mvp_full(args):
+    """BASELINE configs[4]: full-body MVP — 262 144 primitives (512x512 UV grid, 8x8x8 voxels each: a 2.1 GB template), 150
+    cameras of one frame sharded over the ranks (19/18 per GPU at N = 8), one train step = ray generation + raymarch
+    forward + backward per camera against the shared template, template / transform gradients accumulated over the
+    cameras and all-reduced.  The frame owner broadcasts the template."""
+    import torch.distributed as dist
+
+    world, rank, local, dev = _mvp_dist_setup()
+    from goliath_b200 import _lib, synthetic
+    from goliath_b200 import mvpraymarch as mvr
+    from goliath_b200 import utils as gutils
+    from goliath_b200.dist import views_of_rank
+
+    lib = _lib.lib()
+    steps = args.steps if args.steps is not None else 3
+    warmup = max(3, args.warmup if args.warmup is not None else 3)
+    NCAM, SIDE, T = 150, 512, (8, 8, 8)
+    K = SIDE * SIDE
+    cams = views_of_rank(rank, world, NCAM)
+    V = len(cams)
+    s = synthetic.mvp_scene(N=1, side=SIDE, T=(1, 1, 1), img_h=H, img_w=W, density=1.0)  # geometry of the frame
+    primpos = s["primpos"].to(dev).requires_grad_()
+    primrot = s["primrot"].to(dev).requires_grad_()
+    primscale = s["primscale"].to(dev).requires_grad_()
+    views = [synthetic.ring_camera((v * 7) % 16, radius=2.5, img_h=H, img_w=W) for v in cams]
+    yoff = [0.15 * ((v % 5) - 2) for v in cams]  # five rings of cameras at different heights
+    viewpos = torch.stack([c["campos"] + torch.tensor([0.0, y, 0.0]) for c, y in zip(views, yoff)]).to(dev)
+    viewrot = torch.stack([c["viewmat"][:, :3] for c in views]).to(dev).contiguous()
+    focal = torch.full((V, 2), 1.6 * min(H, W), device=dev)
+    princpt = torch.tensor([[W / 2.0, H / 2.0]] * V, device=dev)
+    # template generated on the device (2.1 GB): softplus(1.5 N(0,1)), alpha channel shifted and scaled by the density
+    gen = torch.Generator(device=dev).manual_seed(262144)
+    tpl = torch.nn.functional.softplus(1.5 * torch.randn(1, K, *T, 4, device=dev, generator=gen))
+    tpl[..., 3] = torch.nn.functional.softplus(tpl[..., 3] * 0 + 1.5 * torch.randn(1, K, *T, device=dev, generator=gen) - 1.0) \
+        * float(args.mvp_density)
+    host_tpl = tpl.cpu().pin_memory() if rank == 0 else None
+    tpl.requires_grad_()
+    step_sz = 1.0 / 2000.0
+    host_img = torch.empty(max(V, 1), H, W, 4).pin_memory()
+
+    def step(e2e):
+        if e2e:
+            if rank == 0:
+                tpl.data.copy_(host_tpl, non_blocking=True)   # the frame owner's decoded template arrives from the host
+        if world > 1:
+            dist.broadcast(tpl.data, src=0)                   # ... and goes to the view shards
+        for i in range(V):
+            raypos, raydir, tminmax = gutils.compute_raydirs(viewpos[i:i + 1], viewrot[i:i + 1], focal[i:i + 1],
+                                                             princpt[i:i + 1], (W, H), 1.0)
+            out = mvr.mvpraymarch(raypos, raydir, step_sz, tminmax, (primpos, primrot, primscale), tpl, None)
+            out.backward(_ones_like(out))
+            if e2e:
+                host_img[i].copy_(out.detach()[0], non_blocking=True)
+        if world > 1:
+            for t in (tpl, primpos, primrot, primscale):
+                if t.grad is None:
+                    t.grad = torch.zeros_like(t)
+            dist.all_reduce(tpl.grad)
+            small = torch.cat([primpos.grad.reshape(-1), primrot.grad.reshape(-1), primscale.grad.reshape(-1)])
+            dist.all_reduce(small)
+        for t in (tpl, primpos, primrot, primscale):
+            t.grad = None
+
+    def timed(e2e, n, w):
+        for _ in range(w):
+            step(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        lib.gb_launch_count_reset()
+        evs = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(e2e); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        launches = int(lib.gb_launch_count())
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    proc = path = None
+    if rank == 0:
+        proc, path = sample_clocks_start(local)
+    ms_total, launches = timed(False, steps, warmup)
+    ms_e2e, _ = timed(True, steps, 3)
+    clocks = sample_clocks_stop(proc, path) if rank == 0 else None
+    ext = roof = None
+    if rank == 0 and V > 0:
+        with torch.no_grad():
+            raypos, raydir, tminmax = gutils.compute_raydirs(viewpos[:1], viewrot[:1], focal[:1], princpt[:1], (W, H), 1.0)
+        ext = _raymarch_kernels_alone(dev, raypos, raydir, tminmax, (primpos.detach(), primrot.detach(), primscale.detach()),
+                                      tpl.detach(), step_sz, reps=3)
+        roof = _mvp_roofline(1, K, T, H * W, ext["raymarch_fwd_ms_ours"], ext["raymarch_bwd_ms_ours"])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    mp = NCAM * H * W / 1e6
+    tpl_bytes = K * T[0] * T[1] * T[2] * 16
+    line = {
+        "metric": "rendered megapixels/sec (fwd+bwd) full-body MVP 256k primitives, 150 cameras", "value": mp * steps / (ms_total / 1e3),
+        "unit": "MP/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full-body MVP: 262144 primitives (8x8x8 voxels, 2.1 GB template), 150 cameras %dx%d of one frame, "
+                               "raydirs + mvpraymarch fwd+bwd per camera against the shared template, gradients accumulated "
+                               "and all-reduced" % (H, W),
+                   "name": "mvp_full", "cameras": NCAM, "cameras_this_rank": V, "primitives": K, "template": list(T),
+                   "l2": "template (2.1 GB) larger than L2", "parallelism": "camera-shard x%d (19/18 per GPU at 8)" % world,
+                   "collectives": None if world == 1 else "NCCL broadcast of the template, all-reduce of its gradient (2.1 GB each)",
+                   "alpha_scale": args.mvp_density},
+        "e2e": {"value": mp * steps / (ms_e2e / 1e3), "unit": "MP/s", "h2d_bytes_per_step": tpl_bytes,
+                "d2h_bytes_per_step": NCAM * H * W * 4 * 4, "ms_per_step": ms_e2e / steps,
+                "how": "the frame owner's template from pinned host memory (then broadcast), every camera's rgba image back to "
+                       "pinned host memory; gradients stay on the device"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "reference_extension": ext,
+    }
     print(json.dumps(line))
 
 
@@ -740,8 +1204,10 @@ def run_reference(args):
     CPU implementation of the path is the oracle port, timed with all host threads.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warmup = 1 if args.warmup > 0 else 0
+    # honours --steps / --warmup (same counts as our arm asks for); one CPU step of this workload takes ~1 s on the
+    # host cores of a B200 box, so the default (no flags) is a bounded 5 + 3
+    steps = 5 if args.steps is None else max(1, args.steps)
+    warmup = 3 if args.warmup is None else max(0, args.warmup)
     cpu = cpu_baseline(args, steps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": "rendered megapixels/sec (fwd+bwd) RGCA head 300k Gaussians",
@@ -759,7 +1225,20 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ decoder (rows R1 + R2)
-def run_decoder(args):
+def decoder_summary(args, dev):
+    """The `decoder` sub-object of the headline line (rows R1 + R2 where the driver can see them): big tower on the tensor
+    cores (graph replay), last layer alone, heads, training fwd+bwd of the big tower, decode+shade+render frame."""
+    r = run_decoder(args, quick=True, dev=dev)["decoder"]
+    keep = ("tower_vnocond_ms_tc_graph", "tower_vnocond_ms_simt", "last_layer_ms_simt", "last_layer_alg_GBs_simt",
+            "last_layer_ms_tc16", "heads_ms", "heads_alg_GBs", "full_decoder_ms_tc_graph", "tower_vnocond_fwd_bwd_ms_simt",
+            "frame_decode_shade_render_fwd_ms_graph", "frame_MP_per_s_fwd_graph", "tc_vs_simt_rel_err")
+    out = {k: r[k] for k in keep if k in r}
+    out["what"] = ("RGCA PrimDecoder at native size (1024^2 Gaussians, 162.8 M parameters, random init), B = 1; ms per call, "
+                   "CUDA events, L2 flushed; last_layer = 16->125 @1024^2 on 1.07 GB of mandatory traffic")
+    return out
+
+
+def run_decoder(args, quick=False, dev=None):
     """Inference forward of the RGCA PrimDecoder at native size (B=1, 1024x1024 Gaussians, 162.8 M parameters,
     random init): the two 7-layer towers on the tensor cores (tcgen05 + TMA) and on the SIMT kernels, then the fused heads
     kernel and the SG shade.  Reports ms per part and the last layer's achieved HBM bandwidth on its mandatory bytes
@@ -769,8 +1248,9 @@ def run_decoder(args):
     from goliath_b200.rgca import PrimDecoder
     from goliath_b200.rgca_heads import gaussian_heads, shade_and_compose
 
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
+    if dev is None:
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
     S = 1024
 
     class Geo:
@@ -783,6 +1263,7 @@ def run_decoder(args):
     pos = shell.t().reshape(1, 3, S, S).contiguous().to(dev)
     nml = torch.nn.functional.normalize(shell, dim=1).t().reshape(1, 3, S, S).contiguous().to(dev)
     dec = PrimDecoder(256, Geo(pos, nml), 255 * torch.rand(3, S, S, generator=gen), slabsize=S).to(dev)
+    dec.eval()  # inference timings: no training-mode random back light (rgca.py:590-618)
     with torch.no_grad():
         for n_, p in dec.named_parameters():
             if n_.endswith("bias"):
@@ -881,8 +1362,12 @@ def run_decoder(args):
             p_.grad = None
 
     res["tower_vnocond_fwd_bwd_ms_simt"] = timeit(tower_train, reps=3, warm=1)
-    print(json.dumps({"decoder": res, "config": {"slabsize": S, "params_M": sum(p.numel() for p in dec.parameters()) / 1e6,
-                                                 "lights": args.lights}}))
+    out = {"decoder": res, "config": {"slabsize": S, "params_M": sum(p.numel() for p in dec.parameters()) / 1e6,
+                                      "lights": args.lights}}
+    if quick:
+        return out
+    print(json.dumps(out))
+    return out
 
 
 def run_decoder_library(args):
@@ -1039,5 +1524,9 @@ if __name__ == "__main__":
         run_ext_compare(a)
     elif a.impl == "reference":
         run_reference(a)
+    elif a.config == "hand_mvp":
+        run_hand_mvp(a)
+    elif a.config == "mvp_full":
+        run_mvp_full(a)
     else:
         run_ours(a)

@@ -38,6 +38,8 @@ SIGNATURES = {
     "gb_map_gaussian_to_intersects_dn": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "gb_sort_intersects_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "gb_get_tile_bin_edges_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "gb_get_rank_sort_mode": (_i, []),
+    "gb_set_rank_sort_mode": (None, [_i]),
     "gb_bin_tiles_supported": (_i, [_i]),
     "gb_bin_tiles_workspace_bytes": (_sz, [_i, _i, _i64]),
     "gb_bin_tiles_pack": (_i, [_i] + [_vp] * 7 + [_i, _i, _i, _i64] + [_vp, _vp, _i] + [_vp] * 5 + [_vp]),
@@ -45,6 +47,7 @@ SIGNATURES = {
     "gb_tile_schedule": (_i, [_i, _vp, _vp, _vp]),
     "gb_rasterize_sched_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_sched_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
+    "gb_records_set_colors": (_i, [_i64] + [_vp] * 5 + [_vp]),
     "gb_splat_grad_unpack": (_i, [_i] + [_vp] * 8 + [_vp]),
     "gb_get_blend_mode": (_i, []),
     "gb_set_blend_mode": (None, [_i]),

@@ -34,6 +34,9 @@
 //
 // Integer/byte work with a BIT-EXACT contract: gids_sorted, tile_bins and records are identical to the
 // key-sort path's (tests/test_splat_gpu.py::test_bin_tiles_matches_key_sort).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "splat_record.cuh"
 
@@ -107,10 +110,13 @@ __global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const fl
                                                                  int block_width, int smem_tiles,
                                                                  unsigned* __restrict__ keys,
                                                                  unsigned* __restrict__ hist0 /* [ctas][256] */,
-                                                                 int* __restrict__ tile_counts) {
+                                                                 int* __restrict__ tile_counts,
+                                                                 unsigned* __restrict__ key_bits /* [2], zeroed */) {
   constexpr int kItems = kTileKeys / kGaussBlock;
   extern __shared__ int s_cnt[];
   __shared__ unsigned s_hist[kRadix];
+  __shared__ unsigned s_or, s_orc;
+  if (threadIdx.x == 0) s_or = s_orc = 0u;
   if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
   for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) s_cnt[t] = 0;
   const int base = blockIdx.x * kTileKeys;
@@ -124,6 +130,17 @@ __global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const fl
     k[j] = in ? __float_as_uint(depths[i]) : 0u;
     r[j] = in ? radii[i] : 0;
     c[j] = in ? xys[i] : make_float2(0.f, 0.f);
+  }
+  {  // OR of the VISIBLE keys and of their complements: a bit set in both differs between two visible keys, and the
+     // rank sort only has to order those bits (culled Gaussians never reach a tile, where their rank lands is irrelevant)
+    unsigned o = 0u, oc = 0u;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+      if (r[j] > 0) { o |= k[j]; oc |= ~k[j]; }
+    o = __reduce_or_sync(0xffffffffu, o);
+    oc = __reduce_or_sync(0xffffffffu, oc);
+    __syncthreads();  // s_or / s_orc initialised
+    if ((threadIdx.x & 31) == 0 && (o | oc)) { atomicOr(&s_or, o); atomicOr(&s_orc, oc); }
   }
   __syncthreads();
 #pragma unroll
@@ -143,6 +160,7 @@ __global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const fl
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0 && (s_or | s_orc)) { atomicOr(key_bits, s_or); atomicOr(key_bits + 1, s_orc); }
   if (threadIdx.x < kRadix) hist0[(size_t)blockIdx.x * kRadix + threadIdx.x] = s_hist[threadIdx.x];
   for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) {
     const int cnt = s_cnt[t];
@@ -265,6 +283,149 @@ __global__ void __launch_bounds__(kRankBlock) rank_scatter_kernel(
       if (hist_next) atomicAdd(&hist_next[(size_t)(dst / kTile) * kRadix + ((k[j] >> (shift + 8)) & 0xffu)], 1u);
       if (rank_of) rank_of[v[j]] = (int)dst;
     }
+  }
+}
+
+
+// ------------------------------------------------------------------ 2b. the whole rank sort as ONE cooperative kernel
+// Round-1 launch list (profiles/r01_launches_pipe.txt): 4 x 17-19 us for the four radix passes over 300k keys, each
+// a chain of L2 round trips at ~9 % issue utilisation with a kernel boundary in between.  Here the passes run inside
+// one cooperative launch (grid <= SM count, every CTA co-resident), separated by a grid barrier (an L2 counter), and
+// only the low bits in which the keys actually differ are sorted: depths of a head at ~1 m share their sign,
+// exponent and leading mantissa bits, so 3 passes (or 2) replace 4 and no launch gap remains.  Data written by other
+// CTAs inside the kernel (keys / ids ping-pong, histogram tables) is read with ld.global.cg (L2), never through the
+// non-coherent path.  Same stable LSD ranking as rank_scatter_kernel, same outputs: rank_to_gid and rank_of.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();  // release this CTA's writes
+    atomicAdd(counter, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int kItems>
+__global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
+    int n, int tiles, unsigned* keys_a, unsigned* keys_b, int* vals_a, int* vals_b, unsigned* hist /* [4][tiles][256] */,
+    const unsigned* key_bits, unsigned* barrier /* zeroed */, int* __restrict__ rank_to_gid, int* __restrict__ rank_of) {
+  constexpr int kWarps = kRankBlock / 32;
+  constexpr int kTile = kRankBlock * kItems;
+  __shared__ unsigned s_whist[kWarps][kRadix];
+  __shared__ int s_scan[33];
+  __shared__ uint4 s_part[2][4][kRadix / 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned diff = key_bits[0] & key_bits[1];  // written by depth_keys_kernel (previous launch): plain loads
+  const int bits = diff ? 32 - __clz(diff) : 0;
+  const int passes = (bits + 7) >> 3;  // 0 .. 4
+  unsigned bar_target = 0;
+  const size_t hs = (size_t)tiles * kRadix;
+
+  if (passes == 0) {  // every key equal: the order is the id order
+    for (int i = blockIdx.x * kRankBlock + threadIdx.x; i < n; i += gridDim.x * kRankBlock) {
+      rank_to_gid[i] = i;
+      rank_of[i] = i;
+    }
+    return;
+  }
+  for (int p = 0; p < passes; ++p) {
+    const bool last = (p == passes - 1);
+    const int shift = 8 * p;
+    const unsigned* kin = (p & 1) ? keys_b : keys_a;
+    unsigned* kout = (p & 1) ? keys_a : keys_b;
+    const int* vin = (p == 0) ? nullptr : ((p & 1) ? vals_b : vals_a);
+    int* vout = last ? rank_to_gid : ((p & 1) ? vals_a : vals_b);
+    const unsigned* hist_cur = hist + (size_t)p * hs;
+    unsigned* hist_next = last ? nullptr : hist + (size_t)(p + 1) * hs;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int warp_base = tile * kTile + warp * (32 * kItems);
+      unsigned k[kItems];
+      int v[kItems];
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        const int i = warp_base + j * 32 + lane;
+        k[j] = (i < n) ? __ldcg(kin + i) : 0xffffffffu;
+        v[j] = (i < n) ? (vin ? __ldcg(vin + i) : i) : 0;
+      }
+      {  // column sums of the tile-major table (see rank_scatter_kernel)
+        const int g = threadIdx.x >> 6, c4 = threadIdx.x & 63;
+        const uint4* tab = reinterpret_cast<const uint4*>(hist_cur);
+        uint4 tot = make_uint4(0u, 0u, 0u, 0u), bef = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 8
+        for (int b = g; b < tiles; b += 4) {
+          const uint4 h = __ldcg(tab + (size_t)b * (kRadix / 4) + c4);
+          tot.x += h.x; tot.y += h.y; tot.z += h.z; tot.w += h.w;
+          if (b < tile) { bef.x += h.x; bef.y += h.y; bef.z += h.z; bef.w += h.w; }
+        }
+        s_part[0][g][c4] = tot;
+        s_part[1][g][c4] = bef;
+      }
+      __syncthreads();
+      unsigned before = 0, total = 0;
+      {
+        const unsigned* pt = reinterpret_cast<const unsigned*>(&s_part[0][0][0]);
+        const unsigned* pb = reinterpret_cast<const unsigned*>(&s_part[1][0][0]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          total += pt[g * kRadix + threadIdx.x];
+          before += pb[g * kRadix + threadIdx.x];
+        }
+      }
+      int unused;
+      const unsigned digit_base = (unsigned)block_exclusive_scan((int)total, s_scan, unused);
+      const unsigned my_base = digit_base + before;
+      for (int d = lane; d < kRadix; d += 32) s_whist[warp][d] = 0;
+      __syncwarp();
+      unsigned rank[kItems];
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        const int i = warp_base + j * 32 + lane;
+        const bool valid = i < n;
+        const unsigned dgt = (k[j] >> shift) & 0xffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? dgt : 0x100u);
+        const unsigned lower = peers & ((1u << lane) - 1u);
+        unsigned prev = 0;
+        if (valid) prev = s_whist[warp][dgt];
+        __syncwarp();
+        rank[j] = prev + __popc(lower);
+        if (valid && lower == 0u) s_whist[warp][dgt] = prev + __popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      {
+        const int d = threadIdx.x;
+        unsigned run = my_base;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const unsigned c = s_whist[w][d];
+          s_whist[w][d] = run;
+          run += c;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        const int i = warp_base + j * 32 + lane;
+        if (i < n) {
+          const unsigned dgt = (k[j] >> shift) & 0xffu;
+          const unsigned dst = s_whist[warp][dgt] + rank[j];
+          if (!last) {
+            kout[dst] = k[j];
+            atomicAdd(&hist_next[(size_t)(dst / kTile) * kRadix + ((k[j] >> (shift + 8)) & 0xffu)], 1u);
+          } else {
+            rank_of[v[j]] = (int)dst;
+          }
+          vout[dst] = v[j];
+        }
+      }
+      __syncthreads();  // shared tables are reused by the next tile of this CTA
+    }
+    if (!last) grid_barrier(barrier, bar_target);
   }
 }
 
@@ -428,7 +589,8 @@ __global__ void __launch_bounds__(kSortThreads, 3) tile_sort_pack_kernel(
 }
 
 struct Layout {
-  size_t counts, hist, zero_bytes, cursor, keys_a, keys_b, vals_a, vals_b, rank_of, rec_by_rank, tile_ranks, total;
+  size_t counts, hist, sync, zero_bytes, cursor, keys_a, keys_b, vals_a, vals_b, rank_to_gid, rank_of, rec_by_rank,
+      tile_ranks, total;
 };
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 inline Layout make_layout(int G, int T, int64_t cap) {
@@ -439,12 +601,14 @@ inline Layout make_layout(int G, int T, int64_t cap) {
   size_t o = 0;
   l.counts = o; o += align256((size_t)T * 4);
   l.hist = o;   o += align256(ctas * kRadix * 4 * kRankPasses);
-  l.zero_bytes = o;                       // [counts | hist] are zeroed with one memset per call
+  l.sync = o;   o += 256;                 // [0..1]: OR of the visible keys / of their complements, [2]: grid-barrier counter
+  l.zero_bytes = o;                       // [counts | hist | sync] are zeroed with one memset per call
   l.cursor = o; o += align256((size_t)T * 4);
   l.keys_a = o; o += g4;
   l.keys_b = o; o += g4;
   l.vals_a = o; o += g4;
   l.vals_b = o; o += g4;
+  l.rank_to_gid = o; o += g4;
   l.rank_of = o; o += g4;
   l.rec_by_rank = o; o += align256((size_t)g1 * 48);
   l.tile_ranks = o; o += align256((size_t)(cap > 0 ? cap : 1) * 4);
@@ -452,13 +616,44 @@ inline Layout make_layout(int G, int T, int64_t cap) {
   return l;
 }
 
+// 1: the four radix passes as separate launches (round 1), 0: one cooperative kernel (default).  GOLIATH_B200_RANKSORT=passes|coop
+int g_rank_sort_mode = -1;
+int rank_sort_mode() {
+  if (g_rank_sort_mode < 0) {
+    const char* e = getenv("GOLIATH_B200_RANKSORT");
+    g_rank_sort_mode = (e && strcmp(e, "passes") == 0) ? 1 : 0;
+  }
+  return g_rank_sort_mode;
+}
+int sm_count() {
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return gb::kNumSMs;
+  if (!n[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = gb::kNumSMs;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
 template <int kItems>
-void launch_rank_sort(int G, int ctas, const float* xys, const float* depths, const int32_t* radii, int tbx, int tby,
-                      int block_width, int smem_tiles, unsigned* keys_a, unsigned* keys_b, int* vals_a, int* vals_b,
-                      unsigned* hist, int* counts, int* rank_of, cudaStream_t s) {
+int launch_rank_sort(int G, int ctas, const float* xys, const float* depths, const int32_t* radii, int tbx, int tby,
+                     int block_width, int smem_tiles, unsigned* keys_a, unsigned* keys_b, int* vals_a, int* vals_b,
+                     unsigned* hist, int* counts, unsigned* sync, int* rank_to_gid, int* rank_of, cudaStream_t s) {
   const size_t hs = (size_t)ctas * kRadix;
   depth_keys_kernel<kRankBlock * kItems><<<ctas, kGaussBlock, (size_t)smem_tiles * 4, s>>>(
-      G, (const float2*)xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, hist, counts);
+      G, (const float2*)xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, hist, counts, sync);
+  if (rank_sort_mode() == 0) {
+    int n = G, tiles = ctas;
+    const unsigned* key_bits = sync;
+    unsigned* barrier = sync + 2;
+    void* args[] = {&n, &tiles, &keys_a, &keys_b, &vals_a, &vals_b, &hist, &key_bits, &barrier, &rank_to_gid, &rank_of};
+    const int grid = ctas < sm_count() ? ctas : sm_count();  // one CTA per SM at most: co-resident by construction
+    GB_CUDA(cudaLaunchCooperativeKernel((const void*)rank_sort_coop_kernel<kItems>, dim3(grid), dim3(kRankBlock), args, 0, s));
+    gb::count_launches(2);
+    return 0;
+  }
   // pass 0: a -> b (ids = identity), 1: b -> a, 2: a -> b, 3: b -> a (ids only) => rank_to_gid = vals_a
   rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_a, nullptr, keys_b, vals_b, 0, ctas, hist, hist + hs,
                                                           nullptr);
@@ -466,8 +661,10 @@ void launch_rank_sort(int G, int ctas, const float* xys, const float* depths, co
                                                           hist + 2 * hs, nullptr);
   rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_a, vals_a, keys_b, vals_b, 16, ctas, hist + 2 * hs,
                                                           hist + 3 * hs, nullptr);
-  rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_b, vals_b, nullptr, vals_a, 24, ctas, hist + 3 * hs,
+  rank_scatter_kernel<kItems><<<ctas, kRankBlock, 0, s>>>(G, keys_b, vals_b, nullptr, rank_to_gid, 24, ctas, hist + 3 * hs,
                                                           nullptr, rank_of);
+  gb::count_launches(5);
+  return 0;
 }
 
 // opt in to the large dynamic shared-memory window, once per device and kernel
@@ -483,6 +680,11 @@ int opt_in_smem(K kernel, bool* done) {
 }
 
 }  // namespace
+
+// Depth-rank sort of gb_bin_tiles_pack: 0 = one cooperative kernel over the varying key bits (default), 1 = four
+// radix passes as separate launches (round 1).  Identical outputs; the switch exists for A/B timing and the tests.
+GB_API int gb_get_rank_sort_mode(void) { return rank_sort_mode(); }
+GB_API void gb_set_rank_sort_mode(int mode) { g_rank_sort_mode = mode ? 1 : 0; }
 
 // 1 when gb_bin_tiles_pack supports G Gaussians (one tile's rank bitmap must fit in shared memory)
 GB_API int gb_bin_tiles_supported(int G) { return G >= 1 && ((size_t)gb::cdiv(G, 32) * 4 <= (size_t)kMaxBitmapBytes); }
@@ -515,6 +717,8 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   unsigned* keys_b = (unsigned*)(ws + l.keys_b);
   int* vals_a = (int*)(ws + l.vals_a);
   int* vals_b = (int*)(ws + l.vals_b);
+  int* rank_to_gid = (int*)(ws + l.rank_to_gid);
+  unsigned* sync = (unsigned*)(ws + l.sync);
   int* rank_of = (int*)(ws + l.rank_of);
   float4* rec_by_rank = (float4*)(ws + l.rec_by_rank);
   int* tile_ranks = (int*)(ws + l.tile_ranks);
@@ -531,14 +735,14 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   }
 
   GB_CUDA(cudaMemsetAsync(ws, 0, l.zero_bytes, s));
-  if (items == 8)
-    launch_rank_sort<8>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b, vals_a, vals_b,
-                        hist, counts, rank_of, s);
-  else
-    launch_rank_sort<16>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b, vals_a, vals_b,
-                         hist, counts, rank_of, s);
+  const int es = (items == 8)
+                     ? launch_rank_sort<8>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b,
+                                           vals_a, vals_b, hist, counts, sync, rank_to_gid, rank_of, s)
+                     : launch_rank_sort<16>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b,
+                                            vals_a, vals_b, hist, counts, sync, rank_to_gid, rank_of, s);
+  if (es) return es;
   tile_scan_kernel<<<1, 1024, 0, s>>>(T, (long long)cap, counts, (int2*)tile_bins, cursor, n_out, overflow);
-  gb::count_launches(6);
+  gb::count_launches(1);
   GB_CHECK_LAUNCH();
   const int e = tile_sched ? gb_tile_schedule(T, tile_bins, tile_order, stream)
                            : gb_tile_order(T, tile_bins, tile_order, stream);
@@ -554,7 +758,7 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
     if (e2) return e2;
   }
   tile_sort_pack_kernel<<<T, kSortThreads, smem, s>>>(words, chunk, tile_order, (const int2*)tile_bins, tile_ranks,
-                                                      vals_a, rec_by_rank, gids_sorted, (float4*)records);
+                                                      rank_to_gid, rec_by_rank, gids_sorted, (float4*)records);
   gb::count_launches(2);
   GB_CHECK_LAUNCH();
   return 0;

@@ -72,6 +72,20 @@ __global__ void __launch_bounds__(256) pack_records_fused_kernel(long long n_cap
   gb::pack_record_fused(gids_sorted[i], xys, conics, colors3, depths, opacity, comp, rec + 3 * i);
 }
 
+// OLAT / multi-condition renders: geometry, projection and tile lists of a view are shared by
+// every lighting condition, only the colours change.  Rewrites the colour quarter (rgb + depth) of the packed records
+// in place from a new [G,3] colour table: 16 B per intersection instead of a full re-pack.
+__global__ void __launch_bounds__(256) records_set_colors_kernel(long long n_cap, const int* __restrict__ n_dev,
+                                                                 const int* __restrict__ gids_sorted,
+                                                                 const float* __restrict__ colors3,
+                                                                 const float* __restrict__ depths, float4* __restrict__ rec) {
+  const long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = gids_sorted[i];
+  rec[3 * i + 2] = make_float4(colors3[3 * g], colors3[3 * g + 1], colors3[3 * g + 2], depths[g]);
+}
+
 // Backward glue of the fused render: split the blend's per-Gaussian gradients back into the tensors the projection
 // backward and the caller expect (product rule of opacity * compensation, depth = 4th colour channel).
 __global__ void __launch_bounds__(256) splat_grad_unpack_kernel(int G, const float4* __restrict__ v_colors4,
@@ -451,6 +465,18 @@ GB_API int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int
                                     const float* conics, const float* colors3, const float* depths,
                                     const float* opacity, const float* compensation, float* records, void* stream) {
   return pack_fused_impl(cap, n_dev, gids_sorted, xys, conics, colors3, depths, opacity, compensation, records, stream);
+}
+
+// Colour quarter of the fused-render records from another colour table (same geometry): records[i].c = (colors3[g], depths[g]).
+// n_dev (device int32, may be NULL) = number of valid records; cap sizes the launch.
+GB_API int gb_records_set_colors(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* colors3,
+                                 const float* depths, float* records, void* stream) {
+  if (cap <= 0) return 0;
+  records_set_colors_kernel<<<(unsigned)gb::cdiv64(cap, 256), 256, 0, (cudaStream_t)stream>>>(
+      cap, n_dev, gids_sorted, colors3, depths, (float4*)records);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
 }
 
 // Backward glue of the fused render (all outputs overwritten): v_colors3 [G,3], v_opacity [G], v_comp [G], v_depth [G].

@@ -115,6 +115,13 @@ int gb_pack_records_fused(int64_t n, const int32_t* gids_sorted, const float* xy
                           const float* colors3, const float* depths, const float* opacity, const float* compensation,
                           float* records, void* stream);
 
+/* multi-condition (OLAT) renders: the lighting conditions of a view share geometry, projection and tile lists
+ * (ca_code/utils/light_decorator.py:167 feeds the same avatar under one light at a time); this rewrites only the colour
+ * quarter of the fused-render records in place: records[i].c = (colors3[gids_sorted[i]], depths[gids_sorted[i]]).
+ * n_dev: device int32 count of valid records (may be NULL: cap records). */
+int gb_records_set_colors(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* colors3,
+                          const float* depths, float* records, void* stream);
+
 /* backward glue of the fused render: split v_colors4 / v_opacity_eff into v_colors3, v_opacity, v_comp, v_depth */
 int gb_splat_grad_unpack(int G, const float* v_colors4, const float* v_opac_eff, const float* opacity,
                          const float* compensation, float* v_colors3, float* v_opacity, float* v_comp, float* v_depth,
@@ -134,6 +141,11 @@ int gb_get_tile_bin_edges_dn(int64_t cap, const int32_t* n_dev, const int64_t* i
 int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* xys,
                              const float* conics, const float* colors3, const float* depths, const float* opacity,
                              const float* compensation, float* records, void* stream);
+
+/* depth-rank sort inside gb_bin_tiles_pack: 0 = one cooperative kernel sorting only the key bits that vary (default),
+ * 1 = four radix passes as separate launches.  Identical outputs (A/B timing, tests).  GOLIATH_B200_RANKSORT=coop|passes. */
+int gb_get_rank_sort_mode(void);
+void gb_set_rank_sort_mode(int mode);
 
 /* Bucket binning of the fused render (csrc/splat_bin_tiles.cu): replaces, for the fused path, the whole of gsplat
  * 0.1.11 bin_and_sort_gaussians (compute_cumulative_intersects, map_gaussian_to_intersects, torch.sort,

@@ -88,3 +88,52 @@ def test_view_partition_of_the_baseline_configs():
     assert sorted(len(p) for p in parts) == [18, 18, 19, 19, 19, 19, 19, 19]
     assert sorted(sum(parts, [])) == list(range(150))
     assert views_of_rank(0, 1, 5) == [0, 1, 2, 3, 4] and views_of_rank(3, 4, 2) == []
+
+
+def _exchange_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from goliath_b200.dist import FrameExchange
+
+    n = 1000
+    ex = FrameExchange(n, "cpu", owner=0)
+    frames = [torch.full((n,), float(i + 1)) for i in range(3)] if rank == 0 else [None] * 3  # only the owner has the tables
+    static_in = torch.empty(n)
+    seen, sums = [], []
+    ex.post_input(0, frames[0])
+    for i in range(3):
+        ex.take_input(i, static_in)
+        if i + 1 < 3:
+            ex.post_input(i + 1, frames[i + 1])
+        seen.append(float(static_in[0]))
+        ex.post_grad(i, static_in * (rank + 1))        # rank r contributes (r+1) * table
+        sums.append(float(ex.grad(i)[0]))
+    ex.finish()
+    bad = None
+    if rank != 0:
+        try:
+            FrameExchange(n, "cpu", owner=1).post_input(0, None)
+        except RuntimeError as e:
+            bad = str(e)
+    q.put((rank, seen, sums, ex.bytes_h2d, bad))
+    dist.destroy_process_group()
+
+
+def test_frame_exchange_owner_only_source_and_reduced_grads():
+    """goliath_b200.dist.FrameExchange (the product API bench.py drives): non-owner ranks never provide a table, every
+    rank receives the owner's, the gradient of every frame is the sum over the ranks."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, seen, sums, h2d, bad in res:
+        assert seen == [1.0, 2.0, 3.0]
+        assert sums == [3.0, 6.0, 9.0]                    # (1 + 2) * table
+        assert h2d == (3 * 1000 * 4 if rank == 0 else 0)  # only the owner copies host bytes in
+    assert res[1][4] is not None and "owner" in res[1][4]

@@ -516,9 +516,22 @@ def test_render_views_fused_matches_reference_sequence(cuda):
         assert_close(g1[k], g0[k], rtol=1e-4, atol=2e-5 * np.abs(g0[k]).max(), frac=0.999, what="grad " + k)
 
 
+@pytest.fixture(params=["coop", "passes"])
+def rank_sort(request):
+    """depth-rank sort of the bucket binning: one cooperative kernel over the varying key bits (default) or the four
+    separate radix passes of round 1"""
+    from goliath_b200 import _lib
+
+    L = _lib.lib()
+    before = L.gb_get_rank_sort_mode()
+    L.gb_set_rank_sort_mode({"coop": 0, "passes": 1}[request.param])
+    yield request.param
+    L.gb_set_rank_sort_mode(before)
+
+
 @pytest.mark.parametrize("case", ["dense96", "ragged", "bw8", "ties", "tiny_prims", "one_cta", "two_ctas", "big",
-                                  "many_tiles", "too_many_tiles", "sixteen_per_thread"])
-def test_bin_tiles_matches_key_sort(cuda, case):
+                                  "many_tiles", "too_many_tiles", "sixteen_per_thread", "flat_depth", "wide_depth"])
+def test_bin_tiles_matches_key_sort(cuda, case, rank_sort):
     """The bucket binning of the fused render (depth ranks + per-tile bitmap sort, csrc/splat_bin_tiles.cu) returns
     bit for bit the bins, sorted Gaussian ids and blend records of the key-sort path (csrc/splat_bin.cu + pack)."""
     from goliath_b200 import _lib
@@ -531,9 +544,17 @@ def test_bin_tiles_matches_key_sort(cuda, case):
         "many_tiles": (dict(G=30_000, img_h=768, img_w=1024, seed=17), 8, 2.0),        # 12288 tiles: opt-in smem
         "too_many_tiles": (dict(G=20_000, img_h=600, img_w=640, seed=19), 4, 1.5),     # 24000 tiles: global atomics
         "sixteen_per_thread": (dict(G=400_000, img_h=256, img_w=192, seed=23), 16, 1.5),
+        "flat_depth": (dict(G=6000, img_h=96, img_w=80, seed=31, cam=0), 16, 10.0),   # every depth key identical: 0 passes
+        "wide_depth": (dict(G=9000, img_h=96, img_w=80, seed=37, cam=0), 16, 10.0),   # depths over 12 octaves: 4 passes
     }
     kw, bw, mult = CASES[case] if case in CASES else extra[case]
     s = small_scene(**kw)
+    if case == "flat_depth":    # camera 0 looks down the world z axis: depth = 1000 - z
+        s["means3d"][:, 2] = 0.0
+    if case == "wide_depth":
+        rng = np.random.default_rng(37)
+        s["means3d"][:, 2] = (1000.0 - np.exp2(rng.uniform(-2.0, 10.0, size=len(s["means3d"])))).astype(np.float32)
+        s["means3d"][:, :2] *= 0.05
     H, W = s["img_h"], s["img_w"]
     xys, depths, radii, conics, comp, nth, cov3d = _project_gpu(s, cuda, bw, mult)
     t = _dev(s, cuda)
