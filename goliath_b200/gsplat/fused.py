@@ -51,6 +51,8 @@ class _RenderFused(Function):
             _lib.check_input(t, n)
         means3d, scales, quats, opacity, colors, viewmat, background = ins
         G = means3d.size(0)
+        if G == 0:
+            capacity = None  # nothing to bin: the exact path below returns the background (no device-side count to read)
         dev = means3d.device
         L = _lib.lib()
         f32 = dict(device=dev, dtype=torch.float32)

@@ -30,10 +30,15 @@ def project_gaussians(
     cov3d [G,6]).  viewmat: row-major world->camera, first 12 floats are used ([3,4] or [4,4])."""
     assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
     assert (quats.norm(dim=-1) - 1 < 1e-6).all(), "quats must be normalized"
-    return _ProjectGaussians.apply(
+    outs = _ProjectGaussians.apply(
         means3d.contiguous(), scales.contiguous(), glob_scale, quats.contiguous(), viewmat.contiguous(),
         fx, fy, cx, cy, img_height, img_width, block_width, clip_thresh,
     )
+    # one token per call: rasterize_gaussians reuses a binning only for the tensors of the same projection (rasterize.py)
+    token = object()
+    for t in (outs[0], outs[1], outs[2], outs[5]):  # xys, depths, radii, num_tiles_hit
+        t._gb_bin_token = token
+    return outs
 
 
 class _ProjectGaussians(Function):

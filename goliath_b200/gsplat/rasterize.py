@@ -4,8 +4,9 @@ Call sites in the reference: ca_code/utils/render_gsplat.py:65-78 (rgb) and :90-
 
 Two things differ from a literal re-implementation, neither visible in the results:
   * the reference calls this function twice per view with the SAME (xys, depths, radii, num_tiles_hit) and
-    re-bins / re-sorts each time; here the binning of the last call is kept per device and reused when the very
-    same tensors (same storage, same version counter) come back;
+    re-bins / re-sorts each time; here the binning of the last call is kept per device and reused when the four
+    tensors are the ones ONE `project_gaussians` call returned (they carry that call's token), unmodified since
+    (version counters) and used on the same stream; tensors from anywhere else are always re-binned;
   * with block_width == 16 the blend runs on packed per-intersection records streamed by bulk async copies
     (csrc/splat_blend_packed.cu); other block widths use the generic kernel (csrc/splat_blend.cu).
 """
@@ -25,11 +26,17 @@ def _bin_cached(xys, depths, radii, num_tiles_hit, img_height, img_width, block_
     """(num_intersects, gaussian_ids_sorted, tile_bins, tile_order) — recomputed unless the inputs are the tensors
     of the previous call on this device, unmodified."""
     dev = xys.device
-    key = (dev.index, img_height, img_width, block_width,
-           tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (xys, depths, radii, num_tiles_hit)))
-    hit = _BIN_CACHE.get(dev.index)
-    if hit is not None and hit[0] == key:
-        return hit[2]
+    # reuse only what a single project_gaussians call produced: raw-pointer writers (this library's own kernels, graph
+    # replays into static buffers) do not bump torch's version counter, so foreign tensors are never trusted
+    tokens = [getattr(t, "_gb_bin_token", None) for t in (xys, depths, radii, num_tiles_hit)]
+    token = tokens[0] if tokens[0] is not None and all(t is tokens[0] for t in tokens) else None
+    key = None
+    if token is not None:
+        key = (dev.index, img_height, img_width, block_width, id(token), torch.cuda.current_stream(dev).cuda_stream,
+               tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (xys, depths, radii, num_tiles_hit)))
+        hit = _BIN_CACHE.get(dev.index)
+        if hit is not None and hit[0] == key and hit[1][4] is token:
+            return hit[2]
     tile_bounds = _tile_bounds(img_height, img_width, block_width)
     num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
     if num_intersects < 1:
@@ -45,8 +52,11 @@ def _bin_cached(xys, depths, radii, num_tiles_hit, img_height, img_width, block_
                 _lib.check(_lib.lib().gb_tile_order(T, _lib.ptr(tile_bins), _lib.ptr(tile_order),
                                                     _lib.stream_ptr(dev)), "tile_order")
         res = (num_intersects, gaussian_ids_sorted, tile_bins, tile_order)
-    # the strong references keep the storages alive, so an equal data_ptr really is the same allocation
-    _BIN_CACHE[dev.index] = (key, (xys, depths, radii, num_tiles_hit), res)
+    if key is not None:
+        # the strong references keep the storages (and the token) alive, so equal pointers / ids are the same objects
+        _BIN_CACHE[dev.index] = (key, (xys, depths, radii, num_tiles_hit, token), res)
+    else:
+        _BIN_CACHE.pop(dev.index, None)  # do not pin the previous call's tensors once a foreign call came through
     return res
 
 

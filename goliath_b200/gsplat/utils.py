@@ -9,14 +9,15 @@ from .. import _lib
 
 _WS = {}
 _WS_RETIRED = {}  # outgrown buffers stay allocated: a captured CUDA graph may still hold their addresses
-_DEBUG_ASSUME_N = [None]
 
 
 def _workspace(dev, nbytes: int) -> Tensor:
-    """Grow-only per-device scratch buffer (the C ABI never allocates).  A buffer that is outgrown is retired, not
-    freed — kernels already captured in a CUDA graph keep pointing into it (sizes grow by at least 25 % per step, so the
-    retired buffers together stay below four times the live one)."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (device, stream) — the C ABI never allocates.  Renders issued on different streams
+    get different buffers (a shared one would race); work on one stream is ordered, so sharing inside a stream is safe.
+    A buffer that is outgrown is retired, not freed — kernels already captured in a CUDA graph keep pointing into it
+    (sizes grow by at least 25 % per step, so the retired buffers together stay below four times the live one)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (dev.type, idx, torch.cuda.current_stream(idx).cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
@@ -45,8 +46,6 @@ def compute_cumulative_intersects(num_tiles_hit: Tensor) -> Tuple[int, Tensor]:
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().gb_cumsum_i32(n, _lib.ptr(num_tiles_hit), _lib.ptr(cum), _lib.ptr(ws),
                                             _lib.stream_ptr(dev)), "cumsum")
-    if _DEBUG_ASSUME_N[0] is not None:  # profiling experiment only: how much does the host sync cost?
-        return _DEBUG_ASSUME_N[0], cum
     num_intersects = int(cum[-1].item())  # same host sync as the reference (gsplat utils: cum_tiles_hit[-1].item())
     return num_intersects, cum
 

@@ -179,18 +179,21 @@ def slabs_to_primrgba(primrgb, primalpha, primsize: Tuple[int, int, int] = (16, 
     n_prims = (primrgb.shape[-1] // primsize[0]) * (primrgb.shape[-2] // primsize[1])
     slot, n_out = None, n_prims
     if valid_prims is not None:
-        # valid_prims is a fixed buffer of the model (hand_mvp.py:153-160): its slot table is built once
+        # valid_prims is a fixed buffer of the model (hand_mvp.py:153-160): its slot table is built once.  The entry
+        # holds the mask itself: a freed mask whose address is reused by another one must not hit
         key = (valid_prims.data_ptr(), valid_prims._version, primrgb.device.index)
         hit = _SLOTS.get(key)
+        if hit is not None and hit[2] is not valid_prims:
+            hit = None
         if hit is None:
             v = valid_prims.to(device=primrgb.device).reshape(-1).bool()
             if v.numel() != n_prims:
                 raise RuntimeError("valid_prims must have one entry per primitive")
             ranks = torch.cumsum(v.to(torch.int32), 0, dtype=torch.int32) - 1
-            hit = (torch.where(v, ranks, torch.full_like(ranks, -1)).contiguous(), int(v.sum().item()))
+            hit = (torch.where(v, ranks, torch.full_like(ranks, -1)).contiguous(), int(v.sum().item()), valid_prims)
             if len(_SLOTS) > 16:
                 _SLOTS.clear()
             _SLOTS[key] = hit
-        slot, n_out = hit
+        slot, n_out = hit[0], hit[1]
     mul, add, relu = (25.0, 100.0, 1) if raw else (1.0, 0.0, 0)
     return _SlabsToPrims.apply(primrgb, primalpha, tuple(primsize), slot, n_out, mul, add, relu)

@@ -267,6 +267,28 @@ int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* f_vcond
                       float* g_f_vcond, float* g_postex, float* g_tn, float* g_albedo, const float* light_sh2,
                       const float* g_shsum2, void* stream);
 
+/* ---------------------------------------------------------------- post-render chain + photometric losses (section 8f-2) */
+
+/* replaces CalV5.forward (ca_code/nn/color_cal.py:211-241), the background composite of rgca.AutoEncoder.forward
+ * (ca_code/models/rgca.py:226-230) and LearnableBlur.forward (ca_code/nn/dof_cal.py:44-56; torchvision gaussian_blur 3x3 /
+ * 7x7, reflect padding): pred = blur(cal(rgb) + (1 - alpha) * bg).  rgb / bg / pred [B,3,H,W], alpha [B,1,H,W], cal_w / cal_b /
+ * blur_w [B,3] (blur_w = softmax-ed weights), grey [B] int32.  Stages with NULL tensors are skipped. */
+int gb_post_render_fwd(int B, int H, int W, const float* rgb, const float* alpha, const float* bg, const float* cal_w,
+                       const float* cal_b, const int32_t* grey, const float* blur_w, float* pred, void* stream);
+/* g_pred -> g_rgb (overwritten); g_cal_w / g_cal_b / g_blur_w [B,3] accumulated (zero-filled by the caller, may be NULL). */
+int gb_post_render_bwd(int B, int H, int W, const float* rgb, const float* alpha, const float* bg, const float* cal_w,
+                       const float* cal_b, const int32_t* grey, const float* blur_w, const float* g_pred, float* g_rgb,
+                       float* g_cal_w, float* g_cal_b, float* g_blur_w, void* stream);
+/* replaces rgb_l1 and rgb_ssim (ca_code/loss/__init__.py:391-410, 479-494 over ca_code/utils/ssim.py:25-63): sums [3] fp64
+ * (zero-filled by the caller) = sum |(pred - target) * mask|, sum ssim_map * mask, sum of the mask over 3 channels;
+ * d_mu / d_pp / d_tp [B,3,H,W] are kept for the backward. */
+int gb_ssim_l1_fwd(int B, int H, int W, const float* pred, const float* target, const float* mask, float* d_mu, float* d_pp,
+                   float* d_tp, double* sums, void* stream);
+/* gradient of l1_weight * rgb_l1 + ssim_weight * rgb_ssim w.r.t. pred, times *g_loss (device scalar, NULL = 1). */
+int gb_ssim_l1_bwd(int B, int H, int W, const float* pred, const float* target, const float* mask, const float* d_mu,
+                   const float* d_pp, const float* d_tp, const double* sums, const float* g_loss, float l1_weight,
+                   float ssim_weight, float* g_pred, void* stream);
+
 /* replaces the environment-map specular branch of rgca.PrimDecoder.forward (ca_code/models/rgca.py:548-556):
  * einsum("bxy,bny->bnx", lightrot, ref_dirs) -> dir2uv (ca_code/utils/envmap.py:284-292) -> mipmap_grid_sample of the
  * pre-convolved pyramid at level sigma * level_scale (ca_code/utils/mipmap_sampler.py:13-66: bilinear, border padding,

@@ -25,7 +25,16 @@ def run(tag, K=30):
     torch.cuda.synchronize(); wall = (time.perf_counter() - t0) / K * 1e3
     print(tag, "event ms/step %.3f" % (sum(a.elapsed_time(b) for a, b in ts) / K), "wall ms/step (incl. flush) %.3f" % wall)
 run("with sync   ")
-gu._DEBUG_ASSUME_N[0] = 1078203
+# profiling experiment only: skip the host sync by monkeypatching the count (the scene is the same every step)
+_orig = gu.compute_cumulative_intersects
+def _no_sync(nth):
+    cum = torch.empty_like(nth)
+    ws = gu._workspace(nth.device, gu._lib.lib().gb_cumsum_workspace_bytes(nth.numel()))
+    gu._lib.check(gu._lib.lib().gb_cumsum_i32(nth.numel(), nth.data_ptr(), cum.data_ptr(), ws.data_ptr(), gu._lib.stream_ptr(nth.device)), "cumsum")
+    return 1078203, cum
+gu.compute_cumulative_intersects = _no_sync
+import goliath_b200.gsplat.rasterize as _r, goliath_b200.gsplat.fused as _f
+_r.compute_cumulative_intersects = _f.compute_cumulative_intersects = _no_sync
 run("without sync")
 # CPU-only cost of issuing one step (GPU idle -> measures launch overhead): issue and do not wait
 torch.cuda.synchronize(); t0 = time.perf_counter(); step(); t1 = time.perf_counter(); torch.cuda.synchronize()
