@@ -267,6 +267,38 @@ int gb_rgca_heads_bwd(int B, int G, const float* f_vnocond, const float* f_vcond
                       float* g_f_vcond, float* g_postex, float* g_tn, float* g_albedo, const float* light_sh2,
                       const float* g_shsum2, void* stream);
 
+/* ---------------------------------------------------------------- mesh front end of the decoders (section 8f-4) */
+
+/* replaces vert_normals (ca_code/utils/geom.py:327-346): v [B,V,3], vi [F,3] -> vn [B,V,3]; acc [B,V,3] = scratch
+ * zero-filled by the caller (sum of the unit face normals per vertex), kept for the backward. */
+int gb_vert_normals_fwd(int B, int V, int F, const float* v, const int32_t* vi, float eps, float* acc, float* vn, void* stream);
+/* g_vn -> g_v [B,V,3] (zero-filled by the caller, accumulated); g_acc [B,V,3] scratch. */
+int gb_vert_normals_bwd(int B, int V, int F, const float* v, const int32_t* vi, float eps, const float* acc, const float* g_vn,
+                        float* g_acc, float* g_v, void* stream);
+/* replaces values_to_uv (ca_code/utils/geom.py:308-324, GeometryModule.to_uv): values [B,V,C], index [T,3] int32 (-1 =
+ * uncovered), bary [T,3] -> out [B,C,T] with T = uv_size^2. */
+int gb_values_to_uv_fwd(int B, int V, int C, int64_t T, const float* values, const int32_t* index, const float* bary, float* out,
+                        void* stream);
+/* g_out [B,C,T] -> g_values [B,V,C] (zero-filled by the caller, accumulated). */
+int gb_values_to_uv_bwd(int B, int V, int C, int64_t T, const int32_t* index, const float* bary, const float* g_out,
+                        float* g_values, void* stream);
+
+/* ---------------------------------------------------------------- gradient hygiene + clip + Adam (section 8f-3) */
+
+/* replaces ca_code/utils/train.py:209-215 around the optimizer of config/*.yml (torch.optim.Adam / AdamW): zero the NaN /
+ * Inf gradient entries, clip_grad_norm_(params, max_norm), optimizer.step().  rows: device array of 56-byte records
+ * {float* p, g, m, v; int64 numel; float lr, wd; int32 missed, pad} (g == NULL: parameter skipped; missed = steps it sat out); chunks: device (tensor, chunk) int32
+ * pairs covering every tensor in steps of gb_optim_chunk_elems() elements. */
+int gb_optim_chunk_elems(void);
+int gb_optim_row_bytes(void);
+/* non-finite gradient entries -> 0 in place; *sqnorm (device fp64, zero-filled by the caller) += sum of squares. */
+int gb_grad_sanitize_sqnorm(const void* rows, const int32_t* chunks, int n_chunks, double* sqnorm, void* stream);
+/* Adam (adamw = 0, L2 weight decay) or AdamW (adamw = 1) step; gradients scaled by clamp(max_norm / (sqrt(*sqnorm) + 1e-6),
+ * max = 1) when sqnorm != NULL and max_norm > 0; bias corrections 1 - beta^(step - row.missed); write_grads = 1 stores the clipped
+ * gradients back (what clip_grad_norm_ leaves in p.grad). */
+int gb_adam_step(const void* rows, const int32_t* chunks, int n_chunks, const double* sqnorm, float max_norm, float beta1,
+                 float beta2, float eps, int step, int adamw, int write_grads, void* stream);
+
 /* ---------------------------------------------------------------- post-render chain + photometric losses (section 8f-2) */
 
 /* replaces CalV5.forward (ca_code/nn/color_cal.py:211-241), the background composite of rgca.AutoEncoder.forward

@@ -60,7 +60,9 @@ def main():
     params = cal.holder.params
     g_rgb, g_params, g_blur_raw, g_x3 = th.autograd.grad(loss, [rgb, params, blur.weights_raw, x3])
     # per-frame rows as the fused kernels take them
-    rows = params.detach()[idx]
+    rows = params.detach()[idx].clone()
+    ident = idx == cal.identity_idx       # CalV5 passes the identity camera's image through untouched (color_cal.py:218-221):
+    rows[ident, :3], rows[ident, 3:] = 1.0, 0.0   # the fused kernel's rows for such a frame are w = 1, b = 0
     bw = th.softmax(blur.weights_raw.detach()[blur.name_to_idx(frame_cams)], dim=-1)
     # gradient w.r.t. the per-frame softmax-ed weights: recompute through a leaf at that point
     bw_leaf = bw.clone().requires_grad_()
@@ -70,7 +72,8 @@ def main():
            + bw_leaf[:, 2].reshape(B, 1, 1, 1) * gaussian_blur(x2d, [7, 7]))
     assert th.allclose(x3b, x3.detach(), atol=1e-9)
     (g_bw,) = th.autograd.grad((x3b * g_x3).sum(), [bw_leaf])
-    g_rows = g_params[idx]   # (the reference's lr-scale hook is training policy, not part of the function; rows are distinct)
+    g_rows = g_params[idx].clone()   # (the reference's lr-scale hook is training policy, not part of the function; rows are distinct)
+    assert float(g_rows[ident].abs().max()) == 0.0   # the identity camera's parameters receive no gradient upstream
     d = dict(rgb=rgb, alpha=alpha, bg=bg, image=image, mask=mask, cal_w=rows[:, :3], cal_b=rows[:, 3:],
              grey=th.tensor([int(c.startswith("41")) for c in frame_cams]), blur_w=bw, x1=x1, x2=x2, pred=x3, l1=l1, ssim_loss=ss,
              loss=loss, g_rgb=g_rgb, g_cal_w=g_rows[:, :3], g_cal_b=g_rows[:, 3:], g_blur_w=g_bw, g_pred=g_x3)
