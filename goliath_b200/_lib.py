@@ -38,6 +38,8 @@ SIGNATURES = {
     "gb_map_gaussian_to_intersects_dn": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "gb_sort_intersects_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "gb_get_tile_bin_edges_dn": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "gb_get_tile_sort_mode": (_i, []),
+    "gb_set_tile_sort_mode": (None, [_i]),
     "gb_get_rank_sort_mode": (_i, []),
     "gb_set_rank_sort_mode": (None, [_i]),
     "gb_bin_tiles_supported": (_i, [_i]),
@@ -47,6 +49,11 @@ SIGNATURES = {
     "gb_tile_schedule": (_i, [_i, _vp, _vp, _vp]),
     "gb_rasterize_sched_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),
     "gb_rasterize_sched_bwd": (_i, [_i, _i, _i] + [_vp] * 13 + [_vp]),
+    "gb_records_widen": (_i, [_i64, _vp, _vp, _vp, _vp]),
+    "gb_records_set_colors4": (_i, [_i64, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "gb_rasterize_multi_fwd": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "gb_rasterize_multi_bwd": (_i, [_i, _i, _vp, _vp, _vp, _i] + [_vp] * 9 + [_vp]),
+    "gb_colors12_unpack": (_i, [_i64, _i, _vp, _vp, _vp]),
     "gb_records_set_colors": (_i, [_i64] + [_vp] * 5 + [_vp]),
     "gb_splat_grad_unpack": (_i, [_i] + [_vp] * 8 + [_vp]),
     "gb_get_blend_mode": (_i, []),

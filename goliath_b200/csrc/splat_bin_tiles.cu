@@ -588,6 +588,66 @@ __global__ void __launch_bounds__(kSortThreads, 3) tile_sort_pack_kernel(
   }
 }
 
+// ------------------------------------------------------------------ 5b. the same in two kernels (default)
+// tile_sort_pack_kernel is bound by its heaviest tiles: one CTA walks bitmap clear -> bucket loads -> popcount scan ->
+// rank write-out -> rank read-back -> gid load -> 48-byte record gather -> store, eight dependent global round trips
+// per tile (profiles/r02_launches_head.txt: 51 us against ~12 us of traffic).  Split: the per-tile kernel stops after
+// writing the SORTED RANKS in place over the tile's bucket; a grid-wide kernel then turns every intersection's rank
+// into its Gaussian id and its record, three threads per record (48 B = 3 x 16 B), fully parallel over the 1.08 M
+// intersections whatever the tile lengths are.
+__global__ void __launch_bounds__(kSortThreads, 3) tile_sort_kernel(int words, int chunk, const int* __restrict__ order,
+                                                                    const int2* __restrict__ tile_bins,
+                                                                    int* __restrict__ tile_ranks) {
+  extern __shared__ unsigned s_bits[];
+  __shared__ int s_warp[33];
+  const int tile = order ? order[blockIdx.x] : (int)blockIdx.x;
+  const int2 range = tile_bins[tile];
+  const int n = range.y - range.x;
+  if (n <= 0) return;  // uniform over the CTA
+  for (int w = threadIdx.x; w < words; w += kSortThreads) s_bits[w] = 0u;
+  __syncthreads();
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kSortThreads) {
+    int r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kSortThreads;
+      r[u] = (i < n) ? tile_ranks[range.x + i] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r[u] >= 0) atomicOr(&s_bits[r[u] >> 5], 1u << (r[u] & 31));
+  }
+  __syncthreads();  // every rank of the bucket is in the bitmap: the bucket may now be overwritten
+  const int w0 = threadIdx.x * chunk, w1 = min(words, w0 + chunk);
+  int cnt = 0;
+  for (int w = w0; w < w1; ++w) cnt += __popc(s_bits[w]);
+  int total;
+  int pos = range.x + block_exclusive_scan(cnt, s_warp, total);
+  for (int w = w0; w < w1; ++w) {
+    unsigned m = s_bits[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      tile_ranks[pos++] = w * 32 + b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_records_kernel(long long cap, const int* __restrict__ n_dev,
+                                                             const int* __restrict__ ranks_sorted,
+                                                             const int* __restrict__ rank_to_gid,
+                                                             const float4* __restrict__ rec_by_rank,
+                                                             int* __restrict__ gids_sorted, float4* __restrict__ rec) {
+  const long long n = min((long long)*n_dev, cap);
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index: record j / 3, part j % 3
+  if (j >= 3 * n) return;
+  const long long i = j / 3;
+  const int part = (int)(j - 3 * i);
+  const int r = ranks_sorted[i];
+  rec[j] = gb::ld_nc_f4(rec_by_rank + 3 * (size_t)r + part);
+  if (part == 0) gids_sorted[i] = rank_to_gid[r];
+}
+
 struct Layout {
   size_t counts, hist, sync, zero_bytes, cursor, keys_a, keys_b, vals_a, vals_b, rank_to_gid, rank_of, rec_by_rank,
       tile_ranks, total;
@@ -617,6 +677,14 @@ inline Layout make_layout(int G, int T, int64_t cap) {
 }
 
 // 1: the four radix passes as separate launches (round 1), 0: one cooperative kernel (default).  GOLIATH_B200_RANKSORT=passes|coop
+int g_tile_sort_mode = -1;  // 0: per-tile bitmap sort + grid-wide record gather (default), 1: one kernel per tile (round 1)
+int tile_sort_mode() {
+  if (g_tile_sort_mode < 0) {
+    const char* e = getenv("GOLIATH_B200_TILESORT");
+    g_tile_sort_mode = (e && strcmp(e, "fused") == 0) ? 1 : 0;
+  }
+  return g_tile_sort_mode;
+}
 int g_rank_sort_mode = -1;
 int rank_sort_mode() {
   if (g_rank_sort_mode < 0) {
@@ -683,6 +751,8 @@ int opt_in_smem(K kernel, bool* done) {
 
 // Depth-rank sort of gb_bin_tiles_pack: 0 = one cooperative kernel over the varying key bits (default), 1 = four
 // radix passes as separate launches (round 1).  Identical outputs; the switch exists for A/B timing and the tests.
+GB_API int gb_get_tile_sort_mode(void) { return tile_sort_mode(); }
+GB_API void gb_set_tile_sort_mode(int mode) { g_tile_sort_mode = mode ? 1 : 0; }
 GB_API int gb_get_rank_sort_mode(void) { return rank_sort_mode(); }
 GB_API void gb_set_rank_sort_mode(int mode) { g_rank_sort_mode = mode ? 1 : 0; }
 
@@ -725,7 +795,7 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   const int items = rank_items(G);
   const int ctas = gb::cdiv(G, kRankBlock * items);
   const int smem_tiles = (T <= kMaxSmemTiles) ? T : 0;
-  static bool s_opt_k8[64] = {}, s_opt_k16[64] = {}, s_opt_scat[64] = {}, s_opt_sort[64] = {};
+  static bool s_opt_k8[64] = {}, s_opt_k16[64] = {}, s_opt_scat[64] = {}, s_opt_sort[64] = {}, s_opt_sort2[64] = {};
   if ((size_t)smem_tiles * 8 > 40 * 1024) {
     int e = (items == 8) ? opt_in_smem(depth_keys_kernel<kRankBlock * 8>, s_opt_k8)
                          : opt_in_smem(depth_keys_kernel<kRankBlock * 16>, s_opt_k16);
@@ -741,7 +811,8 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
                      : launch_rank_sort<16>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b,
                                             vals_a, vals_b, hist, counts, sync, rank_to_gid, rank_of, s);
   if (es) return es;
-  tile_scan_kernel<<<1, 1024, 0, s>>>(T, (long long)cap, counts, (int2*)tile_bins, cursor, n_out, overflow);
+  int* n_total = n_out ? n_out : (int*)(sync + 3);  // the record gather below needs the count on the device
+  tile_scan_kernel<<<1, 1024, 0, s>>>(T, (long long)cap, counts, (int2*)tile_bins, cursor, n_total, overflow);
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   const int e = tile_sched ? gb_tile_schedule(T, tile_bins, tile_order, stream)
@@ -753,6 +824,19 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   const int words = gb::cdiv(G, 32);
   const int chunk = gb::cdiv(words, kSortThreads) | 1;
   const size_t smem = (size_t)words * 4;
+  if (tile_sort_mode() == 0) {
+    if (smem > 40 * 1024) {
+      const int e2 = opt_in_smem(tile_sort_kernel, s_opt_sort2);
+      if (e2) return e2;
+    }
+    tile_sort_kernel<<<T, kSortThreads, smem, s>>>(words, chunk, tile_order, (const int2*)tile_bins, tile_ranks);
+    if (cap > 0)
+      gather_records_kernel<<<(unsigned)gb::cdiv64(3 * cap, 256), 256, 0, s>>>((long long)cap, n_total, tile_ranks, rank_to_gid,
+                                                                             rec_by_rank, gids_sorted, (float4*)records);
+    gb::count_launches(3);
+    GB_CHECK_LAUNCH();
+    return 0;
+  }
   if (smem > 40 * 1024) {
     const int e2 = opt_in_smem(tile_sort_pack_kernel, s_opt_sort);
     if (e2) return e2;

@@ -499,6 +499,463 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
   if (cnt > 0) chunk(0, pad4(cnt));
 }
 
+// ================================================================== four lighting conditions per pass (OLAT)
+// BASELINE config 3: the 32 one-light-at-a-time conditions of a view share geometry, projection, tile
+// lists AND every pixel's alphas / transmittances — only the colours differ.  These kernels blend FOUR colour sets in one
+// walk: the quadratic form, ex2, the transmittance recurrence (forward) and the whole (fac, v_sigma) machinery, the cull
+// and the hit compaction (backward) are paid once per hit instead of four times; per condition only 3 FMAs (forward) or
+// the colour-buffer FMAs and the v_colour sums (backward) are added.  Records are "wide": 32 B of geometry + 4 x rgb =
+// 80 B (5 x float4), colour part rewritten per group of conditions by gb_records_set_colors4.
+constexpr int kMK = 4;                 // conditions per pass
+constexpr int kMC = 3 * kMK;           // colour channels per pass
+constexpr int kMRQ = 5;                // float4 per wide record
+constexpr int kMRecBytes = kMRQ * 16;  // 80
+
+__global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
+    int img_w, int img_h, int tbx, const int* order, int sched, const int2* __restrict__ tile_bins,
+    const float4* __restrict__ rec, const float* __restrict__ background, float* __restrict__ out_planes /* [4][H][W][3] */) {
+  __shared__ __align__(128) float4 s_rec[kFwdStages][kStageRecs * kMRQ];  // 40 KB
+  __shared__ __align__(8) unsigned long long s_full[kFwdStages];
+  __shared__ __align__(8) unsigned long long s_empty[kFwdStages];
+  __shared__ int s_ndone;
+  __shared__ int s_tile;
+
+  const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+  if (tr == 0) {
+    s_tile = draw_tile(order, sched, tbx * ((img_h + 15) >> 4));
+#pragma unroll
+    for (int s = 0; s < kFwdStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kPixelWarps);
+    }
+    s_ndone = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (s_tile < 0) return;
+  const Tile tl = make_tile(s_tile, tbx);
+  const int2 range = tile_bins[tl.tile_id];
+  const int num_batches = (range.y - range.x + kStageRecs - 1) / kStageRecs;
+
+  if (warp == kPixelWarps) {  // producer warp (one lane)
+    if (lane != 0) return;
+    volatile int* ndone = &s_ndone;
+    int issued = 0;
+    for (int b = 0; b < num_batches; ++b) {
+      const int s = b % kFwdStages;
+      if (b >= kFwdStages) {
+        const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
+        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
+        }
+        if (*ndone >= kPixelWarps) break;
+      }
+      const int start = range.x + b * kStageRecs;
+      const unsigned bytes = (unsigned)min(kStageRecs, range.y - start) * kMRecBytes;
+      mbar_expect_tx(&s_full[s], bytes);
+      bulk_g2s(&s_rec[s][0], rec + (size_t)start * kMRQ, bytes, &s_full[s]);
+      issued = b + 1;
+    }
+    for (int b = max(0, issued - kFwdStages); b < issued; ++b)
+      mbar_wait(&s_full[b % kFwdStages], (unsigned)((b / kFwdStages) & 1));
+    return;
+  }
+
+  const int wx0 = tl.tx * 16 + ((warp & 1) << 3), wy0 = tl.ty * 16 + ((warp >> 1) << 2);
+  const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+  const bool inside = (pxi < img_w) && (pyi < img_h);
+  const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+  const float fx0 = (float)wx0 + 0.5f, fx1 = (float)wx0 + 7.5f, fy0 = (float)wy0 + 0.5f, fy1 = (float)wy0 + 3.5f;
+
+  bool done = !inside;
+  float T = 1.f;
+  float acc[kMC];
+#pragma unroll
+  for (int c = 0; c < kMC; ++c) acc[c] = 0.f;
+
+  bool counted = false;
+  for (int b = 0; b < num_batches; ++b) {
+    const bool all_done = __all_sync(0xffffffffu, done);
+    if (all_done && !counted) {
+      counted = true;
+      if (lane == 0) atomicAdd(&s_ndone, 1);
+    }
+    const int s = b % kFwdStages;
+    const unsigned par = (unsigned)((b / kFwdStages) & 1);
+    int st = 0;
+    if (lane == 0) {
+      volatile int* ndone = &s_ndone;
+      for (;;) {
+        if (mbar_try(&s_full[s], par)) { st = 1; break; }
+        if (all_done && *ndone >= kPixelWarps) { st = 2; break; }
+      }
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st == 2) break;
+    if (all_done) {
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      continue;
+    }
+    mbar_wait(&s_full[s], par);
+    const float4* sr = s_rec[s];
+    const int batch_start = range.x + b * kStageRecs;
+    const int batch_size = min(kStageRecs, range.y - batch_start);
+    for (int c0 = 0; c0 < batch_size; c0 += 32) {
+      const int ti = c0 + lane;
+      bool hit = false;
+      if (ti < batch_size) hit = footprint_hit(sr[ti * kMRQ], &sr[ti * kMRQ + 1], fx0, fx1, fy0, fy1);
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        int t[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {  // two hits per round: 2 x 12 colour registers
+          live[u] = mask != 0;
+          t[u] = live[u] ? c0 + __ffs(mask) - 1 : t[0];
+          mask &= mask - 1;
+        }
+        float alpha[2], sig[2];
+        float4 col[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 q0 = sr[t[u] * kMRQ], q1 = sr[t[u] * kMRQ + 1];
+          col[u][0] = sr[t[u] * kMRQ + 2]; col[u][1] = sr[t[u] * kMRQ + 3]; col[u][2] = sr[t[u] * kMRQ + 4];
+          const float dx = q0.x - px, dy = q0.y - py;
+          sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+          alpha[u] = fminf(kAlphaMaxFwd, q1.w * __expf(-sig[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
+          const float next_T = T * (1.f - alpha[u]);
+          const bool stop = ok && (next_T <= kTEps);
+          const bool take = ok && !stop;
+          done = done || stop;
+          if (take) {
+            const float vis = alpha[u] * T;
+            const float cc[kMC] = {col[u][0].x, col[u][0].y, col[u][0].z, col[u][0].w, col[u][1].x, col[u][1].y,
+                                   col[u][1].z, col[u][1].w, col[u][2].x, col[u][2].y, col[u][2].z, col[u][2].w};
+#pragma unroll
+            for (int c = 0; c < kMC; ++c) acc[c] += cc[c] * vis;
+            T = next_T;
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+  if (inside) {
+    const size_t pix = (size_t)pyi * img_w + pxi, plane = (size_t)img_h * img_w * 3;
+#pragma unroll
+    for (int k = 0; k < kMK; ++k) {
+      float* o = out_planes + k * plane + pix * 3;
+      o[0] = acc[3 * k + 0] + T * background[0];
+      o[1] = acc[3 * k + 1] + T * background[1];
+      o[2] = acc[3 * k + 2] + T * background[2];
+    }
+  }
+}
+
+constexpr int kMSmRec = kBwdStages * kStageRecs * kMRecBytes;      // 30720
+constexpr int kMSmEntries = kPixelWarps * kEntryCap * kMRecBytes;  // 30720  (entry: x y A B | C o idx - | 12 colours)
+constexpr int kMSmM = kPixelWarps * kChunk * kMStride * 8;         // 33792
+constexpr int kMSmVo = kPixelWarps * 32 * 48;                      // 12288
+constexpr int kMBwdSmem = kMSmRec + kMSmEntries + kMSmM + kMSmVo;  // 107520: two CTAs per SM
+
+__global__ void __launch_bounds__(kBwdThreads, 2) blend_bwd_multi_kernel(
+    int img_w, int img_h, int tbx, const int* order, int sched, const int* __restrict__ gids_sorted,
+    const int2* __restrict__ tile_bins, const float4* __restrict__ rec, const float* __restrict__ background,
+    const float* __restrict__ final_Ts, const int* __restrict__ final_idx,
+    const float* __restrict__ v_planes /* [4][H][W][3] */, float* __restrict__ v_xy, float* __restrict__ v_conic,
+    float* __restrict__ v_colors12 /* [G,12] */, float* __restrict__ v_opacity) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* s_rec = reinterpret_cast<float4*>(smem);
+  __shared__ __align__(8) unsigned long long s_full[kBwdStages];
+  __shared__ int s_ticket[kBwdStages];
+  __shared__ int s_cta_final;
+  __shared__ int s_tile;
+
+  const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+  if (tr == 0) s_tile = draw_tile(order, sched, tbx * ((img_h + 15) >> 4));
+  __syncthreads();
+  if (s_tile < 0) return;
+  float4* E = reinterpret_cast<float4*>(smem + kMSmRec) + warp * kEntryCap * kMRQ;
+  float2* M = reinterpret_cast<float2*>(smem + kMSmRec + kMSmEntries) + warp * kChunk * kMStride;
+  float4* VO = reinterpret_cast<float4*>(smem + kMSmRec + kMSmEntries + kMSmM) + warp * 32 * 3;
+
+  const Tile tl = make_tile(s_tile, tbx);
+  const int2 range = tile_bins[tl.tile_id];
+  if (range.y <= range.x) return;
+  const int wx0 = tl.tx * 16 + ((warp & 1) << 3), wy0 = tl.ty * 16 + ((warp >> 1) << 2);
+  const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
+  const bool inside = (pxi < img_w) && (pyi < img_h);
+  const float px = (float)pxi + 0.5f, py = (float)pyi + 0.5f;
+  const float fx0 = (float)wx0 + 0.5f, fx1 = (float)wx0 + 7.5f, fy0 = (float)wy0 + 0.5f, fy1 = (float)wy0 + 3.5f;
+  const size_t pix = inside ? ((size_t)pyi * img_w + pxi) : 0, plane = (size_t)img_h * img_w * 3;
+
+  const float T_final = inside ? final_Ts[pix] : 1.f;
+  float T = T_final;
+  const int bin_final = inside ? final_idx[pix] : -1;
+  float vo[kMC], buffer[kMC];
+  float bgdot = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMK; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      vo[3 * k + c] = inside ? v_planes[k * plane + pix * 3 + c] : 0.f;
+      buffer[3 * k + c] = 0.f;
+      bgdot += background[c] * vo[3 * k + c];
+    }
+  }
+  VO[lane * 3 + 0] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+  VO[lane * 3 + 1] = make_float4(vo[4], vo[5], vo[6], vo[7]);
+  VO[lane * 3 + 2] = make_float4(vo[8], vo[9], vo[10], vo[11]);
+  const float tfc = -T_final * bgdot;  // no alpha gradient here: the view's alpha belongs to the pass that carries the depth
+
+  int warp_bin_final = bin_final;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
+  if (tr == 0) {
+    s_cta_final = -1;
+#pragma unroll
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      s_ticket[s] = 0;
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_cta_final, warp_bin_final);
+  __syncthreads();
+  const int last = min(s_cta_final, range.y - 1);
+  if (last < range.x) return;
+  const int num_batches = (last - range.x + kStageRecs) / kStageRecs;
+  auto issue = [&](int k) {
+    const int s = k % kBwdStages;
+    const int hi = last - k * kStageRecs;
+    const int lo = max(range.x, hi - kStageRecs + 1);
+    const unsigned bytes = (unsigned)(hi - lo + 1) * kMRecBytes;
+    mbar_expect_tx(&s_full[s], bytes);
+    bulk_g2s(s_rec + s * kStageRecs * kMRQ, rec + (size_t)lo * kMRQ, bytes, &s_full[s]);
+  };
+  if (tr == 0)
+    for (int k = 0; k < min(kBwdStages, num_batches); ++k) issue(k);
+
+  auto chunk = [&](int base, int n) {  // n is a multiple of 2 (pad2 below)
+#pragma unroll 1
+    for (int h0 = 0; h0 < n; h0 += 2) {
+      float al[2], ov[2], ra[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int h = h0 + u;
+        const float4 a0 = E[(base + h) * kMRQ], a1 = E[(base + h) * kMRQ + 1];
+        const float dx = a0.x - px, dy = a0.y - py;
+        const float sigma = 0.5f * (a0.z * dx * dx + a1.x * dy * dy) + a0.w * dx * dy;
+        const float vis = __expf(-sigma);
+        const float alpha = fminf(kAlphaMaxBwd, a1.y * vis);
+        const bool valid = (__float_as_int(a1.z) <= bin_final) && !(sigma < 0.f) && !(alpha < kAlphaMin);
+        al[u] = valid ? alpha : 0.f;
+        ov[u] = valid ? a1.y * vis : 0.f;
+        ra[u] = rcp_approx(1.f - al[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 c0 = E[(base + h0 + u) * kMRQ + 2], c1 = E[(base + h0 + u) * kMRQ + 3], c2 = E[(base + h0 + u) * kMRQ + 4];
+        const float cc[kMC] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+        float v_alpha = tfc;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) v_alpha += (cc[c] * T - buffer[c]) * vo[c];
+        v_alpha *= ra[u];
+        T *= ra[u];
+        const float fac = al[u] * T;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) buffer[c] += cc[c] * fac;
+        M[(h0 + u) * kMStride + lane] = make_float2(fac, -ov[u] * v_alpha);
+      }
+    }
+    __syncwarp();
+    {
+      const int hh = lane & 15, half = lane >> 4;
+      const int he = min(hh, n - 1);
+      const float4 a0 = E[(base + he) * kMRQ], a1 = E[(base + he) * kMRQ + 1];
+      const int e_idx = __float_as_int(a1.z);
+      const int g_id = gids_sorted[e_idx == 0x7fffffff ? 0 : e_idx];
+      const float2* Mrow = M + hh * kMStride + half * 16;
+      const float4* V = VO + half * 16 * 3;
+      float g[kMC];
+#pragma unroll
+      for (int c = 0; c < kMC; ++c) g[c] = 0.f;
+      float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f, sii = 0.f, facmax = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float2 m = Mrow[q];
+        const float4 v0 = V[q * 3], v1 = V[q * 3 + 1], v2 = V[q * 3 + 2];
+        const float fi = (float)(q & 7);
+        facmax = fmaxf(facmax, m.x);
+        g[0] += m.x * v0.x; g[1] += m.x * v0.y; g[2] += m.x * v0.z; g[3] += m.x * v0.w;
+        g[4] += m.x * v1.x; g[5] += m.x * v1.y; g[6] += m.x * v1.z; g[7] += m.x * v1.w;
+        g[8] += m.x * v2.x; g[9] += m.x * v2.y; g[10] += m.x * v2.z; g[11] += m.x * v2.w;
+        if (q < 8) {
+          r00 += m.y;
+          r10 += m.y * fi;
+        } else {
+          r01 += m.y;
+          r11 += m.y * fi;
+        }
+        sii += m.y * (fi * fi);
+      }
+      const float u_ = a0.x - fx0, v_ = a0.y - (fy0 + (float)(2 * half));
+      const float S0 = r00 + r01, Sj = r01, Si = r10 + r11, Sij = r11;
+      const float sx = u_ * S0 - Si, sy = v_ * S0 - Sj;
+      const float sxx = u_ * (u_ * S0 - 2.f * Si) + sii;
+      const float sxy = u_ * (v_ * S0 - Sj) - v_ * Si + Sij;
+      const float syy = v_ * (v_ * S0 - 2.f * Sj) + Sj;
+      float o[kMC + 6];
+#pragma unroll
+      for (int c = 0; c < kMC; ++c) o[c] = g[c];
+      o[kMC + 0] = 0.5f * sxx; o[kMC + 1] = sxy; o[kMC + 2] = 0.5f * syy;
+      o[kMC + 3] = a0.z * sx + a0.w * sy;
+      o[kMC + 4] = a0.w * sx + a1.x * sy;
+      o[kMC + 5] = S0;
+#pragma unroll
+      for (int i = 0; i < kMC + 6; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+      facmax = fmaxf(facmax, __shfl_xor_sync(0xffffffffu, facmax, 16));
+      if (half == 0 && hh < n && facmax > 0.f) {
+        float* vc = v_colors12 + (size_t)kMC * g_id;
+        gb::red_add_v4(vc, o[0], o[1], o[2], o[3]);
+        gb::red_add_v4(vc + 4, o[4], o[5], o[6], o[7]);
+        gb::red_add_v4(vc + 8, o[8], o[9], o[10], o[11]);
+        gb::red_add(v_conic + 3 * (size_t)g_id + 0, o[kMC + 0]);
+        gb::red_add(v_conic + 3 * (size_t)g_id + 1, o[kMC + 1]);
+        gb::red_add(v_conic + 3 * (size_t)g_id + 2, o[kMC + 2]);
+        gb::red_add_v2(v_xy + 2 * (size_t)g_id, o[kMC + 3], o[kMC + 4]);
+        gb::red_add(v_opacity + g_id, -o[kMC + 5] * rcp_approx(a1.y));
+      }
+    }
+    __syncwarp();
+  };
+
+  auto pad2 = [&](int cnt_) {
+    const int padded = (cnt_ + 1) & ~1;
+    if (lane < padded - cnt_) {
+      E[(cnt_ + lane) * kMRQ + 0] = make_float4(0.f, 0.f, 1.f, 0.f);
+      E[(cnt_ + lane) * kMRQ + 1] = make_float4(1.f, 0.f, __int_as_float(0x7fffffff), 0.f);
+      E[(cnt_ + lane) * kMRQ + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      E[(cnt_ + lane) * kMRQ + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+      E[(cnt_ + lane) * kMRQ + 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    return padded;
+  };
+  int cnt = 0;
+  for (int k = 0; k < num_batches; ++k) {
+    const int s = k % kBwdStages;
+    const int hi = last - k * kStageRecs;
+    const int lo = max(range.x, hi - kStageRecs + 1);
+    const int batch_size = hi - lo + 1;
+    while (!mbar_try(&s_full[s], (unsigned)((k / kBwdStages) & 1))) __nanosleep(64);
+    const float4* sr = s_rec + s * kStageRecs * kMRQ;
+    const int j_top = min(batch_size - 1, warp_bin_final - lo);
+    for (int c1 = (j_top & ~31); c1 >= 0 && j_top >= 0; c1 -= 32) {
+      const int tj = c1 + lane;
+      bool hit = false;
+      if (tj <= j_top) hit = footprint_hit(sr[tj * kMRQ], &sr[tj * kMRQ + 1], fx0, fx1, fy0, fy1);
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (mask == 0) continue;
+      if (hit) {
+        const int pos = cnt + __popc(mask & ~((2u << lane) - 1u));
+        const float4 q0 = sr[tj * kMRQ], q1 = sr[tj * kMRQ + 1];
+        E[pos * kMRQ + 0] = make_float4(q0.x, q0.y, q1.x, q1.y);
+        E[pos * kMRQ + 1] = make_float4(q1.z, q1.w, __int_as_float(lo + tj), 0.f);
+        E[pos * kMRQ + 2] = sr[tj * kMRQ + 2];
+        E[pos * kMRQ + 3] = sr[tj * kMRQ + 3];
+        E[pos * kMRQ + 4] = sr[tj * kMRQ + 4];
+      }
+      cnt += __popc(mask);
+      __syncwarp();
+      if (cnt >= kChunk) {
+        int base = 0;
+        while (cnt - base >= kChunk) {
+          chunk(base, kChunk);
+          base += kChunk;
+        }
+        const int left = cnt - base;
+        if (lane < left) {
+          float4 e[kMRQ];
+#pragma unroll
+          for (int q = 0; q < kMRQ; ++q) e[q] = E[(base + lane) * kMRQ + q];
+#pragma unroll
+          for (int q = 0; q < kMRQ; ++q) E[lane * kMRQ + q] = e[q];
+        }
+        cnt = left;
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const int ticket = atomicAdd(&s_ticket[s], 1);
+      if (ticket == kPixelWarps - 1) {
+        __threadfence_block();
+        s_ticket[s] = 0;
+        if (k + kBwdStages < num_batches) issue(k + kBwdStages);
+      }
+    }
+  }
+  if (cnt > 0) chunk(0, pad2(cnt));
+}
+
+// geometry part of the 48-byte records into the 80-byte wide records (once per view)
+__global__ void __launch_bounds__(256) records_widen_kernel(long long cap, const int* __restrict__ n_dev,
+                                                            const float4* __restrict__ rec12, float4* __restrict__ rec20) {
+  const long long n = n_dev ? min((long long)*n_dev, cap) : cap;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rec20[kMRQ * i + 0] = rec12[3 * i + 0];
+  rec20[kMRQ * i + 1] = rec12[3 * i + 1];
+}
+
+// colour part of the wide records: up to four [G,3] colour tables (missing ones read as zero)
+__global__ void __launch_bounds__(256) records_set_colors4_kernel(long long cap, const int* __restrict__ n_dev,
+                                                                  const int* __restrict__ gids_sorted,
+                                                                  const float* __restrict__ colors /* [nk][G][3] */, int nk,
+                                                                  long long G, float4* __restrict__ rec20) {
+  const long long n = n_dev ? min((long long)*n_dev, cap) : cap;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = gids_sorted[i];
+  float c[kMC];
+#pragma unroll
+  for (int k = 0; k < kMK; ++k) {
+    const float* src = colors + ((size_t)k * G + g) * 3;
+    const bool on = k < nk;
+    c[3 * k + 0] = on ? src[0] : 0.f; c[3 * k + 1] = on ? src[1] : 0.f; c[3 * k + 2] = on ? src[2] : 0.f;
+  }
+  rec20[kMRQ * i + 2] = make_float4(c[0], c[1], c[2], c[3]);
+  rec20[kMRQ * i + 3] = make_float4(c[4], c[5], c[6], c[7]);
+  rec20[kMRQ * i + 4] = make_float4(c[8], c[9], c[10], c[11]);
+}
+
+// [G,12] group gradients -> up to four [G,3] tables (overwritten), and the group buffer is cleared for the next pass
+__global__ void __launch_bounds__(256) colors12_unpack_kernel(long long G, int nk, float4* __restrict__ v12,
+                                                              float* __restrict__ v_colors /* [nk][G][3] */) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float4 a = v12[3 * g], b = v12[3 * g + 1], c = v12[3 * g + 2];
+  const float v[kMC] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+  for (int k = 0; k < kMK; ++k)
+    if (k < nk) {
+      float* dst = v_colors + ((size_t)k * G + g) * 3;
+      dst[0] = v[3 * k]; dst[1] = v[3 * k + 1]; dst[2] = v[3 * k + 2];
+    }
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  v12[3 * g] = z; v12[3 * g + 1] = z; v12[3 * g + 2] = z;
+}
+
+bool g_multi_attr_set[64] = {};
+
 bool g_attr_set[64] = {};  // per device: the > 48 KB dynamic shared memory opt-in of the backward kernel
 
 }  // namespace
@@ -550,3 +1007,68 @@ int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorte
 }
 
 }  // namespace gbblend
+
+// ---------------------------------------------------------------- four lighting conditions per pass (OLAT), C ABI
+// wide records [cap, 20] fp32: geometry of the 48-byte records + 4 x rgb.
+GB_API int gb_records_widen(int64_t cap, const int32_t* n_dev, const float* records, float* records_wide, void* stream) {
+  if (cap <= 0) return 0;
+  records_widen_kernel<<<(unsigned)gb::cdiv64(cap, 256), 256, 0, (cudaStream_t)stream>>>(cap, n_dev, (const float4*)records,
+                                                                                         (float4*)records_wide);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+// colors: nk (1..4) consecutive [G,3] tables; missing conditions are blended as black.
+GB_API int gb_records_set_colors4(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* colors, int nk,
+                                  int64_t G, float* records_wide, void* stream) {
+  if (cap <= 0) return 0;
+  if (nk < 1 || nk > 4) return (int)cudaErrorInvalidValue;
+  records_set_colors4_kernel<<<(unsigned)gb::cdiv64(cap, 256), 256, 0, (cudaStream_t)stream>>>(cap, n_dev, gids_sorted, colors, nk,
+                                                                                               G, (float4*)records_wide);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+// out_planes [4][H][W][3]: the four conditions' images (background added); same tile_bins / order as the single pass.
+GB_API int gb_rasterize_multi_fwd(int img_h, int img_w, const int32_t* tile_bins, const int32_t* tile_order, int sched,
+                                  const float* records_wide, const float* background, float* out_planes, void* stream) {
+  if (img_h <= 0 || img_w <= 0) return 0;
+  if (sched && !tile_order) return (int)cudaErrorInvalidValue;
+  const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
+  blend_fwd_multi_kernel<<<tbx * tby, kFwdThreads, 0, (cudaStream_t)stream>>>(
+      img_w, img_h, tbx, tile_order, sched, (const int2*)tile_bins, (const float4*)records_wide, background, out_planes);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+// v_planes [4][H][W][3]; final_Ts / final_idx of the view (from the single-condition pass); v_xy / v_conic / v_opacity are
+// accumulated into; v_colors12 [G,12] (zero-filled) receives the four colour gradients interleaved per Gaussian.
+GB_API int gb_rasterize_multi_bwd(int img_h, int img_w, const int32_t* gids_sorted, const int32_t* tile_bins,
+                                  const int32_t* tile_order, int sched, const float* records_wide, const float* background,
+                                  const float* final_Ts, const int32_t* final_idx, const float* v_planes, float* v_xy,
+                                  float* v_conic, float* v_colors12, float* v_opacity, void* stream) {
+  if (img_h <= 0 || img_w <= 0) return 0;
+  if (sched && !tile_order) return (int)cudaErrorInvalidValue;
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !g_multi_attr_set[dev]) {
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMBwdSmem));
+    if (dev >= 0 && dev < 64) g_multi_attr_set[dev] = true;
+  }
+  const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
+  blend_bwd_multi_kernel<<<tbx * tby, kBwdThreads, kMBwdSmem, (cudaStream_t)stream>>>(
+      img_w, img_h, tbx, tile_order, sched, gids_sorted, (const int2*)tile_bins, (const float4*)records_wide, background, final_Ts,
+      final_idx, v_planes, v_xy, v_conic, v_colors12, v_opacity);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}
+// v_colors12 [G,12] -> nk consecutive [G,3] tables (overwritten); clears v_colors12 for the next group.
+GB_API int gb_colors12_unpack(int64_t G, int nk, float* v_colors12, float* v_colors, void* stream) {
+  if (G <= 0) return 0;
+  if (nk < 1 || nk > 4) return (int)cudaErrorInvalidValue;
+  colors12_unpack_kernel<<<(unsigned)gb::cdiv64(G, 256), 256, 0, (cudaStream_t)stream>>>(G, nk, (float4*)v_colors12, v_colors);
+  gb::count_launches(1);
+  GB_CHECK_LAUNCH();
+  return 0;
+}

@@ -5,10 +5,13 @@ transmittance of every pixel; only the colours differ).
 The reference reaches this case as a batch of B = C renders through rgca.AutoEncoder.render (ca_code/models/rgca.py:112-151,
 driven by ca_code/utils/light_decorator.py:167), i.e. C projections, 2C binnings and 2C blends per view.  Here a view is
 projected and binned once (gsplat/fused.py machinery, csrc/splat_bin_tiles.cu); condition 0 is blended with the depth
-channel (4 channels), every further condition rewrites only the colour quarter of the packed records in place
-(gb_records_set_colors, 16 B per intersection) and runs a 3-channel blend.  The backward mirrors it: geometry
-gradients (xy, conic, opacity) accumulate over the conditions in the same buffers, colour gradients land per condition,
-one projection backward at the end."""
+channel (4 channels); the further conditions go FOUR AT A TIME through blend kernels that walk the tile lists once per
+group — alphas, transmittances, culling and (backward) the whole v_sigma machinery are shared by the four colour sets
+(csrc/splat_blend_mom.cu, gb_rasterize_multi_*; "wide" 80-byte records whose colour part is rewritten per group).
+MODE = "single" keeps the one-condition-per-pass formulation (in-place recolouring of the 48-byte records + 3-channel
+blends) for A/B timing and the tests.  The backward mirrors the forward: geometry gradients (xy, conic, opacity)
+accumulate over the conditions in the same buffers, colour gradients land per condition, one projection backward."""
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -17,6 +20,8 @@ from torch.autograd import Function
 from .. import _lib
 from .fused import _overflow_flag
 from .utils import _tile_bounds, _workspace
+
+MODE = os.environ.get("GOLIATH_B200_OLAT", "multi")  # "multi": four conditions per blend pass; "single": one
 
 
 class _RenderShared(Function):
@@ -75,14 +80,31 @@ class _RenderShared(Function):
             _lib.check(ras_fwd(H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4), _lib.ptr(out4),
                                _lib.ptr(final_Ts), _lib.ptr(final_idx), st), "rasterize_packed_forward")
             rgb[0].copy_(out4[..., :3])
-            for c in range(1, C):
-                _lib.check(L.gb_records_set_colors(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[c]), _lib.ptr(depths),
-                                                   _lib.ptr(records), st), "records_set_colors")
-                _lib.check(ras_fwd(H, W, 3, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(background),
-                                   _lib.ptr(rgb[c]), _lib.ptr(scratch_T), _lib.ptr(scratch_idx), st),
-                           "rasterize_packed_forward")
+            multi = MODE == "multi" and C > 1
+            wide = None
+            if multi:
+                wide = torch.empty(cap, 20, **f32)
+                _lib.check(L.gb_records_widen(cap, _lib.ptr(n_dev), _lib.ptr(records), _lib.ptr(wide), st), "records_widen")
+                stage = torch.empty(4, H, W, 3, **f32)  # a group's four images (the last group may be partial)
+                for c in range(1, C, 4):
+                    nk = min(4, C - c)
+                    _lib.check(L.gb_records_set_colors4(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[c]), nk, G,
+                                                        _lib.ptr(wide), st), "records_set_colors4")
+                    dst = rgb[c:c + 4] if nk == 4 else stage
+                    _lib.check(L.gb_rasterize_multi_fwd(H, W, _lib.ptr(bins), _lib.ptr(order), sched, _lib.ptr(wide),
+                                                        _lib.ptr(background), _lib.ptr(dst), st), "rasterize_multi_forward")
+                    if nk < 4:
+                        rgb[c:c + nk].copy_(stage[:nk])
+            else:
+                for c in range(1, C):
+                    _lib.check(L.gb_records_set_colors(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[c]), _lib.ptr(depths),
+                                                       _lib.ptr(records), st), "records_set_colors")
+                    _lib.check(ras_fwd(H, W, 3, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(background),
+                                       _lib.ptr(rgb[c]), _lib.ptr(scratch_T), _lib.ptr(scratch_idx), st),
+                               "rasterize_packed_forward")
         ctx.save_for_backward(means3d, scales, quats, opacity, colors, viewmat, bg4, cov3d, depths, radii, conics, comp, gids,
                               bins, order, records, n_dev, final_Ts, final_idx)
+        ctx.wide = wide  # scratch of the multi-condition passes (colour part rewritten per group in the backward)
         ctx.meta = (C, G, H, W, cap, float(glob_scale), float(fx), float(fy), sched)
         ctx.mark_non_differentiable(radii)
         ctx.set_materialize_grads(False)
@@ -108,7 +130,7 @@ class _RenderShared(Function):
         acc = torch.zeros(G * 10, **f32)  # v_xy | v_conic | v_col4 (condition 0) | v_opacity_eff: one fill
         v_xy, v_conic = acc[:2 * G].view(G, 2), acc[2 * G:5 * G].view(G, 3)
         v_col4, v_opeff = acc[5 * G:9 * G].view(G, 4), acc[9 * G:]
-        v_colors = torch.zeros(C, G, 3, **f32)
+        v_colors = (torch.empty if ctx.wide is not None else torch.zeros)(C, G, 3, **f32)  # multi: every table is overwritten
         v_opacity = torch.empty(G, 1, **f32)
         v_comp, v_dep = torch.empty(G, **f32), torch.empty(G, **f32)
         g_cov2d, g_cov3d = torch.empty(G, 3, **f32), torch.empty(G, 6, **f32)
@@ -117,18 +139,37 @@ class _RenderShared(Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             ras_bwd = L.gb_rasterize_sched_bwd if sched else L.gb_rasterize_packed_bwd
-            # the records hold the colours of condition C-1 (left by the forward): walk the conditions downwards
-            for c in range(C - 1, 0, -1):
-                if c != C - 1:
-                    _lib.check(L.gb_records_set_colors(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[c]),
-                                                       _lib.ptr(depths), _lib.ptr(records), st), "records_set_colors")
-                _lib.check(ras_bwd(H, W, 3, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg3),
-                                   _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_rgb[c]), _lib.ptr(zero_alpha),
-                                   _lib.ptr(v_xy), _lib.ptr(v_conic), _lib.ptr(v_colors[c]), _lib.ptr(v_opeff), st),
-                           "rasterize_packed_backward")
-            if C > 1:
-                _lib.check(L.gb_records_set_colors(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[0]), _lib.ptr(depths),
-                                                   _lib.ptr(records), st), "records_set_colors")
+            wide = ctx.wide
+            if wide is not None:
+                # four conditions per pass: colour gradients arrive interleaved [G,12] and are split per group
+                v12 = torch.zeros(G, 12, **f32)
+                stage = torch.zeros(4, H, W, 3, **f32)
+                for c in range(1, C, 4):
+                    nk = min(4, C - c)
+                    _lib.check(L.gb_records_set_colors4(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[c]), nk, G,
+                                                        _lib.ptr(wide), st), "records_set_colors4")
+                    src = v_rgb[c:c + 4]
+                    if nk < 4:
+                        stage[:nk].copy_(v_rgb[c:c + nk])
+                        src = stage
+                    _lib.check(L.gb_rasterize_multi_bwd(H, W, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), sched,
+                                                        _lib.ptr(wide), _lib.ptr(bg3), _lib.ptr(final_Ts), _lib.ptr(final_idx),
+                                                        _lib.ptr(src), _lib.ptr(v_xy), _lib.ptr(v_conic), _lib.ptr(v12),
+                                                        _lib.ptr(v_opeff), st), "rasterize_multi_backward")
+                    _lib.check(L.gb_colors12_unpack(G, nk, _lib.ptr(v12), _lib.ptr(v_colors[c]), st), "colors12_unpack")
+            else:
+                # the records hold the colours of condition C-1 (left by the forward): walk the conditions downwards
+                for c in range(C - 1, 0, -1):
+                    if c != C - 1:
+                        _lib.check(L.gb_records_set_colors(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[c]),
+                                                           _lib.ptr(depths), _lib.ptr(records), st), "records_set_colors")
+                    _lib.check(ras_bwd(H, W, 3, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg3),
+                                       _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_rgb[c]), _lib.ptr(zero_alpha),
+                                       _lib.ptr(v_xy), _lib.ptr(v_conic), _lib.ptr(v_colors[c]), _lib.ptr(v_opeff), st),
+                               "rasterize_packed_backward")
+                if C > 1:
+                    _lib.check(L.gb_records_set_colors(cap, _lib.ptr(n_dev), _lib.ptr(gids), _lib.ptr(colors[0]), _lib.ptr(depths),
+                                                       _lib.ptr(records), st), "records_set_colors")
             _lib.check(ras_bwd(H, W, 4, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4),
                                _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out4), _lib.ptr(v_alpha), _lib.ptr(v_xy),
                                _lib.ptr(v_conic), _lib.ptr(v_col4), _lib.ptr(v_opeff), st), "rasterize_packed_backward")

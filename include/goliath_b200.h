@@ -122,6 +122,25 @@ int gb_pack_records_fused(int64_t n, const int32_t* gids_sorted, const float* xy
 int gb_records_set_colors(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* colors3,
                           const float* depths, float* records, void* stream);
 
+/* four lighting conditions per blend pass (OLAT, BASELINE config 3): the conditions of a view share every alpha and
+ * transmittance, so one walk of the tile lists blends four colour sets (csrc/splat_blend_mom.cu).  "Wide" records [cap,20]
+ * fp32 = the 32-byte geometry of the packed records + 4 x rgb; gb_records_widen copies the geometry once per view,
+ * gb_records_set_colors4 rewrites the colour part per group of (up to 4) conditions from nk consecutive [G,3] tables. */
+int gb_records_widen(int64_t cap, const int32_t* n_dev, const float* records, float* records_wide, void* stream);
+int gb_records_set_colors4(int64_t cap, const int32_t* n_dev, const int32_t* gids_sorted, const float* colors, int nk,
+                           int64_t G, float* records_wide, void* stream);
+/* out_planes [4][H][W][3] (3-channel background added to each). */
+int gb_rasterize_multi_fwd(int img_h, int img_w, const int32_t* tile_bins, const int32_t* tile_order, int sched,
+                           const float* records_wide, const float* background, float* out_planes, void* stream);
+/* v_planes [4][H][W][3]; final_Ts / final_idx from the view's single-condition pass; v_xy / v_conic / v_opacity accumulated;
+ * v_colors12 [G,12] (zero-filled): the four colour gradients interleaved per Gaussian, split by gb_colors12_unpack (which
+ * also clears it for the next group). */
+int gb_rasterize_multi_bwd(int img_h, int img_w, const int32_t* gids_sorted, const int32_t* tile_bins,
+                           const int32_t* tile_order, int sched, const float* records_wide, const float* background,
+                           const float* final_Ts, const int32_t* final_idx, const float* v_planes, float* v_xy, float* v_conic,
+                           float* v_colors12, float* v_opacity, void* stream);
+int gb_colors12_unpack(int64_t G, int nk, float* v_colors12, float* v_colors, void* stream);
+
 /* backward glue of the fused render: split v_colors4 / v_opacity_eff into v_colors3, v_opacity, v_comp, v_depth */
 int gb_splat_grad_unpack(int G, const float* v_colors4, const float* v_opac_eff, const float* opacity,
                          const float* compensation, float* v_colors3, float* v_opacity, float* v_comp, float* v_depth,
@@ -145,6 +164,10 @@ int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* g
 /* depth-rank sort inside gb_bin_tiles_pack: 0 = one cooperative kernel sorting only the key bits that vary (default),
  * 1 = four radix passes as separate launches.  Identical outputs (A/B timing, tests).  GOLIATH_B200_RANKSORT=coop|passes. */
 int gb_get_rank_sort_mode(void);
+/* per-tile ordering inside gb_bin_tiles_pack: 0 = bitmap sort per tile + one grid-wide record gather (default), 1 = one
+ * kernel per tile doing both (round 1).  Identical outputs.  GOLIATH_B200_TILESORT=split|fused. */
+int gb_get_tile_sort_mode(void);
+void gb_set_tile_sort_mode(int mode);
 void gb_set_rank_sort_mode(int mode);
 
 /* Bucket binning of the fused render (csrc/splat_bin_tiles.cu): replaces, for the fused path, the whole of gsplat

@@ -4,7 +4,7 @@ set -u
 OUT=gpurun_out/r2e
 mkdir -p $OUT
 echo "== pytest new" > $OUT/pytest.log
-timeout 900 python -m pytest tests/test_photo_loss_gpu.py tests/test_optim_gpu.py tests/test_geom_gpu.py -q -m gpu >> $OUT/pytest.log 2>&1
+timeout 900 python -m pytest tests/test_photo_loss_gpu.py tests/test_optim_gpu.py tests/test_geom_gpu.py tests/test_olat_gpu.py tests/test_splat_gpu.py tests/test_fullpath_gpu.py -q -m gpu >> $OUT/pytest.log 2>&1
 echo "rc=$?" >> $OUT/pytest.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $TR bench.py --gpus 2 --steps 100 --warmup 10 > $OUT/bench_head_n2.json 2> $OUT/bench_head_n2.err

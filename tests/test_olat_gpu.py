@@ -10,15 +10,26 @@ from util import assert_close, small_scene, t2n
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("capacity", [None, 1 << 16])
-def test_render_shared_equals_per_condition_renders(cuda, capacity):
+@pytest.fixture(params=["multi", "single"])
+def olat_mode(request):
+    """four conditions per blend pass (default) or one condition per pass"""
+    from goliath_b200.gsplat import olat
+
+    before = olat.MODE
+    olat.MODE = request.param
+    yield request.param
+    olat.MODE = before
+
+
+@pytest.mark.parametrize("capacity,C", [(None, 4), (1 << 16, 6), (1 << 16, 9)])
+def test_render_shared_equals_per_condition_renders(cuda, capacity, C, olat_mode):
     from goliath_b200.gsplat.fused import check_overflow, render_fused
     from goliath_b200.gsplat.olat import render_shared
 
     s = small_scene(G=3000, img_h=96, img_w=80)
     mult = 12.0
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
-    H, W, C = s["img_h"], s["img_w"], 4
+    H, W = s["img_h"], s["img_w"]
     gen = torch.Generator().manual_seed(3)
     cols = torch.rand(C, 3000, 3, generator=gen).to(cuda)
     w_rgb = torch.randn(C, H, W, 3, generator=gen).to(cuda)
@@ -59,7 +70,7 @@ def test_render_shared_equals_per_condition_renders(cuda, capacity):
         assert_close(a, b, rtol=1e-4, atol=2e-5 * float(np.abs(b).max()), frac=0.999, what="grad " + name)
 
 
-def test_render_views_shared_shapes_and_depth(cuda):
+def test_render_views_shared_shapes_and_depth(cuda, olat_mode):
     from goliath_b200.gsplat.olat import render_views_shared
     from goliath_b200.render import render_views
 
