@@ -64,6 +64,8 @@ SIGNATURES = {
     "gb_compute_raydirs_bwd": (_i, []),
     "gb_mvp_aabb_workspace_bytes": (_sz, [_i, _i]),
     "gb_mvp_compute_aabb": (_i, [_i, _i] + [_vp] * 8 + [_vp]),
+    "gb_get_raymarch_mode": (_i, []),
+    "gb_set_raymarch_mode": (None, [_i]),
     "gb_mvp_raymarch_fwd": (_i, [_i] * 4 + [_vp, _vp, _f] + [_vp] * 5 + [_i] * 3 + [_vp] + [_i] * 3 + [_vp] * 4
                             + [_i, _f, _f, _i, _i, _vp]),
     "gb_deconv_tc_weight_bytes": (_sz, [_i, _i]),

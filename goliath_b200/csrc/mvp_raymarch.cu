@@ -22,6 +22,9 @@
 //    with a recursive-halving exchange (16 shuffles instead of 75) and issued as one RED per value by 15 lanes;
 //  * current stream / current device everywhere; bounds scratch comes from the caller (no cudaMalloc per call,
 //    bvh.cu:261-293).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -365,6 +368,112 @@ __global__ void raymarch_fwd_kernel(RMArgs a) {
   if (a.raysat) { a.raysat[3 * o] = raysat.x; a.raysat[3 * o + 1] = raysat.y; a.raysat[3 * o + 2] = raysat.z; }
 }
 
+// ------------------------------------------------------------------ forward, lane-compacted sampling (algo 0, no shadow)
+// ncu on the kernel above (profiles/r01_raymarch_fwd_ncu.txt): the sampling block — fade (3 pow + exp), trilinear setup,
+// 8 corner loads — runs with 6 of 32 lanes active, because a primitive overlaps only a few rays of the warp's 8x4
+// footprint at a given step.  Here the warp ENQUEUES the (ray, primitive) pairs that are inside a primitive (local
+// coordinate + primitive id, compacted with a ballot) and SAMPLES them 32 at a time with every lane busy, whichever
+// ray or primitive an item belongs to; the results are then APPLIED in the original order — group by group (one group =
+// one (step, primitive), at most one item per ray), each ray picking its own result — so the additive accumulation
+// with saturation sees exactly the sequence of the kernel above: rays stay bit-identical (same expressions on the same
+// values, executed by another lane).  `sat` is only known at apply time: enqueueing uses the value of the last flush
+// (a superset; the apply step ignores items of saturated rays).
+constexpr int kQueue = 64;  // items per warp: < 32 pending + one group of up to 32
+struct RMQueue {
+  float4 q[kQueue];        // y0.xyz, primitive id (int bits)
+  float4 s[kQueue];        // sampled rgba (alpha already faded)
+  unsigned g[kQueue];      // ballot of each pending group
+};
+
+__global__ void raymarch_fwd_queue_kernel(RMArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+  int* s_hit = reinterpret_cast<int*>(smem);
+  float2* s_ivl = reinterpret_cast<float2*>(smem + (size_t)nwarps * kMaxHit * sizeof(int));
+  RMQueue* s_q = reinterpret_cast<RMQueue*>(smem + (size_t)nwarps * kMaxHit * (sizeof(int) + sizeof(float2)));
+  RaySetup r = setup_ray(a, s_hit, s_ivl);
+  const unsigned full = 0xffffffffu;
+  const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+  RMQueue& Q = s_q[(threadIdx.y * blockDim.x + threadIdx.x) >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  const size_t tsz = (size_t)a.TD * a.TH * a.TW;
+  const float stepsize = a.stepsize;
+  const float4* tbase = a.tplate + (size_t)r.n * a.K * tsz;
+
+  float4 rgba = make_float4(0.f, 0.f, 0.f, 0.f);
+  float3 raysat = make_float3(-1.f, -1.f, -1.f);
+  bool sat = false;
+  float t = r.t;
+  float3 pos = r.pos;
+  const bool live0 = !(t > r.rtmax + 1e-5f);
+  float tlo = warp_min(live0 ? t : INFINITY), thi = warp_max(live0 ? t : -INFINITY);
+  const float margin = 2.f * stepsize + 1e-3f;
+  int qn = 0, ng = 0;  // pending items / groups (warp-uniform)
+
+  auto flush = [&]() {
+    __syncwarp();
+    for (int base = 0; base < qn; base += 32) {  // sample: every lane takes one item
+      const int i = base + lane;
+      if (i < qn) {
+        const float4 it = Q.q[i];
+        const float3 y0 = make_float3(it.x, it.y, it.z);
+        const int k = __float_as_int(it.w);
+        const float fade = __expf(-a.fadescale * (__powf(fabsf(y0.x), a.fadeexp) + __powf(fabsf(y0.y), a.fadeexp) +
+                                                  __powf(fabsf(y0.z), a.fadeexp)));
+        float4 sv = sample4(a.TD, a.TH, a.TW, tbase + (size_t)k * tsz, y0);
+        sv.w *= fade;
+        Q.s[i] = sv;
+      }
+    }
+    __syncwarp();
+    int off = 0;
+    for (int g = 0; g < ng; ++g) {  // apply: original order, each ray picks its own result
+      const unsigned m = Q.g[g];
+      if (((m >> lane) & 1u) && !sat) {
+        const float4 sv = Q.s[off + __popc(m & lt)];
+        // PrimAccumAdditive::forward_prim (primaccum.h:63-79)
+        const float newalpha = rgba.w + sv.w * stepsize;
+        const float contrib = fminf(newalpha, 1.f) - rgba.w;
+        rgba.x += sv.x * contrib; rgba.y += sv.y * contrib; rgba.z += sv.z * contrib; rgba.w += 1.f * contrib;
+        if (newalpha >= 1.f) {
+          raysat = make_float3(sv.x, sv.y, sv.z);
+          sat = true;
+        }
+      }
+      off += __popc(m);
+    }
+    qn = 0;
+    ng = 0;
+    __syncwarp();
+  };
+
+  while (!__all_sync(full, t > r.rtmax + 1e-5f || sat)) {
+    for (int ks = 0; ks < r.nhit; ++ks) {
+      const float2 iv = r.ivl[ks];
+      if (thi + margin < iv.x || tlo - margin > iv.y) continue;  // warp-uniform: nobody is inside this box now
+      const int k = r.hit[ks];
+      const Local L = prim_local(r, k, pos);
+      const bool in = inside_unit(L.y0) && !sat && t < r.rtmax + 1e-5f;
+      const unsigned m = __ballot_sync(full, in);
+      if (m == 0u) continue;
+      if (in) Q.q[qn + __popc(m & lt)] = make_float4(L.y0.x, L.y0.y, L.y0.z, __int_as_float(k));
+      if (lane == 0) Q.g[ng] = m;
+      qn += __popc(m);
+      ++ng;
+      if (qn >= 32) flush();
+    }
+    t += stepsize;
+    pos = pos + r.raydir * stepsize;
+    tlo += stepsize;
+    thi += stepsize;
+    if (qn >= 16) flush();  // keeps `sat` fresh: a saturated ray stops enqueueing (and the loop may end) a step later at most
+  }
+  flush();
+  const size_t o = ((size_t)r.n * a.H + r.h) * a.W + r.w;
+  a.rayrgba[o] = rgba;
+  if (a.raysat) { a.raysat[3 * o] = raysat.x; a.raysat[3 * o + 1] = raysat.y; a.raysat[3 * o + 2] = raysat.z; }
+}
+
 // ------------------------------------------------------------------ backward
 // recursive-halving reduction of 16 per-lane values: 8+4+2+1+1 = 16 shuffles; afterwards the lane with index L
 // (even) holds the warp total of slot (L >> 1)
@@ -537,6 +646,15 @@ __global__ void __launch_bounds__(256) compute_aabb_kernel(int N, int K, const f
   }
 }
 
+int g_raymarch_mode = -1;  // 0: lane-compacted sampling queue (forward, algo 0, no shadow), 1: round-1 kernels everywhere
+int raymarch_mode() {
+  if (g_raymarch_mode < 0) {
+    const char* e = getenv("GOLIATH_B200_RAYMARCH");
+    g_raymarch_mode = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+  }
+  return g_raymarch_mode;
+}
+
 int fill_and_launch_check(const RMArgs& a, int bx, int by) {
   if (a.N <= 0 || a.H <= 0 || a.W <= 0) return 1;
   // whole warps only: the hit list is a warp-wide union built with full-mask votes (the reference asserts the
@@ -546,6 +664,10 @@ int fill_and_launch_check(const RMArgs& a, int bx, int by) {
 }
 
 }  // namespace
+
+// 0 = lane-compacted sampling in the forward march (default), 1 = the round-1 kernel; identical outputs (A/B, tests).
+GB_API int gb_get_raymarch_mode(void) { return raymarch_mode(); }
+GB_API void gb_set_raymarch_mode(int mode) { g_raymarch_mode = mode ? 1 : 0; }
 
 // scratch for gb_mvp_compute_aabb: N*(K-1) int flags (zeroed by the call itself)
 GB_API size_t gb_mvp_aabb_workspace_bytes(int N, int K) { return (size_t)N * (K > 1 ? K - 1 : 1) * sizeof(int); }
@@ -597,7 +719,13 @@ GB_API int gb_mvp_raymarch_fwd(int N, int H, int W, int K, const float* raypos, 
     raymarch_fwd_kernel<WP, SH><<<grid, block, smem, s>>>(a);                                                      \
   } while (0)
   if (algo == 1) { if (shadow) GB_RM_FWD(true, true); else GB_RM_FWD(true, false); }
-  else { if (shadow) GB_RM_FWD(false, true); else GB_RM_FWD(false, false); }
+  else if (shadow) GB_RM_FWD(false, true);
+  else if (raymarch_mode() == 0) {  // lane-compacted sampling (default for algo 0 without the shadow splat)
+    const size_t smem_q = smem + (size_t)nwarps * sizeof(RMQueue);
+    if (smem_q > 48 * 1024)
+      GB_CUDA(cudaFuncSetAttribute(raymarch_fwd_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    raymarch_fwd_queue_kernel<<<grid, block, smem_q, s>>>(a);
+  } else GB_RM_FWD(false, false);
 #undef GB_RM_FWD
   gb::count_launches(1);
   GB_CHECK_LAUNCH();

@@ -87,11 +87,12 @@ struct AdamArgs {
 
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float coef, const AdamArgs& a, float lr,
                                          float wd, float bc1, float bc2_sqrt) {
-  g *= coef;
+  g *= coef;                                 // what clip_grad_norm_ leaves in p.grad (stored back when asked)
+  float ge = g;                              // the gradient Adam sees
   if (a.adamw) p *= 1.f - lr * wd;           // decoupled decay (torch.optim.AdamW)
-  else if (wd != 0.f) g += wd * p;           // L2 (torch.optim.Adam weight_decay)
-  m = a.beta1 * m + (1.f - a.beta1) * g;     // exp_avg.lerp_(grad, 1 - beta1)
-  v = a.beta2 * v + (1.f - a.beta2) * g * g; // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  else if (wd != 0.f) ge += wd * p;          // L2 (torch.optim.Adam weight_decay), not written back
+  m = a.beta1 * m + (1.f - a.beta1) * ge;    // exp_avg.lerp_(grad, 1 - beta1)
+  v = a.beta2 * v + (1.f - a.beta2) * ge * ge; // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
   const float denom = sqrtf(v) / bc2_sqrt + a.eps;
   p -= (lr / bc1) * (m / denom);
 }

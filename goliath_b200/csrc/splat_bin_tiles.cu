@@ -326,13 +326,33 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
   unsigned bar_target = 0;
   const size_t hs = (size_t)tiles * kRadix;
 
-  if (passes == 0) {  // every key equal: the order is the id order
+  if (passes == 0) {  // every visible key equal: the order is the id order
     for (int i = blockIdx.x * kRankBlock + threadIdx.x; i < n; i += gridDim.x * kRankBlock) {
       rank_to_gid[i] = i;
       rank_of[i] = i;
     }
     return;
   }
+  // per-warp digit counts of one tile's keys (registers k[]), left in s_whist; rank[] = rank among equal digits
+  // inside the warp's chunk.  "Earlier in memory" == (smaller item index j, then smaller lane): stable.
+  auto warp_ranks = [&](const unsigned (&k)[kItems], int warp_base, int shift, unsigned (&rank)[kItems]) {
+    for (int d = lane; d < kRadix; d += 32) s_whist[warp][d] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int i = warp_base + j * 32 + lane;
+      const bool valid = i < n;
+      const unsigned dgt = (k[j] >> shift) & 0xffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? dgt : 0x100u);
+      const unsigned lower = peers & ((1u << lane) - 1u);
+      unsigned prev = 0;
+      if (valid) prev = s_whist[warp][dgt];
+      __syncwarp();
+      rank[j] = prev + __popc(lower);
+      if (valid && lower == 0u) s_whist[warp][dgt] = prev + __popc(peers);
+      __syncwarp();
+    }
+  };
   for (int p = 0; p < passes; ++p) {
     const bool last = (p == passes - 1);
     const int shift = 8 * p;
@@ -340,8 +360,33 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
     unsigned* kout = (p & 1) ? keys_a : keys_b;
     const int* vin = (p == 0) ? nullptr : ((p & 1) ? vals_b : vals_a);
     int* vout = last ? rank_to_gid : ((p & 1) ? vals_a : vals_b);
-    const unsigned* hist_cur = hist + (size_t)p * hs;
-    unsigned* hist_next = last ? nullptr : hist + (size_t)(p + 1) * hs;
+    unsigned* hist_cur = hist + (size_t)p * hs;
+    // ---- phase A (passes > 0; pass 0's table was written by depth_keys_kernel): this pass's digit histogram of every
+    // tile, from the keys as the previous pass left them.  No global atomics: round 2's first version accumulated the
+    // next table with one RED per key while scattering, and the concentrated top digit of a head's depths put hundreds of
+    // REDs on the same address per tile (ncu: 6 % issue-active, 18 us per pass).
+    if (p > 0) {
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int warp_base = tile * kTile + warp * (32 * kItems);
+        unsigned k[kItems], rank[kItems];
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+          const int i = warp_base + j * 32 + lane;
+          k[j] = (i < n) ? __ldcg(kin + i) : 0xffffffffu;
+        }
+        warp_ranks(k, warp_base, shift, rank);
+        __syncthreads();
+        {
+          unsigned c = 0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) c += s_whist[w][threadIdx.x];
+          hist_cur[(size_t)tile * kRadix + threadIdx.x] = c;
+        }
+        __syncthreads();
+      }
+      grid_barrier(barrier, bar_target);
+    }
+    // ---- phase B: column prefix over the tiles, then the stable scatter
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int warp_base = tile * kTile + warp * (32 * kItems);
       unsigned k[kItems];
@@ -379,23 +424,8 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
       int unused;
       const unsigned digit_base = (unsigned)block_exclusive_scan((int)total, s_scan, unused);
       const unsigned my_base = digit_base + before;
-      for (int d = lane; d < kRadix; d += 32) s_whist[warp][d] = 0;
-      __syncwarp();
       unsigned rank[kItems];
-#pragma unroll
-      for (int j = 0; j < kItems; ++j) {
-        const int i = warp_base + j * 32 + lane;
-        const bool valid = i < n;
-        const unsigned dgt = (k[j] >> shift) & 0xffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? dgt : 0x100u);
-        const unsigned lower = peers & ((1u << lane) - 1u);
-        unsigned prev = 0;
-        if (valid) prev = s_whist[warp][dgt];
-        __syncwarp();
-        rank[j] = prev + __popc(lower);
-        if (valid && lower == 0u) s_whist[warp][dgt] = prev + __popc(peers);
-        __syncwarp();
-      }
+      warp_ranks(k, warp_base, shift, rank);
       __syncthreads();
       {
         const int d = threadIdx.x;
@@ -414,12 +444,8 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
         if (i < n) {
           const unsigned dgt = (k[j] >> shift) & 0xffu;
           const unsigned dst = s_whist[warp][dgt] + rank[j];
-          if (!last) {
-            kout[dst] = k[j];
-            atomicAdd(&hist_next[(size_t)(dst / kTile) * kRadix + ((k[j] >> (shift + 8)) & 0xffu)], 1u);
-          } else {
-            rank_of[v[j]] = (int)dst;
-          }
+          if (!last) kout[dst] = k[j];
+          else rank_of[v[j]] = (int)dst;
           vout[dst] = v[j];
         }
       }

@@ -243,6 +243,12 @@ int gb_mvp_compute_aabb(int N, int K, const float* primpos, const float* primrot
                         const int32_t* sortedobjid, const int32_t* nodechildren, const int32_t* nodeparent,
                         float* nodeaabb, void* workspace, void* stream);
 
+/* forward march formulation for algo 0 without the shadow splat: 0 = lane-compacted sampling queue (default: inside-the-box
+ * (ray, primitive) pairs are enqueued, sampled 32 at a time with every lane busy, applied in the original order), 1 = the
+ * per-primitive formulation of round 1.  Identical outputs.  GOLIATH_B200_RAYMARCH=queue|legacy. */
+int gb_get_raymarch_mode(void);
+void gb_set_raymarch_mode(int mode);
+
 /* replaces mvpraymarchlib.raymarch_forward — mvpraymarch.cpp:179-283 -> mvpraymarch_kernel.cu:41-130.
  * template [N,K,TD,TH,TW,4] channels-last; warp [N,K,WD,WH,WW,3] or NULL (algo 0); rayrgba [N,H,W,4] out;
  * raysat [N,H,W,3] out or NULL; shadow [N,K,TD,TH,TW,2] accumulated or NULL.  The arguments the reference

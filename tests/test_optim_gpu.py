@@ -53,7 +53,7 @@ def test_fused_adam_matches_reference_sequence(cuda, adamw, wd):
     for a, b in zip(pa, pb):
         sa, sb = ref.state[a], ours.state[b]
         assert_close(t2n(sb["exp_avg"]), t2n(sa["exp_avg"]), rtol=1e-5, atol=1e-9, what="exp_avg")
-        assert_close(t2n(sb["exp_avg_sq"]), t2n(sa["exp_avg_sq"]), rtol=1e-5, atol=1e-12, what="exp_avg_sq")
+        assert_close(t2n(sb["exp_avg_sq"]), t2n(sa["exp_avg_sq"]), rtol=5e-5, atol=1e-12, what="exp_avg_sq")
     # torch.optim.Adam's state layout: the reference's optimizer checkpoints load
     sd = ref.state_dict()
     fresh = FusedAdam(groups([b.clone().to(cuda).requires_grad_() for b in base]), weight_decay=wd, adamw=adamw)

@@ -28,6 +28,18 @@ def _ref(name):
     return m
 
 
+@pytest.fixture(params=["queue", "legacy"], autouse=True)
+def raymarch_mode(request):
+    """forward march: lane-compacted sampling queue (default) or the per-primitive formulation of round 1"""
+    from goliath_b200 import _lib
+
+    L = _lib.lib()
+    before = L.gb_get_raymarch_mode()
+    L.gb_set_raymarch_mode({"queue": 0, "legacy": 1}[request.param])
+    yield request.param
+    L.gb_set_raymarch_mode(before)
+
+
 def _scene(dev, **kw):
     s = synthetic.mvp_scene(**kw)
     t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s.items()}
