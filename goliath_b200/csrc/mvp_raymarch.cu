@@ -604,6 +604,196 @@ __global__ void raymarch_bwd_kernel(RMArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ backward, lane-compacted (algo 0)
+// Same idea as raymarch_fwd_queue_kernel, four phases per flush:
+//   1 (lanes = items)  fade + trilinear sample of every queued (ray, primitive) pair
+//   2 (lanes = rays)   the ordered recurrence of PrimAccumAdditive::forwardbackward_prim (primaccum.h:81-98): each ray walks
+//                      its own items group by group, updates (rgba, sat) and leaves dL/d(sample) of every item in shared memory
+//   3 (lanes = items)  PrimSamplerTW::backward (primsampler.h:69-92): fade gradient, template-gradient REDs (one 16-byte RED per
+//                      trilinear corner), gradient of the local coordinate
+//   4 (lanes = items)  PrimTransfSRT::backward (primtransf.h:155-179): the 15 transform sums, reduced over runs of consecutive
+//                      items of the SAME primitive with a segmented shuffle scan, one RED per value and run
+// Per ray the arithmetic and its order are those of raymarch_bwd_kernel<false>; sums over the rays of a warp are re-associated
+// (different reduction tree), as they already are between the reference and round 1.
+struct RMQueueB {
+  float4 q[kQueue];   // y0.xyz, primitive id (bit-inverted for the clamped duplicate threads of an edge block)
+  float4 x[kQueue];   // xmt.xyz (sample position minus primitive centre), fade
+  float4 s[kQueue];   // sampled rgba, alpha already faded
+  float4 d[kQueue];   // dL/d(sample) rgba (alpha part before the fade factor)
+  unsigned g[kQueue];
+};
+
+__global__ void raymarch_bwd_queue_kernel(RMArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+  int* s_hit = reinterpret_cast<int*>(smem);
+  float2* s_ivl = reinterpret_cast<float2*>(smem + (size_t)nwarps * kMaxHit * sizeof(int));
+  RMQueueB* s_q = reinterpret_cast<RMQueueB*>(smem + (size_t)nwarps * kMaxHit * (sizeof(int) + sizeof(float2)));
+  RaySetup r = setup_ray(a, s_hit, s_ivl);
+  const unsigned full = 0xffffffffu;
+  const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+  RMQueueB& Q = s_q[(threadIdx.y * blockDim.x + threadIdx.x) >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  const size_t tsz = (size_t)a.TD * a.TH * a.TW;
+  const float stepsize = a.stepsize;
+  const size_t o = ((size_t)r.n * a.H + r.h) * a.W + r.w;
+  const float4* tbase = a.tplate + (size_t)r.n * a.K * tsz;
+  float* gtbase = a.grad_tplate + (size_t)r.n * a.K * 4 * tsz;
+
+  float4 rgba = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 dL = a.grad_rayrgba[o];
+  const float3 raysat = ld3(a.raysat + 3 * o);
+  const bool hs = raysat.x > -1.f;
+  const float4 ref = hs ? make_float4(raysat.x, raysat.y, raysat.z, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  bool sat = false;
+  float t = r.t;
+  float3 pos = r.pos;
+  const bool live0 = (t < r.rtmax + 1e-5f);
+  float tlo = warp_min(live0 ? t : INFINITY), thi = warp_max(live0 ? t : -INFINITY);
+  const float margin = 2.f * stepsize + 1e-3f;
+  int qn = 0, ng = 0;
+
+  auto flush = [&]() {
+    __syncwarp();
+    for (int base = 0; base < qn; base += 32) {  // phase 1
+      const int i = base + lane;
+      if (i < qn) {
+        const float4 it = Q.q[i];
+        const float3 y0 = make_float3(it.x, it.y, it.z);
+        const int kv = __float_as_int(it.w), k = kv < 0 ? ~kv : kv;
+        const float fade = __expf(-a.fadescale * (__powf(fabsf(y0.x), a.fadeexp) + __powf(fabsf(y0.y), a.fadeexp) +
+                                                  __powf(fabsf(y0.z), a.fadeexp)));
+        float4 sv = sample4(a.TD, a.TH, a.TW, tbase + (size_t)k * tsz, y0);
+        sv.w *= fade;
+        Q.s[i] = sv;
+        Q.x[i].w = fade;
+      }
+    }
+    __syncwarp();
+    int off = 0;
+    for (int g = 0; g < ng; ++g) {  // phase 2
+      const unsigned m = Q.g[g];
+      if ((m >> lane) & 1u) {
+        const int i = off + __popc(m & lt);
+        float4 dLs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!sat) {
+          const float4 sv = Q.s[i];
+          const float aw = sv.w * stepsize;
+          const bool thissat = rgba.w + aw >= 1.f;
+          sat = sat || thissat;
+          const float weight = sat ? (1.f - rgba.w) : aw;
+          dLs.x = weight * dL.x; dLs.y = weight * dL.y; dLs.z = weight * dL.z;
+          dLs.w = sat ? 0.f
+                      : stepsize * ((sv.x - ref.x) * dL.x + (sv.y - ref.y) * dL.y + (sv.z - ref.z) * dL.z + (1.f - ref.w) * dL.w);
+          rgba.x += sv.x * weight; rgba.y += sv.y * weight; rgba.z += sv.z * weight; rgba.w += 1.f * weight;
+        }
+        Q.d[i] = dLs;
+      }
+      off += __popc(m);
+    }
+    __syncwarp();
+    for (int base = 0; base < qn; base += 32) {  // phases 3 and 4
+      const int i = base + lane;
+      const bool act = i < qn;
+      int kv = -1 - 0x7fffffff;  // never equal to a real id
+      float v[15];
+#pragma unroll
+      for (int c = 0; c < 15; ++c) v[c] = 0.f;
+      if (act) {
+        const float4 it = Q.q[i];
+        kv = __float_as_int(it.w);
+        const bool valid = kv >= 0;
+        const int k = valid ? kv : ~kv;
+        kv = k;  // runs are formed on the primitive id alone
+        const float4 dl = Q.d[i];
+        if (valid && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f)) {
+          const float3 y0 = make_float3(it.x, it.y, it.z);
+          const float4 xm = Q.x[i];
+          const float4 sv = Q.s[i];
+          float3 dfade = make_float3(__powf(fabsf(y0.x), a.fadeexp - 1.f) * (y0.x > 0.f ? 1.f : -1.f),
+                                     __powf(fabsf(y0.y), a.fadeexp - 1.f) * (y0.y > 0.f ? 1.f : -1.f),
+                                     __powf(fabsf(y0.z), a.fadeexp - 1.f) * (y0.z > 0.f ? 1.f : -1.f));
+          dfade = dfade * (-(a.fadescale * a.fadeexp));
+          float3 dLy0 = dfade * sv.w * dl.w;
+          const float4 gs = make_float4(dl.x, dl.y, dl.z, dl.w * xm.w);
+          const float3 dLy1 = sample4_bwd(a.TD, a.TH, a.TW, tbase + (size_t)k * tsz, gtbase + (size_t)k * 4 * tsz, y0, gs, true);
+          dLy0 = dLy0 + dLy1;
+          const float3 xmt = make_float3(xm.x, xm.y, xm.z);
+          const float3 pr0 = ld3(r.pr + 9 * (size_t)k), pr1 = ld3(r.pr + 9 * (size_t)k + 3), pr2 = ld3(r.pr + 9 * (size_t)k + 6);
+          const float3 ps = ld3(r.ps + 3 * (size_t)k);
+          const float3 rxmt = pr0 * xmt.x + pr1 * xmt.y + pr2 * xmt.z;
+          const float3 gsc = rxmt * dLy0;
+          const float3 d = dLy0 * ps;
+          v[0] = -dot3(pr0, d); v[1] = -dot3(pr1, d); v[2] = -dot3(pr2, d);
+          v[3] = xmt.x * d.x; v[4] = xmt.x * d.y; v[5] = xmt.x * d.z;
+          v[6] = xmt.y * d.x; v[7] = xmt.y * d.y; v[8] = xmt.y * d.z;
+          v[9] = xmt.z * d.x; v[10] = xmt.z * d.y; v[11] = xmt.z * d.z;
+          v[12] = gsc.x; v[13] = gsc.y; v[14] = gsc.z;
+        }
+      }
+      // segmented inclusive scan over runs of equal primitive id; the last lane of a run adds the run's sums
+      const int kprev = __shfl_up_sync(full, kv, 1);
+      const bool head = (lane == 0) || (kprev != kv);
+      const unsigned hm = __ballot_sync(full, head);
+      const int myhead = 31 - __clz(hm & (lt | (1u << lane)));
+      const int dist = lane - myhead;
+#pragma unroll
+      for (int sh = 1; sh < 32; sh <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 15; ++c) {
+          const float up = __shfl_up_sync(full, v[c], sh);
+          if (dist >= sh) v[c] += up;
+        }
+      }
+      const bool tail = act && (lane == 31 || ((hm >> (lane + 1)) & 1u));
+      if (tail) {
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) any = any || (v[c] != 0.f);
+        if (any) {
+          const size_t nk = (size_t)r.n * a.K + kv;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) gb::red_add(a.grad_primpos + nk * 3 + c, v[c]);
+#pragma unroll
+          for (int c = 0; c < 9; ++c) gb::red_add(a.grad_primrot + nk * 9 + c, v[3 + c]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) gb::red_add(a.grad_primscale + nk * 3 + c, v[12 + c]);
+        }
+      }
+    }
+    qn = 0;
+    ng = 0;
+    __syncwarp();
+  };
+
+  while (__any_sync(full, (t < r.rtmax + 1e-5f) && !sat)) {
+    for (int ks = 0; ks < r.nhit; ++ks) {
+      const float2 iv = r.ivl[ks];
+      if (thi + margin < iv.x || tlo - margin > iv.y) continue;
+      const int k = r.hit[ks];
+      const Local L = prim_local(r, k, pos);
+      const bool in = inside_unit(L.y0) && !sat && t < r.rtmax + 1e-5f;
+      const unsigned m = __ballot_sync(full, in);
+      if (m == 0u) continue;
+      if (in) {
+        const int i = qn + __popc(m & lt);
+        Q.q[i] = make_float4(L.y0.x, L.y0.y, L.y0.z, __int_as_float(r.validthread ? k : ~k));
+        Q.x[i] = make_float4(L.xmt.x, L.xmt.y, L.xmt.z, 0.f);
+      }
+      if (lane == 0) Q.g[ng] = m;
+      qn += __popc(m);
+      ++ng;
+      if (qn >= 32) flush();
+    }
+    t += stepsize;
+    pos = pos + r.raydir * stepsize;
+    tlo += stepsize;
+    thi += stepsize;
+    if (qn >= 16) flush();
+  }
+  flush();
+}
+
 // ------------------------------------------------------------------ BVH bounds (any binary tree, Karras bottom-up)
 __global__ void __launch_bounds__(256) compute_aabb_kernel(int N, int K, const float* __restrict__ primpos,
                                                            const float* __restrict__ primrot,
@@ -646,11 +836,15 @@ __global__ void __launch_bounds__(256) compute_aabb_kernel(int N, int K, const f
   }
 }
 
-int g_raymarch_mode = -1;  // 0: lane-compacted sampling queue (forward, algo 0, no shadow), 1: round-1 kernels everywhere
+// bit 0: lane-compacted sampling queue in the forward march, bit 1: in the backward march (algo 0, no shadow splat).
+// Default 0 = the per-primitive kernels: measured on B200 (profiles/r02_bench_hand_mvp*.json) the queue forward is SLOWER
+// (6.0 vs 5.0 ms at config 4, 17.3 vs 15.8 ms at config 5) — the march is bound by dependent-load latency (BVH walk,
+// template corners), not by issue slots, and the queue adds shared-memory round trips per group.  Kept as a tested option.
+int g_raymarch_mode = -1;
 int raymarch_mode() {
   if (g_raymarch_mode < 0) {
     const char* e = getenv("GOLIATH_B200_RAYMARCH");
-    g_raymarch_mode = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+    g_raymarch_mode = !e ? 0 : strcmp(e, "queue") == 0 ? 3 : strcmp(e, "queue-fwd") == 0 ? 1 : strcmp(e, "queue-bwd") == 0 ? 2 : 0;
   }
   return g_raymarch_mode;
 }
@@ -665,9 +859,10 @@ int fill_and_launch_check(const RMArgs& a, int bx, int by) {
 
 }  // namespace
 
-// 0 = lane-compacted sampling in the forward march (default), 1 = the round-1 kernel; identical outputs (A/B, tests).
+// bit 0 / bit 1: lane-compacted sampling queue in the forward / backward march (default 0: per-primitive kernels);
+// rays identical, transform gradients to re-association (A/B, tests).
 GB_API int gb_get_raymarch_mode(void) { return raymarch_mode(); }
-GB_API void gb_set_raymarch_mode(int mode) { g_raymarch_mode = mode ? 1 : 0; }
+GB_API void gb_set_raymarch_mode(int mode) { g_raymarch_mode = mode & 3; }
 
 // scratch for gb_mvp_compute_aabb: N*(K-1) int flags (zeroed by the call itself)
 GB_API size_t gb_mvp_aabb_workspace_bytes(int N, int K) { return (size_t)N * (K > 1 ? K - 1 : 1) * sizeof(int); }
@@ -720,7 +915,7 @@ GB_API int gb_mvp_raymarch_fwd(int N, int H, int W, int K, const float* raypos, 
   } while (0)
   if (algo == 1) { if (shadow) GB_RM_FWD(true, true); else GB_RM_FWD(true, false); }
   else if (shadow) GB_RM_FWD(false, true);
-  else if (raymarch_mode() == 0) {  // lane-compacted sampling (default for algo 0 without the shadow splat)
+  else if (raymarch_mode() & 1) {  // lane-compacted sampling (option, algo 0 without the shadow splat)
     const size_t smem_q = smem + (size_t)nwarps * sizeof(RMQueue);
     if (smem_q > 48 * 1024)
       GB_CUDA(cudaFuncSetAttribute(raymarch_fwd_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
@@ -762,6 +957,11 @@ GB_API int gb_mvp_raymarch_bwd(int N, int H, int W, int K, const float* raypos, 
     if (smem > 48 * 1024)
       GB_CUDA(cudaFuncSetAttribute(raymarch_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     raymarch_bwd_kernel<true><<<grid, block, smem, s>>>(a);
+  } else if (raymarch_mode() & 2) {  // lane-compacted backward (option, algo 0)
+    const size_t smem_q = smem + (size_t)nwarps * sizeof(RMQueueB);
+    if (smem_q > 48 * 1024)
+      GB_CUDA(cudaFuncSetAttribute(raymarch_bwd_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    raymarch_bwd_queue_kernel<<<grid, block, smem_q, s>>>(a);
   } else {
     if (smem > 48 * 1024)
       GB_CUDA(cudaFuncSetAttribute(raymarch_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -199,18 +199,38 @@ def render_views_shared(width: int, height: int, Rt: torch.Tensor, geom: Dict[st
     colors [V,C,G,3]; Rt [V,3,4]; intrinsics_host: V tuples (fx, fy, cx, cy).  Returns rgb [V,C,3,H,W] (a permuted view
     of the blended [V,C,H,W,3], as the reference returns `out_color.permute(2,0,1)`), alpha [V,1,H,W] (detached, as
     rgca.py:137), depth [V,1,H,W] = blended depth / alpha.clamp(0.05, 1)."""
+    from ..render import _nullctx, view_streams
+
     V = Rt.shape[0]
     bg = torch.zeros(3, device=Rt.device) if background is None else background
     rgbs: List[torch.Tensor] = []
     alphas: List[torch.Tensor] = []
     depths: List[torch.Tensor] = []
+    # independent views on a small pool of side streams (see render.render_views): their kernels overlap on the device
+    pool = view_streams(Rt.device, V) if (capacity is not None and V > 1) else None
+    main = torch.cuda.current_stream(Rt.device) if pool else None
+    def per_view(x, last):  # views with a view / stack backward (`x[v]` would zero-fill a full-batch gradient per field)
+        return [x.reshape(-1, last)] if V == 1 else [t.reshape(-1, last) for t in torch.unbind(x, 0)]
+    gp, gs, gq, go = (per_view(geom["primpos"], 3), per_view(geom["primscale"], 3), per_view(geom["primqvec"], 4),
+                      per_view(geom["opacity"], 1))
+    cols = [colors.reshape(colors.shape[1:])] if V == 1 else list(torch.unbind(colors, 0))
     for v in range(V):
         fx, fy, cx, cy = intrinsics_host[v]
-        rgb, depth_raw, alpha, _ = render_shared(
-            geom["primpos"][v].reshape(-1, 3), geom["primscale"][v].reshape(-1, 3), 1.0, geom["primqvec"][v].reshape(-1, 4),
-            Rt[v], fx, fy, cx, cy, height, width, geom["opacity"][v].reshape(-1, 1), colors[v], bg, 0.1, capacity)
-        a = alpha.detach()
+        side = pool[v % len(pool)] if pool else None
+        if side is not None and v < len(pool):
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else _nullctx()):
+            rgb, depth_raw, alpha, _ = render_shared(gp[v], gs[v], 1.0, gq[v], Rt[v], fx, fy, cx, cy, height, width, go[v], cols[v],
+                                                     bg, 0.1, capacity)
+            a = alpha.detach()
+            dep = depth_raw / a.clamp(0.05, 1.0)
+        if side is not None:
+            for t_ in (rgb, a, dep):
+                t_.record_stream(main)
         rgbs.append(rgb)
         alphas.append(a[None])
-        depths.append((depth_raw / a.clamp(0.05, 1.0))[None])
+        depths.append(dep[None])
+    if pool:
+        for side in pool[:min(V, len(pool))]:
+            main.wait_stream(side)
     return torch.stack(rgbs).permute(0, 1, 4, 2, 3), torch.stack(alphas), torch.stack(depths)

@@ -243,9 +243,10 @@ int gb_mvp_compute_aabb(int N, int K, const float* primpos, const float* primrot
                         const int32_t* sortedobjid, const int32_t* nodechildren, const int32_t* nodeparent,
                         float* nodeaabb, void* workspace, void* stream);
 
-/* forward march formulation for algo 0 without the shadow splat: 0 = lane-compacted sampling queue (default: inside-the-box
- * (ray, primitive) pairs are enqueued, sampled 32 at a time with every lane busy, applied in the original order), 1 = the
- * per-primitive formulation of round 1.  Identical outputs.  GOLIATH_B200_RAYMARCH=queue|legacy. */
+/* march formulation for algo 0 without the shadow splat: bit 0 / bit 1 = lane-compacted sampling queue in the forward /
+ * backward march (inside-the-box (ray, primitive) pairs are enqueued, sampled 32 at a time with every lane busy, applied in
+ * the original order); 0 (default) = the per-primitive kernels, which measured faster on B200.
+ * GOLIATH_B200_RAYMARCH=legacy|queue-fwd|queue-bwd|queue. */
 int gb_get_raymarch_mode(void);
 void gb_set_raymarch_mode(int mode);
 

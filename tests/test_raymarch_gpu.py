@@ -28,14 +28,14 @@ def _ref(name):
     return m
 
 
-@pytest.fixture(params=["queue", "legacy"], autouse=True)
+@pytest.fixture(params=["legacy", "queue"], autouse=True)
 def raymarch_mode(request):
-    """forward march: lane-compacted sampling queue (default) or the per-primitive formulation of round 1"""
+    """march formulation: per-primitive kernels (default) or the lane-compacted sampling queue, forward and backward"""
     from goliath_b200 import _lib
 
     L = _lib.lib()
     before = L.gb_get_raymarch_mode()
-    L.gb_set_raymarch_mode({"queue": 0, "legacy": 1}[request.param])
+    L.gb_set_raymarch_mode({"legacy": 0, "queue": 3}[request.param])
     yield request.param
     L.gb_set_raymarch_mode(before)
 
