@@ -693,7 +693,9 @@ def run_ours(args):
                                       ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
                                                                                       ", step captured in a CUDA graph"))),
                         "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
-                        "rank_sort": ["cooperative (one launch, varying key bits only)", "4 radix passes"][int(lib.gb_get_rank_sort_mode())],
+                        "rank_sort": ["cooperative LSD (one launch, varying key bits only)", "4 radix passes",
+                                      "2048 key buckets + in-bucket ranking (cooperative LSD fallback)"][int(lib.gb_get_rank_sort_mode())],
+                        "tile_sort": ["bitmap sort per tile + grid-wide record gather", "one kernel per tile"][int(lib.gb_get_tile_sort_mode())],
                         "blend": ["batch (CTA-synchronous)", "pipe (warp-decoupled)", "affine (warp-decoupled, SM-affine "
                                   "tile schedule)", "mom (exact cull, 4-hit ILP forward, transposed-reduction backward)",
                                   "mom-affine (mom over the SM-affine tile schedule)"][int(lib.gb_get_blend_mode())],

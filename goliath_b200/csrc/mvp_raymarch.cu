@@ -837,14 +837,15 @@ __global__ void __launch_bounds__(256) compute_aabb_kernel(int N, int K, const f
 }
 
 // bit 0: lane-compacted sampling queue in the forward march, bit 1: in the backward march (algo 0, no shadow splat).
-// Default 0 = the per-primitive kernels: measured on B200 (profiles/r02_bench_hand_mvp*.json) the queue forward is SLOWER
-// (6.0 vs 5.0 ms at config 4, 17.3 vs 15.8 ms at config 5) — the march is bound by dependent-load latency (BVH walk,
-// template corners), not by issue slots, and the queue adds shared-memory round trips per group.  Kept as a tested option.
+// Default 2 = queue in the BACKWARD only, from measurement on B200 (profiles/r02_bench_hand_mvp*.json): the backward, whose
+// per-item block carries the template-gradient REDs and the fade / position gradients, gains (9.9 -> 8.3 ms at config 4);
+// the forward is SLOWER with the queue (6.0 vs 5.0 ms at config 4, 17.3 vs 15.8 ms at config 5) — it is bound by
+// dependent-load latency (BVH walk, template corners), not by issue slots, and the queue adds shared-memory round trips.
 int g_raymarch_mode = -1;
 int raymarch_mode() {
   if (g_raymarch_mode < 0) {
     const char* e = getenv("GOLIATH_B200_RAYMARCH");
-    g_raymarch_mode = !e ? 0 : strcmp(e, "queue") == 0 ? 3 : strcmp(e, "queue-fwd") == 0 ? 1 : strcmp(e, "queue-bwd") == 0 ? 2 : 0;
+    g_raymarch_mode = !e ? 2 : strcmp(e, "queue") == 0 ? 3 : strcmp(e, "queue-fwd") == 0 ? 1 : strcmp(e, "queue-bwd") == 0 ? 2 : 0;
   }
   return g_raymarch_mode;
 }
@@ -859,7 +860,7 @@ int fill_and_launch_check(const RMArgs& a, int bx, int by) {
 
 }  // namespace
 
-// bit 0 / bit 1: lane-compacted sampling queue in the forward / backward march (default 0: per-primitive kernels);
+// bit 0 / bit 1: lane-compacted sampling queue in the forward / backward march (default 2: backward only);
 // rays identical, transform gradients to re-association (A/B, tests).
 GB_API int gb_get_raymarch_mode(void) { return raymarch_mode(); }
 GB_API void gb_set_raymarch_mode(int mode) { g_raymarch_mode = mode & 3; }

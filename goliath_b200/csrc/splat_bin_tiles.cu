@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const fl
   constexpr int kItems = kTileKeys / kGaussBlock;
   extern __shared__ int s_cnt[];
   __shared__ unsigned s_hist[kRadix];
-  __shared__ unsigned s_or, s_orc;
-  if (threadIdx.x == 0) s_or = s_orc = 0u;
+  __shared__ unsigned s_or, s_orc, s_max, s_maxc;
+  if (threadIdx.x == 0) s_or = s_orc = s_max = s_maxc = 0u;
   if (threadIdx.x < kRadix) s_hist[threadIdx.x] = 0;
   for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) s_cnt[t] = 0;
   const int base = blockIdx.x * kTileKeys;
@@ -133,14 +133,18 @@ __global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const fl
   }
   {  // OR of the VISIBLE keys and of their complements: a bit set in both differs between two visible keys, and the
      // rank sort only has to order those bits (culled Gaussians never reach a tile, where their rank lands is irrelevant)
-    unsigned o = 0u, oc = 0u;
+    unsigned o = 0u, oc = 0u, mx = 0u, mxc = 0u;  // mxc = max of the complements = ~min
 #pragma unroll
     for (int j = 0; j < kItems; ++j)
-      if (r[j] > 0) { o |= k[j]; oc |= ~k[j]; }
+      if (r[j] > 0) { o |= k[j]; oc |= ~k[j]; mx = max(mx, k[j]); mxc = max(mxc, ~k[j]); }
     o = __reduce_or_sync(0xffffffffu, o);
     oc = __reduce_or_sync(0xffffffffu, oc);
-    __syncthreads();  // s_or / s_orc initialised
-    if ((threadIdx.x & 31) == 0 && (o | oc)) { atomicOr(&s_or, o); atomicOr(&s_orc, oc); }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    mxc = __reduce_max_sync(0xffffffffu, mxc);
+    __syncthreads();  // the shared accumulators are initialised
+    if ((threadIdx.x & 31) == 0 && (o | oc)) {
+      atomicOr(&s_or, o); atomicOr(&s_orc, oc); atomicMax(&s_max, mx); atomicMax(&s_maxc, mxc);
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -160,7 +164,10 @@ __global__ void __launch_bounds__(kGaussBlock) depth_keys_kernel(int G, const fl
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && (s_or | s_orc)) { atomicOr(key_bits, s_or); atomicOr(key_bits + 1, s_orc); }
+  if (threadIdx.x == 0 && (s_or | s_orc)) {
+    atomicOr(key_bits, s_or); atomicOr(key_bits + 1, s_orc);
+    atomicMax(key_bits + 4, s_max); atomicMax(key_bits + 5, s_maxc);  // [4] = max visible key, [5] = ~min visible key
+  }
   if (threadIdx.x < kRadix) hist0[(size_t)blockIdx.x * kRadix + threadIdx.x] = s_hist[threadIdx.x];
   for (int t = threadIdx.x; t < smem_tiles; t += kGaussBlock) {
     const int cnt = s_cnt[t];
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
   __shared__ int s_scan[33];
   __shared__ uint4 s_part[2][4][kRadix / 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (key_bits[7] && !key_bits[6]) return;  // launched as the fallback of the bucket ranking, which did the job
   const unsigned diff = key_bits[0] & key_bits[1];  // written by depth_keys_kernel (previous launch): plain loads
   const int bits = diff ? 32 - __clz(diff) : 0;
   const int passes = (bits + 7) >> 3;  // 0 .. 4
@@ -452,6 +460,143 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
       __syncthreads();  // shared tables are reused by the next tile of this CTA
     }
     if (!last) grid_barrier(barrier, bar_target);
+  }
+}
+
+// ------------------------------------------------------------------ 2c. depth ranks by buckets (default)
+// The cooperative LSD sort above is latency-bound: 147 CTAs of 8 warps walk 3 passes of dependent L2 round trips and
+// grid barriers (ncu: 6 % issue-active, 44 us for 300 k keys).  The ranks only have to order the VISIBLE Gaussians
+// by (depth bits, id), so: (1) the visible keys are dealt into 2048 buckets that split [min key, max key] evenly
+// (monotone in the key: bucket order == depth order), counts privatised per CTA; (2) one CTA scans the counts;
+// (3) the (key, id) pairs are scattered into their bucket (slots claimed per CTA, order inside a bucket arbitrary);
+// (4) one CTA per bucket ranks its ~150 pairs against each other in shared memory (n^2 compares on (key, id): exact,
+// ties by id).  Independent kernels with a handful of round trips each instead of a 3-pass dependency chain.  A bucket
+// larger than kBucketCap (degenerate depth distributions, e.g. every depth equal) raises a device flag: the bucket
+// kernels then do nothing and the cooperative LSD sort, launched behind them, takes over (otherwise it exits at once).
+constexpr int kBuckets = 2048;
+constexpr int kBucketCap = 2048;   // pairs of one bucket held in shared memory (16 KB)
+constexpr int kBucketThreads = 128;
+
+__device__ __forceinline__ int bucket_of(unsigned key, unsigned kmin, unsigned long long range) {
+  return (int)(((unsigned long long)(key - kmin) * (unsigned long long)kBuckets) / range);
+}
+
+template <int kTileKeys>
+__global__ void __launch_bounds__(kGaussBlock) rank_bucket_count_kernel(int G, const unsigned* __restrict__ keys,
+                                                                        const int* __restrict__ radii,
+                                                                        const unsigned* __restrict__ key_bits,
+                                                                        int* __restrict__ bcount) {
+  constexpr int kItems = kTileKeys / kGaussBlock;
+  __shared__ int s_cnt[kBuckets];
+  for (int t = threadIdx.x; t < kBuckets; t += kGaussBlock) s_cnt[t] = 0;
+  const unsigned kmax = key_bits[4], kmin = ~key_bits[5];
+  const unsigned long long range = (unsigned long long)(kmax - kmin) + 1ull;
+  __syncthreads();
+  const int base = blockIdx.x * kTileKeys;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = base + j * kGaussBlock + threadIdx.x;
+    if (i < G && radii[i] > 0) atomicAdd(&s_cnt[bucket_of(keys[i], kmin, range)], 1);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kBuckets; t += kGaussBlock) {
+    const int c = s_cnt[t];
+    if (c) atomicAdd(&bcount[t], c);
+  }
+}
+
+__global__ void __launch_bounds__(1024) rank_bucket_scan_kernel(const int* __restrict__ bcount, int* __restrict__ boffset,
+                                                                int* __restrict__ bcursor, unsigned* __restrict__ flags) {
+  __shared__ int s_warp[33];
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  int carry = 0;
+  for (int base = 0; base < kBuckets; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = bcount[i];
+    int total;
+    const int ex = block_exclusive_scan(v, s_warp, total);
+    boffset[i] = carry + ex;
+    bcursor[i] = 0;
+    atomicMax(&s_max, v);
+    carry += total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flags[6] = (s_max > kBucketCap) ? 1u : 0u;  // 1: the cooperative LSD sort must do the ranking
+}
+
+template <int kTileKeys>
+__global__ void __launch_bounds__(kGaussBlock) rank_bucket_scatter_kernel(int G, const unsigned* __restrict__ keys,
+                                                                          const int* __restrict__ radii,
+                                                                          const unsigned* __restrict__ key_bits,
+                                                                          const int* __restrict__ boffset,
+                                                                          int* __restrict__ bcursor,
+                                                                          unsigned* __restrict__ pair_keys,
+                                                                          int* __restrict__ pair_ids) {
+  constexpr int kItems = kTileKeys / kGaussBlock;
+  __shared__ int s_cnt[kBuckets];
+  __shared__ int s_base[kBuckets];
+  if (key_bits[6]) return;  // fallback path active
+  for (int t = threadIdx.x; t < kBuckets; t += kGaussBlock) s_cnt[t] = 0;
+  const unsigned kmax = key_bits[4], kmin = ~key_bits[5];
+  const unsigned long long range = (unsigned long long)(kmax - kmin) + 1ull;
+  __syncthreads();
+  const int base = blockIdx.x * kTileKeys;
+  unsigned k[kItems];
+  int b[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int i = base + j * kGaussBlock + threadIdx.x;
+    b[j] = -1;
+    if (i < G && radii[i] > 0) {
+      k[j] = keys[i];
+      b[j] = bucket_of(k[j], kmin, range);
+      atomicAdd(&s_cnt[b[j]], 1);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kBuckets; t += kGaussBlock) {
+    const int c = s_cnt[t];
+    s_base[t] = c ? boffset[t] + atomicAdd(&bcursor[t], c) : 0;
+    s_cnt[t] = 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    if (b[j] < 0) continue;
+    const int pos = s_base[b[j]] + atomicAdd(&s_cnt[b[j]], 1);
+    pair_keys[pos] = k[j];
+    pair_ids[pos] = base + j * kGaussBlock + threadIdx.x;
+  }
+}
+
+__global__ void __launch_bounds__(kBucketThreads) rank_bucket_sort_kernel(const int* __restrict__ bcount,
+                                                                          const int* __restrict__ boffset,
+                                                                          const unsigned* __restrict__ key_bits,
+                                                                          const unsigned* __restrict__ pair_keys,
+                                                                          const int* __restrict__ pair_ids,
+                                                                          int* __restrict__ rank_to_gid, int* __restrict__ rank_of) {
+  __shared__ unsigned s_k[kBucketCap];
+  __shared__ int s_id[kBucketCap];
+  if (key_bits[6]) return;
+  const int n = bcount[blockIdx.x], off = boffset[blockIdx.x];
+  if (n <= 0) return;
+  for (int i = threadIdx.x; i < n; i += kBucketThreads) {
+    s_k[i] = pair_keys[off + i];
+    s_id[i] = pair_ids[off + i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kBucketThreads) {
+    const unsigned ki = s_k[i];
+    const int idi = s_id[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {  // every lane reads the same s_k[j] / s_id[j]: shared-memory broadcasts
+      const unsigned kj = s_k[j];
+      r += (kj < ki || (kj == ki && s_id[j] < idi)) ? 1 : 0;
+    }
+    rank_to_gid[off + r] = idi;
+    rank_of[idi] = off + r;
   }
 }
 
@@ -675,7 +820,7 @@ __global__ void __launch_bounds__(256) gather_records_kernel(long long cap, cons
 }
 
 struct Layout {
-  size_t counts, hist, sync, zero_bytes, cursor, keys_a, keys_b, vals_a, vals_b, rank_to_gid, rank_of, rec_by_rank,
+  size_t counts, hist, buckets, sync, zero_bytes, cursor, keys_a, keys_b, vals_a, vals_b, rank_to_gid, rank_of, rec_by_rank,
       tile_ranks, total;
 };
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -687,6 +832,7 @@ inline Layout make_layout(int G, int T, int64_t cap) {
   size_t o = 0;
   l.counts = o; o += align256((size_t)T * 4);
   l.hist = o;   o += align256(ctas * kRadix * 4 * kRankPasses);
+  l.buckets = o; o += align256((size_t)3 * 2048 * 4);  // bucket ranking: counts | offsets | cursors
   l.sync = o;   o += 256;                 // [0..1]: OR of the visible keys / of their complements, [2]: grid-barrier counter
   l.zero_bytes = o;                       // [counts | hist | sync] are zeroed with one memset per call
   l.cursor = o; o += align256((size_t)T * 4);
@@ -711,11 +857,11 @@ int tile_sort_mode() {
   }
   return g_tile_sort_mode;
 }
-int g_rank_sort_mode = -1;
+int g_rank_sort_mode = -1;  // 0: cooperative LSD sort, 1: four separate radix passes (round 1), 2: bucket ranking (+ fallback)
 int rank_sort_mode() {
   if (g_rank_sort_mode < 0) {
     const char* e = getenv("GOLIATH_B200_RANKSORT");
-    g_rank_sort_mode = (e && strcmp(e, "passes") == 0) ? 1 : 0;
+    g_rank_sort_mode = !e ? 2 : strcmp(e, "passes") == 0 ? 1 : strcmp(e, "coop") == 0 ? 0 : 2;
   }
   return g_rank_sort_mode;
 }
@@ -734,16 +880,30 @@ int sm_count() {
 template <int kItems>
 int launch_rank_sort(int G, int ctas, const float* xys, const float* depths, const int32_t* radii, int tbx, int tby,
                      int block_width, int smem_tiles, unsigned* keys_a, unsigned* keys_b, int* vals_a, int* vals_b,
-                     unsigned* hist, int* counts, unsigned* sync, int* rank_to_gid, int* rank_of, cudaStream_t s) {
+                     unsigned* hist, int* counts, int* buckets, unsigned* sync, int* rank_to_gid, int* rank_of, cudaStream_t s) {
   const size_t hs = (size_t)ctas * kRadix;
   depth_keys_kernel<kRankBlock * kItems><<<ctas, kGaussBlock, (size_t)smem_tiles * 4, s>>>(
       G, (const float2*)xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, hist, counts, sync);
-  if (rank_sort_mode() == 0) {
+  const int mode = rank_sort_mode();
+  if (mode == 2) {  // bucket ranking
+    int* bcount = buckets;
+    int* boffset = bcount + kBuckets;
+    int* bcursor = boffset + kBuckets;
+    rank_bucket_count_kernel<kRankBlock * kItems><<<ctas, kGaussBlock, 0, s>>>(G, keys_a, radii, sync, bcount);
+    rank_bucket_scan_kernel<<<1, 1024, 0, s>>>(bcount, boffset, bcursor, sync);
+    rank_bucket_scatter_kernel<kRankBlock * kItems><<<ctas, kGaussBlock, 0, s>>>(G, keys_a, radii, sync, boffset, bcursor, keys_b,
+                                                                               vals_b);
+    rank_bucket_sort_kernel<<<kBuckets, kBucketThreads, 0, s>>>(bcount, boffset, sync, keys_b, vals_b, rank_to_gid, rank_of);
+    gb::count_launches(4);
+  }
+  if (mode == 0 || mode == 2) {
     int n = G, tiles = ctas;
     const unsigned* key_bits = sync;
     unsigned* barrier = sync + 2;
     void* args[] = {&n, &tiles, &keys_a, &keys_b, &vals_a, &vals_b, &hist, &key_bits, &barrier, &rank_to_gid, &rank_of};
     const int grid = ctas < sm_count() ? ctas : sm_count();  // one CTA per SM at most: co-resident by construction
+    // mode 2: sync[7] = 1 tells the cooperative kernel it is only the fallback (it exits unless sync[6] was raised)
+    if (mode == 2) GB_CUDA(cudaMemsetAsync(sync + 7, 0xff, 4, s));
     GB_CUDA(cudaLaunchCooperativeKernel((const void*)rank_sort_coop_kernel<kItems>, dim3(grid), dim3(kRankBlock), args, 0, s));
     gb::count_launches(2);
     return 0;
@@ -780,7 +940,7 @@ int opt_in_smem(K kernel, bool* done) {
 GB_API int gb_get_tile_sort_mode(void) { return tile_sort_mode(); }
 GB_API void gb_set_tile_sort_mode(int mode) { g_tile_sort_mode = mode ? 1 : 0; }
 GB_API int gb_get_rank_sort_mode(void) { return rank_sort_mode(); }
-GB_API void gb_set_rank_sort_mode(int mode) { g_rank_sort_mode = mode ? 1 : 0; }
+GB_API void gb_set_rank_sort_mode(int mode) { g_rank_sort_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 // 1 when gb_bin_tiles_pack supports G Gaussians (one tile's rank bitmap must fit in shared memory)
 GB_API int gb_bin_tiles_supported(int G) { return G >= 1 && ((size_t)gb::cdiv(G, 32) * 4 <= (size_t)kMaxBitmapBytes); }
@@ -833,9 +993,9 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   GB_CUDA(cudaMemsetAsync(ws, 0, l.zero_bytes, s));
   const int es = (items == 8)
                      ? launch_rank_sort<8>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b,
-                                           vals_a, vals_b, hist, counts, sync, rank_to_gid, rank_of, s)
+                                           vals_a, vals_b, hist, counts, (int*)(ws + l.buckets), sync, rank_to_gid, rank_of, s)
                      : launch_rank_sort<16>(G, ctas, xys, depths, radii, tbx, tby, block_width, smem_tiles, keys_a, keys_b,
-                                            vals_a, vals_b, hist, counts, sync, rank_to_gid, rank_of, s);
+                                            vals_a, vals_b, hist, counts, (int*)(ws + l.buckets), sync, rank_to_gid, rank_of, s);
   if (es) return es;
   int* n_total = n_out ? n_out : (int*)(sync + 3);  // the record gather below needs the count on the device
   tile_scan_kernel<<<1, 1024, 0, s>>>(T, (long long)cap, counts, (int2*)tile_bins, cursor, n_total, overflow);

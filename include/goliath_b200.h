@@ -161,8 +161,10 @@ int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* g
                              const float* conics, const float* colors3, const float* depths, const float* opacity,
                              const float* compensation, float* records, void* stream);
 
-/* depth-rank sort inside gb_bin_tiles_pack: 0 = one cooperative kernel sorting only the key bits that vary (default),
- * 1 = four radix passes as separate launches.  Identical outputs (A/B timing, tests).  GOLIATH_B200_RANKSORT=coop|passes. */
+/* depth ranks inside gb_bin_tiles_pack: 2 = 2048 key buckets + in-bucket ranking of the visible Gaussians (default; a
+ * device flag hands degenerate depth distributions to the cooperative sort), 0 = one cooperative LSD kernel over the key
+ * bits that vary, 1 = four radix passes as separate launches (round 1).  Identical outputs.
+ * GOLIATH_B200_RANKSORT=buckets|coop|passes. */
 int gb_get_rank_sort_mode(void);
 /* per-tile ordering inside gb_bin_tiles_pack: 0 = bitmap sort per tile + one grid-wide record gather (default), 1 = one
  * kernel per tile doing both (round 1).  Identical outputs.  GOLIATH_B200_TILESORT=split|fused. */
@@ -245,8 +247,8 @@ int gb_mvp_compute_aabb(int N, int K, const float* primpos, const float* primrot
 
 /* march formulation for algo 0 without the shadow splat: bit 0 / bit 1 = lane-compacted sampling queue in the forward /
  * backward march (inside-the-box (ray, primitive) pairs are enqueued, sampled 32 at a time with every lane busy, applied in
- * the original order); 0 (default) = the per-primitive kernels, which measured faster on B200.
- * GOLIATH_B200_RAYMARCH=legacy|queue-fwd|queue-bwd|queue. */
+ * the original order); default 2: the backward only (measured: backward 9.9 -> 8.3 ms at config 4, forward slower
+ * with the queue).  GOLIATH_B200_RAYMARCH=legacy|queue-fwd|queue-bwd|queue. */
 int gb_get_raymarch_mode(void);
 void gb_set_raymarch_mode(int mode);
 

@@ -516,17 +516,18 @@ def test_render_views_fused_matches_reference_sequence(cuda):
         assert_close(g1[k], g0[k], rtol=1e-4, atol=2e-5 * np.abs(g0[k]).max(), frac=0.999, what="grad " + k)
 
 
-@pytest.fixture(params=["coop+split", "passes+fused", "coop+fused"])
+@pytest.fixture(params=["buckets+split", "coop+split", "passes+fused", "buckets+fused"])
 def rank_sort(request):
-    """variants of the bucket binning: depth-rank sort as one cooperative kernel over the varying key bits (default) or
-    as the four radix passes of round 1; per-tile ordering as bitmap sort + grid-wide record gather (default) or as the
+    """variants of the bucket binning: depth ranks by 2048 key buckets + in-bucket ranking (default, cooperative LSD
+    fallback for degenerate depth distributions), as one cooperative LSD kernel over the varying key bits, or as the
+    four radix passes of round 1; per-tile ordering as bitmap sort + grid-wide record gather (default) or as the
     single per-tile kernel of round 1"""
     from goliath_b200 import _lib
 
     L = _lib.lib()
     before = (L.gb_get_rank_sort_mode(), L.gb_get_tile_sort_mode())
     rs, ts = request.param.split("+")
-    L.gb_set_rank_sort_mode({"coop": 0, "passes": 1}[rs])
+    L.gb_set_rank_sort_mode({"coop": 0, "passes": 1, "buckets": 2}[rs])
     L.gb_set_tile_sort_mode({"split": 0, "fused": 1}[ts])
     yield request.param
     L.gb_set_rank_sort_mode(before[0])
