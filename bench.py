@@ -160,7 +160,7 @@ def sample_clocks_stop(p, path):
     return out
 
 
-def kernel_roofline(dev, packed, cam, flush):
+def kernel_roofline(dev, packed, cam, flush, sm_mhz=None):
     """Time the blend kernels alone through the C ABI (CUDA events on the launch stream, L2 flushed between
     launches) and report achieved ALGORITHMIC bytes/s (SURVEY.md §8d formulas) against the measured HBM peak."""
     from goliath_b200 import _lib
@@ -275,18 +275,31 @@ def kernel_roofline(dev, packed, cam, flush):
             "ms": t_bin, "alg_bytes": bytes_bin, "gbs": bytes_bin / t_bin / 1e6},
     }
     dom = max((k for k in ks if k.startswith("blend")), key=lambda k: ks[k]["ms"])
-    # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the same scene
-    # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); not measurable live
-    traffic, ncu_note = None, None
-    try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][dom]
+    # DRAM bytes and warp instructions per launch of the dominant kernel come from the committed `ncu --set full`
+    # capture of the same scene (profiles/r02_traffic.json, written by scripts/ncu_summary.py traffic; neither is
+    # measurable live).  The blend is not HBM-bound at this operating point: the second figure is
+    # the bound that does apply, warp instructions / (SMs x 4 schedulers x SM clock x the live duration).
+    traffic, ncu_note, issue = None, None, None
+    for fname in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            caps = json.load(open(os.path.join(ROOT, "profiles", fname)))["kernels"]
+            cap = caps[dom]
+        except Exception:
+            continue
         traffic = cap["dram_bytes"]
-        # the blend is not HBM-bound at this operating point: what the same capture says binds it
         ncu_note = {k: cap[k] for k in ("issue_active_pct", "sm_cycles_active_over_elapsed", "top_stalls") if k in cap}
-    except Exception:
-        pass
+        ncu_note["capture"] = "profiles/" + fname
+        if cap.get("warp_inst") and sm_mhz:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
+            def slot_frac(k):
+                return caps[k]["warp_inst"] / (sms * 4 * sm_mhz * 1e6 * ks[k]["ms"] * 1e-3)
+
+            issue = {"warp_inst": int(cap["warp_inst"]), "sm_mhz": sm_mhz, "sms": sms, "frac": slot_frac(dom),
+                     "kernels": {k: slot_frac(k) for k in ks if k in caps and caps[k].get("warp_inst")}}
+        break
     roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": ks[dom]["gbs"] / peak, "traffic": traffic, "ncu": ncu_note, "peak_source": which, "intersections": int(I),
+            "frac": ks[dom]["gbs"] / peak, "traffic": traffic, "issue_slot": issue, "ncu": ncu_note, "peak_source": which, "intersections": int(I),
             "kernels": ks}
     return roof
 
@@ -659,7 +672,7 @@ def run_ours(args):
         overflow = check_overflow(dev)
     roof = cpu = dec = None
     if rank == 0 and wl.key == "head":
-        roof = kernel_roofline(dev, resident, wl.cam, flush)
+        roof = kernel_roofline(dev, resident, wl.cam, flush, (clocks or {}).get("sm_mhz"))
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args, steps=3, warmup=3)
             try:
@@ -1414,6 +1427,27 @@ def run_decoder_library(args):
         res["tower_vnocond_ms_library"] = timeit(lambda: tower(x))
         h5 = torch.randn(1, 16, 512, 512, device=dev)
         res["last_layer_ms_library"] = timeit(lambda: torch.nn.functional.conv_transpose2d(h5, ws[-1], None, 2, 1) + bs[-1][None])
+    # forward + backward (data, weight and untied-bias gradients), the training pass the SIMT backward of --decoder is
+    # compared with
+    for t in ws + bs:
+        t.requires_grad_(True)
+    xg = x.clone().requires_grad_(True)
+
+    def fwd_bwd():
+        out = tower(xg)
+        out.backward(torch.ones_like(out))
+        for t in ws + bs + [xg]:
+            t.grad = None
+
+    res["tower_vnocond_fwd_bwd_ms_library"] = timeit(fwd_bwd)
+    h5g = h5.clone().requires_grad_(True)
+
+    def last_fwd_bwd():
+        out = torch.nn.functional.conv_transpose2d(h5g, ws[-1], None, 2, 1) + bs[-1][None]
+        out.backward(torch.ones_like(out))
+        ws[-1].grad = bs[-1].grad = h5g.grad = None
+
+    res["last_layer_fwd_bwd_ms_library"] = timeit(last_fwd_bwd)
     print(json.dumps({"decoder_library": res}))
 
 

@@ -848,7 +848,9 @@ inline Layout make_layout(int G, int T, int64_t cap) {
   return l;
 }
 
-// 1: the four radix passes as separate launches (round 1), 0: one cooperative kernel (default).  GOLIATH_B200_RANKSORT=passes|coop
+// 1: the four radix passes as separate launches (round 1), 0: one cooperative kernel (default), 2: 2048 key buckets +
+// in-bucket n^2 ranking (measured slower: 65 us for the in-bucket pass at 300k, profiles/r02_launches_head_buckets.txt).
+// GOLIATH_B200_RANKSORT=passes|coop|buckets
 int g_tile_sort_mode = -1;  // 0: per-tile bitmap sort + grid-wide record gather (default), 1: one kernel per tile (round 1)
 int tile_sort_mode() {
   if (g_tile_sort_mode < 0) {
@@ -861,7 +863,7 @@ int g_rank_sort_mode = -1;  // 0: cooperative LSD sort, 1: four separate radix p
 int rank_sort_mode() {
   if (g_rank_sort_mode < 0) {
     const char* e = getenv("GOLIATH_B200_RANKSORT");
-    g_rank_sort_mode = !e ? 2 : strcmp(e, "passes") == 0 ? 1 : strcmp(e, "coop") == 0 ? 0 : 2;
+    g_rank_sort_mode = !e ? 0 : strcmp(e, "passes") == 0 ? 1 : strcmp(e, "buckets") == 0 ? 2 : 0;
   }
   return g_rank_sort_mode;
 }

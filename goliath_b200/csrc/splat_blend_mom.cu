@@ -27,6 +27,9 @@
 //
 // Stages are recycled as in the pipeline kernels (mbarrier ring, cp.async.bulk), but a warp has finished with a
 // stage as soon as it has culled it — the entries carry what phases A and B need.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "splat_blend_common.cuh"
 
@@ -48,6 +51,14 @@ constexpr float kCullMargin = 2e-3f;  // slack of the exact cull test (ex2.appro
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// __expf(-s) with flush-to-zero: ex2.approx of s * -log2(e) without the denormal range guard (3 instructions per hit).
+// Results differ from __expf only where the result is below 2^-126, i.e. alpha < 1/255: skipped either way.
+__device__ __forceinline__ float exp_neg(float s) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s * -1.4426950408889634f));
   return r;
 }
 
@@ -85,7 +96,12 @@ __device__ __forceinline__ Tile make_tile(int tile_id, int tbx) {
 }
 
 // ------------------------------------------------------------------ forward
-template <int C>
+// LIST = false: a round takes up to four hits of the current 32-record cull step (a step with 9 hits costs 3 rounds, 12 slots).
+// LIST = true : the warp first culls the whole stage (up to 128 records, four independent tests in flight) into a
+//               per-warp list of hit indices, then blends the list four entries per round (one LDS.128 fetches the four
+//               indices): rounds are full except the last one of a stage, and the mask walk (brev / flo / lop per hit
+//               on the uniform path) is gone.  Same per-pixel operations in the same order -> identical pixels.
+template <int C, bool LIST>
 __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
     int img_w, int img_h, int tbx, const int* order, int sched, const int2* __restrict__ tile_bins,
     const float4* __restrict__ rec, const float* __restrict__ background, float* __restrict__ final_Ts,
@@ -95,6 +111,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
   __shared__ __align__(8) unsigned long long s_empty[kFwdStages];
   __shared__ int s_ndone;  // pixel warps whose 32 pixels are saturated
   __shared__ int s_tile;
+  __shared__ __align__(16) int s_hits[LIST ? kPixelWarps : 1][LIST ? kStageRecs + 4 : 4];
 
   const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
   if (tr == 0) {
@@ -174,51 +191,105 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
     const float4* sr = s_rec[s];
     const int batch_start = range.x + b * kStageRecs;
     const int batch_size = min(kStageRecs, range.y - batch_start);
-    for (int c0 = 0; c0 < batch_size; c0 += 32) {
-      const int ti = c0 + lane;
-      bool hit = false;
-      if (ti < batch_size) hit = footprint_hit(sr[ti * 3], &sr[ti * 3 + 1], fx0, fx1, fy0, fy1);
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        // up to four hits per round: independent alphas, serial transmittance
-        int t[4];
-        bool live[4];
+    if (LIST) {
+      int* hl = s_hits[LIST ? warp : 0];
+      const unsigned lt = (1u << lane) - 1u;
+      int cnt = 0;
+#pragma unroll 4
+      for (int c0 = 0; c0 < batch_size; c0 += 32) {
+        const int ti = c0 + lane;
+        bool hit = false;
+        if (ti < batch_size) hit = footprint_hit(sr[ti * 3], &sr[ti * 3 + 1], fx0, fx1, fy0, fy1);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (hit) hl[cnt + __popc(mask & lt)] = ti;
+        cnt += __popc(mask);
+      }
+      __syncwarp();
+      for (int i0 = 0; i0 < cnt; i0 += 16) {  // saturation is polled every four rounds
+        const int i1 = min(i0 + 16, cnt);
+        for (int i = i0; i < i1; i += 4) {
+          const int4 e = *reinterpret_cast<const int4*>(hl + i);
+          bool live[4];
+          int t[4];
+          live[0] = true; live[1] = i + 1 < cnt; live[2] = i + 2 < cnt; live[3] = i + 3 < cnt;
+          t[0] = e.x; t[1] = live[1] ? e.y : e.x; t[2] = live[2] ? e.z : e.x; t[3] = live[3] ? e.w : e.x;
+          float alpha[4], sig[4];
+          float4 col[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          live[u] = mask != 0;
-          t[u] = live[u] ? c0 + __ffs(mask) - 1 : t[0];
-          mask &= mask - 1;  // 0 & anything == 0
-        }
-        float alpha[4], sig[4];
-        float4 col[4];
+          for (int u = 0; u < 4; ++u) {
+            const float4 q0 = sr[t[u] * 3], q1 = sr[t[u] * 3 + 1];
+            col[u] = sr[t[u] * 3 + 2];
+            const float dx = q0.x - px, dy = q0.y - py;
+            sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+            alpha[u] = fminf(kAlphaMaxFwd, q1.w * exp_neg(sig[u]));
+          }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 q0 = sr[t[u] * 3], q1 = sr[t[u] * 3 + 1];
-          col[u] = sr[t[u] * 3 + 2];
-          const float dx = q0.x - px, dy = q0.y - py;
-          sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
-          alpha[u] = fminf(kAlphaMaxFwd, q1.w * __expf(-sig[u]));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
-          const float next_T = T * (1.f - alpha[u]);
-          const bool stop = ok && (next_T <= kTEps);
-          const bool take = ok && !stop;
-          done = done || stop;
-          if (take) {
-            const float vis = alpha[u] * T;
-            acc[0] += col[u].x * vis;
-            acc[1] += col[u].y * vis;
-            acc[2] += col[u].z * vis;
-            if (C == 4) acc[3] += col[u].w * vis;
-            T = next_T;
-            cur_idx = batch_start + t[u];
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
+            const float next_T = T * (1.f - alpha[u]);
+            const bool stop = ok && (next_T <= kTEps);
+            const bool take = ok && !stop;
+            done = done || stop;
+            if (take) {
+              const float vis = alpha[u] * T;
+              acc[0] += col[u].x * vis;
+              acc[1] += col[u].y * vis;
+              acc[2] += col[u].z * vis;
+              if (C == 4) acc[3] += col[u].w * vis;
+              T = next_T;
+              cur_idx = batch_start + t[u];
+            }
           }
         }
+        if (__all_sync(0xffffffffu, done)) break;
       }
-      if (__all_sync(0xffffffffu, done)) break;
-    }
+    } else {
+    for (int c0 = 0; c0 < batch_size; c0 += 32) {
+        const int ti = c0 + lane;
+        bool hit = false;
+        if (ti < batch_size) hit = footprint_hit(sr[ti * 3], &sr[ti * 3 + 1], fx0, fx1, fy0, fy1);
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          // up to four hits per round: independent alphas, serial transmittance
+          int t[4];
+          bool live[4];
+  #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            live[u] = mask != 0;
+            t[u] = live[u] ? c0 + __ffs(mask) - 1 : t[0];
+            mask &= mask - 1;  // 0 & anything == 0
+          }
+          float alpha[4], sig[4];
+          float4 col[4];
+  #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 q0 = sr[t[u] * 3], q1 = sr[t[u] * 3 + 1];
+            col[u] = sr[t[u] * 3 + 2];
+            const float dx = q0.x - px, dy = q0.y - py;
+            sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+            alpha[u] = fminf(kAlphaMaxFwd, q1.w * __expf(-sig[u]));
+          }
+  #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
+            const float next_T = T * (1.f - alpha[u]);
+            const bool stop = ok && (next_T <= kTEps);
+            const bool take = ok && !stop;
+            done = done || stop;
+            if (take) {
+              const float vis = alpha[u] * T;
+              acc[0] += col[u].x * vis;
+              acc[1] += col[u].y * vis;
+              acc[2] += col[u].z * vis;
+              if (C == 4) acc[3] += col[u].w * vis;
+              T = next_T;
+              cur_idx = batch_start + t[u];
+            }
+          }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+      }
+  }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);
   }
@@ -280,14 +351,14 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
 
   const float T_final = inside ? final_Ts[pix] : 1.f;
   float T = T_final;
-  float buffer[4] = {0.f, 0.f, 0.f, 0.f};
+  float bufv = 0.f;  // (colour accumulated behind the current Gaussian) . v_out
   const int bin_final = inside ? final_idx[pix] : -1;
   float vo[4] = {0.f, 0.f, 0.f, 0.f};
   float voa = 0.f;
   if (inside) {
 #pragma unroll
     for (int c = 0; c < C; ++c) vo[c] = v_output[pix * C + c];
-    voa = v_output_alpha[pix];
+    voa = v_output_alpha ? v_output_alpha[pix] : 0.f;  // NULL = no gradient through alpha
   }
   VO[lane] = make_float4(vo[0], vo[1], vo[2], vo[3]);
   float bgdot = 0.f;
@@ -340,7 +411,7 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
         col[u] = E[(base + h) * 3 + 2];
         const float dx = a0.x - px, dy = a0.y - py;
         const float sigma = 0.5f * (a0.z * dx * dx + a1.x * dy * dy) + a0.w * dx * dy;
-        const float vis = __expf(-sigma);
+        const float vis = exp_neg(sigma);
         const float alpha = fminf(kAlphaMaxBwd, a1.y * vis);
         // pixels outside the image have bin_final = -1, padding entries have idx = INT_MAX
         const bool valid = (__float_as_int(a1.z) <= bin_final) && !(sigma < 0.f) && !(alpha < kAlphaMin);
@@ -352,15 +423,16 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
       for (int u = 0; u < 4; ++u) {
         // v_alpha = sum_c (c_c T' - buffer_c ra) v_out_c + T_final ra (v_out_alpha - bg.v_out) with T' = T ra:
         // the common factor ra is applied once
+        // sum_c (c_c T - buffer_c) v_out_c = T (c . v_out) - (buffer . v_out): only the SCALAR buffer . v_out is carried
+        // (buffer_c += c_c fac  =>  buffer . v_out += fac (c . v_out)); c . v_out is off the serial chain
         const float cc[4] = {col[u].x, col[u].y, col[u].z, col[u].w};
-        float v_alpha = tfc;
+        float cv = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) v_alpha += (cc[c] * T - buffer[c]) * vo[c];
-        v_alpha *= ra[u];
+        for (int c = 0; c < C; ++c) cv += cc[c] * vo[c];
+        const float v_alpha = ((cv * T - bufv) + tfc) * ra[u];
         T *= ra[u];
         const float fac = al[u] * T;
-#pragma unroll
-        for (int c = 0; c < C; ++c) buffer[c] += cc[c] * fac;
+        bufv += cv * fac;
         M[(h0 + u) * kMStride + lane] = make_float2(fac, -ov[u] * v_alpha);  // (fac, v_sigma); zeros when not valid
       }
     }
@@ -621,7 +693,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
           col[u][0] = sr[t[u] * kMRQ + 2]; col[u][1] = sr[t[u] * kMRQ + 3]; col[u][2] = sr[t[u] * kMRQ + 4];
           const float dx = q0.x - px, dy = q0.y - py;
           sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
-          alpha[u] = fminf(kAlphaMaxFwd, q1.w * __expf(-sig[u]));
+          alpha[u] = fminf(kAlphaMaxFwd, q1.w * exp_neg(sig[u]));
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -697,14 +769,14 @@ __global__ void __launch_bounds__(kBwdThreads, 2) blend_bwd_multi_kernel(
   const float T_final = inside ? final_Ts[pix] : 1.f;
   float T = T_final;
   const int bin_final = inside ? final_idx[pix] : -1;
-  float vo[kMC], buffer[kMC];
+  float vo[kMC];
+  float bufv = 0.f;
   float bgdot = 0.f;
 #pragma unroll
   for (int k = 0; k < kMK; ++k) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       vo[3 * k + c] = inside ? v_planes[k * plane + pix * 3 + c] : 0.f;
-      buffer[3 * k + c] = 0.f;
       bgdot += background[c] * vo[3 * k + c];
     }
   }
@@ -752,7 +824,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) blend_bwd_multi_kernel(
         const float4 a0 = E[(base + h) * kMRQ], a1 = E[(base + h) * kMRQ + 1];
         const float dx = a0.x - px, dy = a0.y - py;
         const float sigma = 0.5f * (a0.z * dx * dx + a1.x * dy * dy) + a0.w * dx * dy;
-        const float vis = __expf(-sigma);
+        const float vis = exp_neg(sigma);
         const float alpha = fminf(kAlphaMaxBwd, a1.y * vis);
         const bool valid = (__float_as_int(a1.z) <= bin_final) && !(sigma < 0.f) && !(alpha < kAlphaMin);
         al[u] = valid ? alpha : 0.f;
@@ -763,14 +835,13 @@ __global__ void __launch_bounds__(kBwdThreads, 2) blend_bwd_multi_kernel(
       for (int u = 0; u < 2; ++u) {
         const float4 c0 = E[(base + h0 + u) * kMRQ + 2], c1 = E[(base + h0 + u) * kMRQ + 3], c2 = E[(base + h0 + u) * kMRQ + 4];
         const float cc[kMC] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
-        float v_alpha = tfc;
+        float cv = 0.f;  // c . v_out over the 12 channels; only the scalar buffer . v_out is carried (see the single pass)
 #pragma unroll
-        for (int c = 0; c < kMC; ++c) v_alpha += (cc[c] * T - buffer[c]) * vo[c];
-        v_alpha *= ra[u];
+        for (int c = 0; c < kMC; ++c) cv += cc[c] * vo[c];
+        const float v_alpha = ((cv * T - bufv) + tfc) * ra[u];
         T *= ra[u];
         const float fac = al[u] * T;
-#pragma unroll
-        for (int c = 0; c < kMC; ++c) buffer[c] += cc[c] * fac;
+        bufv += cv * fac;
         M[(h0 + u) * kMStride + lane] = make_float2(fac, -ov[u] * v_alpha);
       }
     }
@@ -962,19 +1033,28 @@ bool g_attr_set[64] = {};  // per device: the > 48 KB dynamic shared memory opt-
 
 namespace gbblend {
 
+// GOLIATH_B200_BLEND_FWD = list (default) | rounds: hit list per stage vs up to four hits of one cull step per round
+static bool fwd_list_variant() {
+  const char* e = getenv("GOLIATH_B200_BLEND_FWD");
+  return !(e && !strcmp(e, "rounds"));
+}
+
 int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
                    const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
                    cudaStream_t s) {
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   if (sched && !tile_order) return (int)cudaErrorInvalidValue;
-  if (channels == 3)
-    blend_fwd_ilp_kernel<3><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched, (const int2*)tile_bins,
-                                                              (const float4*)records, background, final_Ts, final_idx,
-                                                              out_img);
-  else
-    blend_fwd_ilp_kernel<4><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched, (const int2*)tile_bins,
-                                                              (const float4*)records, background, final_Ts, final_idx,
-                                                              out_img);
+  static const bool list = fwd_list_variant();
+#define GB_FWD_MOM(CC, LL)                                                                                              \
+  blend_fwd_ilp_kernel<CC, LL><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched,                  \
+                                                                 (const int2*)tile_bins, (const float4*)records,        \
+                                                                 background, final_Ts, final_idx, out_img)
+  if (channels == 3) {
+    if (list) GB_FWD_MOM(3, true); else GB_FWD_MOM(3, false);
+  } else {
+    if (list) GB_FWD_MOM(4, true); else GB_FWD_MOM(4, false);
+  }
+#undef GB_FWD_MOM
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;

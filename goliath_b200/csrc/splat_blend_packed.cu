@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_packed_kernel(
   if (inside) {
 #pragma unroll
     for (int c = 0; c < C; ++c) vo[c] = v_output[pix * C + c];
-    voa = v_output_alpha[pix];
+    voa = v_output_alpha ? v_output_alpha[pix] : 0.f;  // NULL = no gradient through alpha
   }
   float bgdot = 0.f;
 #pragma unroll

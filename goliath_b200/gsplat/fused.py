@@ -156,7 +156,7 @@ class _RenderFused(Function):
         L = _lib.lib()
         f32 = dict(device=dev, dtype=torch.float32)
         v_out4 = torch.zeros(H, W, 4, **f32) if v_out4 is None else v_out4.contiguous()
-        v_alpha = torch.zeros(H, W, **f32) if v_alpha is None else v_alpha.contiguous()
+        v_alpha = None if v_alpha is None else v_alpha.contiguous()  # NULL: no gradient through alpha (no zero fill)
         acc = torch.zeros(G * 10, **f32)  # the four atomically-accumulated gradient arrays, one fill
         v_xy, v_conic = acc[:2 * G].view(G, 2), acc[2 * G:5 * G].view(G, 3)
         v_col4, v_opeff = acc[5 * G:9 * G].view(G, 4), acc[9 * G:]

@@ -125,8 +125,8 @@ class _RenderShared(Function):
             v_out4[..., 3].zero_()
         else:
             v_out4[..., 3] = v_depth
-        v_alpha = torch.zeros(H, W, **f32) if v_alpha is None else v_alpha.contiguous()
-        zero_alpha = torch.zeros(H, W, **f32) if C > 1 else None
+        v_alpha = None if v_alpha is None else v_alpha.contiguous()  # NULL: no gradient through alpha
+        zero_alpha = None  # the conditions after the first carry no alpha gradient
         acc = torch.zeros(G * 10, **f32)  # v_xy | v_conic | v_col4 (condition 0) | v_opacity_eff: one fill
         v_xy, v_conic = acc[:2 * G].view(G, 2), acc[2 * G:5 * G].view(G, 3)
         v_col4, v_opeff = acc[5 * G:9 * G].view(G, 4), acc[9 * G:]

@@ -95,7 +95,8 @@ int gb_rasterize_fwd(int img_h, int img_w, int block_width, int channels, const 
                      int32_t* final_idx, void* stream);
 
 /* replaces gsplat._C.rasterize_backward.  v_xy [G,2], v_conic [G,3], v_colors [G,C], v_opacity [G] are
- * accumulated into (caller zeroes them). */
+ * accumulated into (caller zeroes them).  v_output_alpha [H,W] may be NULL (no gradient through alpha) here and in every
+ * gb_rasterize_*_bwd below. */
 int gb_rasterize_bwd(int img_h, int img_w, int block_width, int channels, const int32_t* gids_sorted,
                      const int32_t* tile_bins, const float* xys, const float* conics, const float* colors,
                      const float* opacities, const float* background, const float* final_Ts,

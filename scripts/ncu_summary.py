@@ -3,6 +3,7 @@ shares; (2) a --set full .ncu-rep -> the metrics the roofline discussion uses.  
 needed to READ a report).  Usage:
   python scripts/ncu_summary.py launches gpurun_out/launches.csv > profiles/rNN_launches.txt
   python scripts/ncu_summary.py report  gpurun_out/x.ncu-rep   > profiles/rNN_x_ncu.txt
+  python scripts/ncu_summary.py traffic gpurun_out/x.ncu-rep [more.ncu-rep ...] > profiles/rNN_traffic.json
 """
 import collections
 import csv
@@ -61,5 +62,53 @@ def report(path):
         print()
 
 
+def traffic(paths):
+    """Per kernel (first launch of each name): DRAM bytes, warp instructions, issue-active share, top stall reasons.
+    bench.py reads this file for roofline.traffic and roofline.issue_slot."""
+    import json
+    import re
+
+    kernels = {}
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        idx = {h: i for i, h in enumerate(rows[0])}
+        units = rows[1]
+
+        def val(r, m, to=None):
+            v = float(r[idx[m]].replace(",", ""))
+            u = units[idx[m]]
+            if to == "byte":
+                v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+            if to == "us":
+                v *= {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(u, 1e-3)
+            return v
+
+        for r in rows[2:]:
+            name = re.sub(r"^(void\s+)?(\(anonymous namespace\)::)?", "", r[idx["Kernel Name"]].split("(")[0]).strip()
+            name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+            if name in kernels:
+                continue
+            rd, wr = val(r, "dram__bytes_read.sum", "byte"), val(r, "dram__bytes_write.sum", "byte")
+            stalls = sorted(((val(r, m), m.split("stalled_")[1].split("_per_issue")[0]) for m in idx
+                             if m.startswith("smsp__average_warps_issue_stalled_") and m.endswith("_per_issue_active.ratio")
+                             and "selected" not in m), reverse=True)
+            kernels[name] = {
+                "dram_bytes": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
+                "time_us": round(val(r, "gpu__time_duration.sum", "us"), 1),
+                "issue_active_pct": round(val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), 1),
+                "sm_cycles_active_over_elapsed": round(val(r, "sm__cycles_active.avg") / val(r, "sm__cycles_elapsed.max"), 2),
+                "warp_inst": int(val(r, "smsp__inst_executed.sum")),
+                "registers": int(val(r, "launch__registers_per_thread")),
+                "top_stalls": [s for _, s in stalls[:3]],
+            }
+    print(json.dumps({"source": "ncu --set full --clock-control none captures: " + ", ".join(paths) +
+                      " (bench scene: 300k Gaussians, 1024x667, one view); written by scripts/ncu_summary.py traffic",
+                      "kernels": kernels}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
+    else:
+        {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
