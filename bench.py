@@ -92,18 +92,36 @@ def unpack(flat, G=None):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+SHADE_STREAM = os.environ.get("GOLIATH_B200_SHADE_STREAM", "1") != "0"
+
+
 def gpu_step(packed, cam, li, capacity=None):
     """forward + backward of shade + render for one view; returns (rgb, alpha, depth)."""
     from goliath_b200.render import render_views
     from goliath_b200.rgca_heads import shade_compose
 
     u = packed  # dict of leaf tensors (contiguous views of the flat buffer)
-    # rgca.py:557-575: SG specular shade * spec_vis + clamped diffuse, clamped (one fused kernel each way)
-    color = shade_compose(u["lobe_dirs"][None], u["sigma"][None], li["light_intensity"], li["light_pos"],
-                          u["primpos"][None], li["n_lights"], u["diff_color"][None], u["spec_vis"][None])
+    # rgca.py:557-575: SG specular shade * spec_vis + clamped diffuse, clamped (one fused kernel each way).  Sync-free
+    # path: the shade runs on a side stream beside the projection and the binning, which only need the colours at their
+    # last kernel (render_views(color_event=...)); autograd runs its backward there too, beside the projection backward.
+    ev = None
+    if capacity is not None and SHADE_STREAM:
+        from goliath_b200.render import shade_stream
+        dev = u["primpos"].device
+        main, side = torch.cuda.current_stream(dev), shade_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            color = shade_compose(u["lobe_dirs"][None], u["sigma"][None], li["light_intensity"], li["light_pos"],
+                                  u["primpos"][None], li["n_lights"], u["diff_color"][None], u["spec_vis"][None])
+            ev = torch.cuda.Event()
+            ev.record(side)
+    else:
+        color = shade_compose(u["lobe_dirs"][None], u["sigma"][None], li["light_intensity"], li["light_pos"],
+                              u["primpos"][None], li["n_lights"], u["diff_color"][None], u["spec_vis"][None])
     preds = dict(primpos=u["primpos"][None], primqvec=u["primqvec"][None], primscale=u["primscale"][None],
                  opacity=u["opacity"][None], color=color)
-    rgb, alpha, depth = render_views(W, H, None, cam["Rt"], preds, intrinsics_host=[cam["intr"]], capacity=capacity)
+    rgb, alpha, depth = render_views(W, H, None, cam["Rt"], preds, intrinsics_host=[cam["intr"]], capacity=capacity,
+                                     color_event=ev)
     torch.autograd.backward([rgb, depth], [_ones_like(rgb), _ones_like(depth)])  # v_out = 1 (SURVEY.md §8d)
     return rgb, alpha, depth
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "gb_bin_tiles_supported": (_i, [_i]),
     "gb_bin_tiles_workspace_bytes": (_sz, [_i, _i, _i64]),
     "gb_bin_tiles_pack": (_i, [_i] + [_vp] * 7 + [_i, _i, _i, _i64] + [_vp, _vp, _i] + [_vp] * 5 + [_vp]),
+    "gb_bin_tiles_pack_ev": (_i, [_i] + [_vp] * 7 + [_i, _i, _i, _i64] + [_vp, _vp, _i] + [_vp] * 5 + [_vp, _vp]),
     "gb_tile_schedule_ints": (_i, [_i]),
     "gb_tile_schedule": (_i, [_i, _vp, _vp, _vp]),
     "gb_rasterize_sched_fwd": (_i, [_i, _i, _i] + [_vp] * 7 + [_vp]),

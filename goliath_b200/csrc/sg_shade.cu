@@ -28,6 +28,43 @@ constexpr int kLightChunk = 256;  // 256 lights * 24 B = 6 KB of shared memory
 
 __device__ __forceinline__ float sq(float v) { return v * v; }
 
+// ---- the fused (shade_compose) pass, w_type 0: the per-pair arithmetic regrouped for the FP32 / SFU pipes.
+// The drop-in binding above keeps the reference's operation order (bit parity with sg.cu); the fused pass has the
+// oracle's 1e-4 bar instead and evaluates a pair with 3 SFU operations and ~33 instructions (was 4 / 53):
+//   cos    = (l . dir) * rsqrt(l . l)                      (no normalised light vector, no division)
+//   angle  = acos(cos) = sqrt(1 - |c|) * P7(|c|), reflected for c < 0   (Abramowitz & Stegun 4.4.46, |err| <= 2e-8)
+//   weight = ex2(-0.5 log2e (angle / sigma)^2) / (sigma K)   with 1 / sigma and 1 / (sigma K) hoisted per Gaussian and the
+//            normalisation applied once to the light sum.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// acos of c in [-1, 1]; `a` = |c|, `s` = 1 - a are shared with the caller
+__device__ __forceinline__ float acos_as(float c, float a, float s) {
+  float p = -0.0012624911f;
+  p = p * a + 0.0066700901f;
+  p = p * a - 0.0170881256f;
+  p = p * a + 0.0308918810f;
+  p = p * a - 0.0501743046f;
+  p = p * a + 0.0889789874f;
+  p = p * a - 0.2145988016f;
+  p = p * a + 1.5707963050f;
+  const float r = sqrt_approx(s) * p;
+  return c < 0.f ? 3.14159265358979f - r : r;
+}
+constexpr float kHalfLog2e = 0.72134752044448f;  // 0.5 * log2(e)
+
 // Optional fusion of the shade's surroundings in ca_code/models/rgca.py:557-575 (and F.normalize of
 // extensions/sgutils/sgutils.py:74-75) into the same pass: lobe direction normalised in-kernel, specular = integral *
 // spec_vis, colour = clamp(clamp(diffuse, 0) + specular, 0).  The per-(Gaussian, light) arithmetic is untouched.
@@ -83,6 +120,19 @@ __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict_
       s_lv[i] = light_values[((size_t)n * L + l0) * 3 + i];
     }
     __syncthreads();
+    if (FUSED && WT == 0) {
+      const float inv_sigma = 1.f / sigma;
+#pragma unroll 4
+      for (int l = 0; l < cnt; ++l) {
+        const float lx = s_lp[3 * l] - pp.x, ly = s_lp[3 * l + 1] - pp.y, lz = s_lp[3 * l + 2] - pp.z;
+        const float rinv = rsqrt_approx(lx * lx + ly * ly + lz * lz);
+        const float c = fminf(fmaxf((lx * dir.x + ly * dir.y + lz * dir.z) * rinv, -1.f), 1.f);
+        const float a = fabsf(c);
+        const float t = acos_as(c, a, 1.f - a) * inv_sigma;
+        const float w = ex2_approx(-kHalfLog2e * (t * t));
+        sum.x += s_lv[3 * l] * w; sum.y += s_lv[3 * l + 1] * w; sum.z += s_lv[3 * l + 2] * w;
+      }
+    } else {
 #pragma unroll 4
     for (int l = 0; l < cnt; ++l) {
       float lx = s_lp[3 * l] - pp.x, ly = s_lp[3 * l + 1] - pp.y, lz = s_lp[3 * l + 2] - pp.z;
@@ -103,6 +153,11 @@ __global__ void __launch_bounds__(kBlock) sg_fwd_kernel(const float* __restrict_
       }
       sum.x += s_lv[3 * l] * w; sum.y += s_lv[3 * l + 1] * w; sum.z += s_lv[3 * l + 2] * w;
     }
+    }
+  }
+  if (FUSED && WT == 0) {  // the hoisted 1 / (sigma K)
+    const float norm = INVSQRT2PI23 / sigma;
+    sum.x *= norm; sum.y *= norm; sum.z *= norm;
   }
   if (active && !FUSED) {
     integral[3 * o] = sum.x; integral[3 * o + 1] = sum.y; integral[3 * o + 2] = sum.z;
@@ -175,6 +230,30 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
       if (LIGHT_GRAD) s_gl[i] = 0.f;
     }
     __syncthreads();
+    if (FUSED && WT == 0 && !LIGHT_GRAD) {
+      // un-normalised accumulators: gsig_un = sum dLw ev (t^2 - 1), gdir_un = sum dLw ev t rs rinv l, integ_un = sum e ev
+      // (t = angle / sigma, rs = 1 / sqrt(1 - c^2)); the factors K^-1 sigma^-2 and K^-1 sigma^-1 are applied after the loop
+      const float inv_sigma = 1.f / sigma;
+#pragma unroll 4
+      for (int l = 0; l < cnt; ++l) {
+        const float lx = s_lp[3 * l] - pp.x, ly = s_lp[3 * l + 1] - pp.y, lz = s_lp[3 * l + 2] - pp.z;
+        const float e0 = s_lv[3 * l], e1 = s_lv[3 * l + 1], e2 = s_lv[3 * l + 2];
+        const float rinv = rsqrt_approx(lx * lx + ly * ly + lz * lz);
+        const float cu = (lx * dir.x + ly * dir.y + lz * dir.z) * rinv;
+        const float c = fminf(fmaxf(cu, -1.f), 1.f);
+        const float a = fabsf(c), s1 = 1.f - a;
+        const float t = acos_as(c, a, s1) * inv_sigma;
+        const float t2 = t * t;
+        const float ev = ex2_approx(-kHalfLog2e * t2);
+        const float dLw = (gi.x * e0 + gi.y * e1 + gi.z * e2) * ev;
+        gsig += dLw * (t2 - 1.f);
+        // d angle / d cos = -1 / sqrt(1 - c^2) inside (-1, 1); the reference's -20 at the clamp edges (sg.cu:129)
+        const float rs = (fabsf(cu) < 1.f) ? rsqrt_approx(s1 * (1.f + a)) : 20.f;
+        const float k = dLw * t * rs * rinv;
+        gdir.x += k * lx; gdir.y += k * ly; gdir.z += k * lz;
+        integ.x += e0 * ev; integ.y += e1 * ev; integ.z += e2 * ev;
+      }
+    } else {
 #pragma unroll 2
     for (int l = 0; l < cnt; ++l) {
       float lx = s_lp[3 * l] - pp.x, ly = s_lp[3 * l + 1] - pp.y, lz = s_lp[3 * l + 2] - pp.z;
@@ -220,11 +299,19 @@ __global__ void __launch_bounds__(kBlock) sg_bwd_kernel(const float* __restrict_
         }
       }
     }
+    }
     if (LIGHT_GRAD) {
       __syncthreads();
       for (int i = threadIdx.x; i < cnt * 3; i += kBlock)
         gb::red_add(grad_light_values + ((size_t)n * L + l0) * 3 + i, s_gl[i]);
     }
+  }
+  if (FUSED && WT == 0 && !LIGHT_GRAD) {  // the hoisted factors of the regrouped loop
+    const float inv_sigma = 1.f / sigma;
+    const float fw = INVSQRT2PI23 * inv_sigma, fg = fw * inv_sigma;
+    gsig *= fg;
+    gdir.x *= fg; gdir.y *= fg; gdir.z *= fg;
+    integ.x *= fw; integ.y *= fw; integ.z *= fw;
   }
   if (active) {
     grad_sigmas[o] = gsig;

@@ -42,6 +42,11 @@
 
 extern "C" int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
 extern "C" int gb_tile_schedule(int num_tiles, const int32_t* tile_bins, int32_t* sched, void* stream);
+GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                                const float* colors3, const float* opacity, const float* compensation, int img_h,
+                                int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
+                                int tile_sched, int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
+                                void* workspace, void* colors_ready, void* stream);
 
 namespace {
 
@@ -804,10 +809,15 @@ __global__ void __launch_bounds__(kSortThreads, 3) tile_sort_kernel(int words, i
   }
 }
 
+// The colour quarter (rgb + view depth) is read HERE, by Gaussian id, not from the by-rank table: colours are the only
+// input of the binning that comes from the shade, so everything before this kernel can run beside the shade forward
+// (gb_bin_tiles_pack_ev waits for the caller's "colours ready" event just before this launch).
 __global__ void __launch_bounds__(256) gather_records_kernel(long long cap, const int* __restrict__ n_dev,
                                                              const int* __restrict__ ranks_sorted,
                                                              const int* __restrict__ rank_to_gid,
                                                              const float4* __restrict__ rec_by_rank,
+                                                             const float* __restrict__ colors3,
+                                                             const float* __restrict__ depths,
                                                              int* __restrict__ gids_sorted, float4* __restrict__ rec) {
   const long long n = min((long long)*n_dev, cap);
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index: record j / 3, part j % 3
@@ -815,6 +825,11 @@ __global__ void __launch_bounds__(256) gather_records_kernel(long long cap, cons
   const long long i = j / 3;
   const int part = (int)(j - 3 * i);
   const int r = ranks_sorted[i];
+  if (part == 2) {
+    const int g = rank_to_gid[r];
+    rec[j] = make_float4(colors3[3 * (size_t)g], colors3[3 * (size_t)g + 1], colors3[3 * (size_t)g + 2], depths[g]);
+    return;
+  }
   rec[j] = gb::ld_nc_f4(rec_by_rank + 3 * (size_t)r + part);
   if (part == 0) gids_sorted[i] = rank_to_gid[r];
 }
@@ -961,6 +976,19 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
                              int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
                              int tile_sched, int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
                              void* workspace, void* stream) {
+  return gb_bin_tiles_pack_ev(G, xys, depths, radii, conics, colors3, opacity, compensation, img_h, img_w, block_width, cap,
+                              tile_bins, tile_order, tile_sched, gids_sorted, records, n_out, overflow, workspace, nullptr,
+                              stream);
+}
+
+// Same, with the colours allowed to arrive late: `colors_ready` (a cudaEvent_t recorded on the stream that produces
+// colors3, or NULL) is waited for on `stream` just before the first kernel that reads colors3 — the final record gather
+// with the split tile sort (default) — so depth ranks, tile buckets and the per-tile sort overlap the caller's shade.
+GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                                const float* colors3, const float* opacity, const float* compensation, int img_h,
+                                int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
+                                int tile_sched, int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
+                                void* workspace, void* colors_ready, void* stream) {
   if (!gb_bin_tiles_supported(G) || block_width < 1 || cap < 0) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   const int tbx = gb::cdiv(img_w, block_width), tby = gb::cdiv(img_h, block_width);
@@ -1006,21 +1034,25 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
   const int e = tile_sched ? gb_tile_schedule(T, tile_bins, tile_order, stream)
                            : gb_tile_order(T, tile_bins, tile_order, stream);
   if (e) return e;
+  const bool split = tile_sort_mode() == 0;  // split: the colour quarter of the records is gathered by the last kernel
+  if (!split && colors_ready) GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
   tile_scatter_kernel<<<gb::cdiv(G, kGaussBlock * kScatItems), kGaussBlock, (size_t)smem_tiles * 8, s>>>(
-      G, (const float2*)xys, radii, rank_of, conics, colors3, depths, opacity, compensation, tbx, tby, block_width,
-      (long long)cap, smem_tiles, cursor, tile_ranks, rec_by_rank);
+      G, (const float2*)xys, radii, rank_of, conics, split ? nullptr : colors3, depths, opacity, compensation, tbx, tby,
+      block_width, (long long)cap, smem_tiles, cursor, tile_ranks, rec_by_rank);
   const int words = gb::cdiv(G, 32);
   const int chunk = gb::cdiv(words, kSortThreads) | 1;
   const size_t smem = (size_t)words * 4;
-  if (tile_sort_mode() == 0) {
+  if (split) {
     if (smem > 40 * 1024) {
       const int e2 = opt_in_smem(tile_sort_kernel, s_opt_sort2);
       if (e2) return e2;
     }
     tile_sort_kernel<<<T, kSortThreads, smem, s>>>(words, chunk, tile_order, (const int2*)tile_bins, tile_ranks);
+    if (colors_ready) GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
     if (cap > 0)
       gather_records_kernel<<<(unsigned)gb::cdiv64(3 * cap, 256), 256, 0, s>>>((long long)cap, n_total, tile_ranks, rank_to_gid,
-                                                                             rec_by_rank, gids_sorted, (float4*)records);
+                                                                             rec_by_rank, colors3, depths, gids_sorted,
+                                                                             (float4*)records);
     gb::count_launches(3);
     GB_CHECK_LAUNCH();
     return 0;

@@ -26,6 +26,7 @@ __device__ __forceinline__ void cull_box(float A, float B, float Cc, float o, fl
 
 // Fused-render record of Gaussian g: opacity = opacity * compensation and 4th colour channel = view-space
 // depth, i.e. exactly what ca_code/utils/render_gsplat.py:72 and :97 feed to the two rasterise calls.
+// colors3 == nullptr: the colour quarter is left to a later pass (csrc/splat_bin_tiles.cu gathers it by Gaussian id).
 __device__ __forceinline__ void pack_record_fused(int g, const float2* __restrict__ xys,
                                                   const float* __restrict__ conics,
                                                   const float* __restrict__ colors3,
@@ -39,7 +40,7 @@ __device__ __forceinline__ void pack_record_fused(int g, const float2* __restric
   cull_box(A, B, Cc, o, ex, ey);
   out3[0] = make_float4(xy.x, xy.y, ex, ey);
   out3[1] = make_float4(A, B, Cc, o);
-  out3[2] = make_float4(colors3[3 * g], colors3[3 * g + 1], colors3[3 * g + 2], depths[g]);
+  if (colors3) out3[2] = make_float4(colors3[3 * g], colors3[3 * g + 1], colors3[3 * g + 2], depths[g]);
 }
 
 }  // namespace gb

@@ -144,11 +144,26 @@ class _FinishView(th.autograd.Function):
         return g_out4, None
 
 
+_SHADE_STREAMS = {}
+
+
+def shade_stream(device):
+    """The side stream a caller may run its shade on while render_views projects and bins (see `color_event` there)."""
+    dev = th.device(device)
+    st = _SHADE_STREAMS.get(dev)
+    if st is None:
+        st = _SHADE_STREAMS[dev] = th.cuda.Stream(device=dev)
+    return st
+
+
 def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, intrinsics_host=None, fused=True,
-                 capacity=None):
+                 capacity=None, color_event=None):
     """rgca.AutoEncoder.render (rgca.py:112-151): loop over the batch, stack, alpha from the DETACHED final_T,
     depth normalised by alpha.clamp(0.05, 1).  `intrinsics_host` (list of (fx,fy,cx,cy)) avoids the reference's
-    four `.item()` device syncs per view when the caller already has them on the host."""
+    four `.item()` device syncs per view when the caller already has them on the host.  `color_event`: preds["color"]
+    is still being written on another stream (shade_stream) and this torch.cuda.Event was recorded after its last writer;
+    the sync-free fused path then waits for it only where the colours are first read (the record gather at the end of the
+    binning), so projection, depth ranks, tile buckets and the per-tile sort run beside the shade."""
     B = Rt.shape[0]
     if fused:
         # per view: one autograd node for project + bin/sort + pack + blend and one for the post-processing.  With several
@@ -178,7 +193,7 @@ def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, in
                 out4, alpha, _ = render_fused(
                     pv["primpos"][b].contiguous(), pv["primscale"][b].contiguous(), 1.0, pv["primqvec"][b].contiguous(),
                     Rt[b], fx, fy, cx, cy, height, width, pv["opacity"][b].contiguous(), pv["color"][b].contiguous(),
-                    _black(Rt.device), 0.1, capacity)
+                    _black(Rt.device), 0.1, capacity, colors_event=color_event)
                 r, a, d = _FinishView.apply(out4, alpha)
             if side is not None:
                 for t_ in (r, a, d):
@@ -190,6 +205,8 @@ def render_views(width: int, height: int, K: th.Tensor, Rt: th.Tensor, preds, in
         if B == 1:
             return rgbs[0][None], alphas[0][None], depths[0][None]
         return th.stack(rgbs), th.stack(alphas), th.stack(depths)
+    if color_event is not None:
+        th.cuda.current_stream(Rt.device).wait_event(color_event)
     rgbs, Ts, depths = [], [], []
     for b in range(B):
         if intrinsics_host is not None:

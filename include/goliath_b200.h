@@ -162,10 +162,10 @@ int gb_pack_records_fused_dn(int64_t cap, const int32_t* n_dev, const int32_t* g
                              const float* conics, const float* colors3, const float* depths, const float* opacity,
                              const float* compensation, float* records, void* stream);
 
-/* depth ranks inside gb_bin_tiles_pack: 2 = 2048 key buckets + in-bucket ranking of the visible Gaussians (default; a
- * device flag hands degenerate depth distributions to the cooperative sort), 0 = one cooperative LSD kernel over the key
- * bits that vary, 1 = four radix passes as separate launches (round 1).  Identical outputs.
- * GOLIATH_B200_RANKSORT=buckets|coop|passes. */
+/* depth ranks inside gb_bin_tiles_pack: 0 = one cooperative LSD kernel over the key bits that vary (default), 1 = four
+ * radix passes as separate launches (round 1), 2 = 2048 key buckets + in-bucket ranking of the visible Gaussians (a
+ * device flag hands degenerate depth distributions to the cooperative sort; measured slower).  Identical outputs.
+ * GOLIATH_B200_RANKSORT=coop|passes|buckets. */
 int gb_get_rank_sort_mode(void);
 /* per-tile ordering inside gb_bin_tiles_pack: 0 = bitmap sort per tile + one grid-wide record gather (default), 1 = one
  * kernel per tile doing both (round 1).  Identical outputs.  GOLIATH_B200_TILESORT=split|fused. */
@@ -188,6 +188,15 @@ int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const int32_
                       int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int tile_sched,
                       int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
                       void* stream);
+/* Same, with colors3 allowed to arrive late: colors_ready (cudaEvent_t recorded on the stream that writes colors3, or
+ * NULL) is waited for on `stream` just before the first kernel that reads colors3 (the final record gather with the
+ * split tile sort), so ranks, buckets and the per-tile sort run beside the caller's shade (rgca.py:557-575 precedes
+ * render_gsplat.py:65 in the reference; only the colours depend on it). */
+int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                         const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
+                         int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int tile_sched,
+                         int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
+                         void* colors_ready, void* stream);
 
 /* launch order of the tiles, longest list first: order [T] int32 */
 int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);

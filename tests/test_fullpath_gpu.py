@@ -91,3 +91,56 @@ def test_benchmarked_binning_is_bit_exact_at_bench_size(orc, cuda):
     assert int(ovf) == 0
     assert np.array_equal(t2n(bins), b["tile_bins"]), "tile_bins"
     assert np.array_equal(t2n(gids[:n]), b["gaussian_ids_sorted"]), "gaussian_ids_sorted"
+
+
+def _step_variant(cuda, G, split, side_stream, graph=False):
+    """bench.gpu_step with the sync-free render as one autograd node or two, shade on the main or on the side stream."""
+    import bench
+    from goliath_b200 import synthetic
+    from goliath_b200.gsplat import fused
+
+    li = {k: v.to(cuda) for k, v in synthetic.lights(8).items()}
+    c = synthetic.ring_camera(1, img_h=bench.H, img_w=bench.W)
+    cam = dict(Rt=c["viewmat"][None].to(cuda), intr=(c["fx"], c["fy"], c["cx"], c["cy"]))
+    leaves = {k: v.detach().requires_grad_() for k, v in bench.unpack(bench.packed_scene(G).to(cuda)).items()}
+    old = (fused.SPLIT, bench.SHADE_STREAM)
+    fused.SPLIT, bench.SHADE_STREAM = split, side_stream
+    try:
+        cap = max(8 * G, 1 << 20)
+        if graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):  # warm-up outside the capture (workspace allocation, lazy module loads)
+                    for v in leaves.values():
+                        v.grad = None
+                    bench.gpu_step(leaves, cam, li, capacity=cap)
+            torch.cuda.current_stream().wait_stream(s)
+            for v in leaves.values():
+                v.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                rgb, alpha, depth = bench.gpu_step(leaves, cam, li, capacity=cap)
+            g.replay()
+        else:
+            rgb, alpha, depth = bench.gpu_step(leaves, cam, li, capacity=cap)
+        torch.cuda.synchronize()
+    finally:
+        fused.SPLIT, bench.SHADE_STREAM = old
+    return t2n(rgb), t2n(alpha), t2n(depth), {k: t2n(v.grad) for k, v in leaves.items()}
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_split_nodes_and_side_stream_match_single_node(cuda, graph):
+    """The two-node render with the shade on a side stream (colours waited for inside gb_bin_tiles_pack_ev, projection
+    backward beside the shade backward) against the single-node render on one stream: same kernels, same inputs —
+    images identical, gradients equal up to the order of the atomic adds.  Also under CUDA-graph capture (fork/join)."""
+    G = 60_000
+    ref = _step_variant(cuda, G, split=False, side_stream=False)
+    for split, side in ((True, False), (True, True), (False, True)):
+        got = _step_variant(cuda, G, split, side, graph=graph)
+        for name, a, b in zip(("rgb", "alpha", "depth"), got[:3], ref[:3]):
+            assert np.array_equal(a, b), (name, split, side)
+        for k, want in ref[3].items():
+            assert_close(got[3][k], want, rtol=1e-4, atol=1e-5 * float(np.abs(want).max()), frac=0.9999,
+                         what="grad %s split=%s side=%s" % (k, split, side))
