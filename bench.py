@@ -93,6 +93,7 @@ def unpack(flat, G=None):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 SHADE_STREAM = os.environ.get("GOLIATH_B200_SHADE_STREAM", "1") != "0"
+HIGH_PRIO = os.environ.get("GOLIATH_B200_RENDER_PRIO", "1") != "0"
 
 
 def gpu_step(packed, cam, li, capacity=None):
@@ -470,7 +471,10 @@ def run_ours(args):
                 wl.compute(static_in)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        from goliath_b200.render import render_stream
+        # captured on a high-priority stream: the shade's side stream (lowest priority) then only takes what the binning
+        # kernels leave idle; kernel nodes keep the priority of the stream they were captured on
+        with torch.cuda.graph(g, stream=render_stream(dev) if HIGH_PRIO else None):
             outs = wl.compute(static_in)
         state["graph"], state["outs"] = g, outs
 

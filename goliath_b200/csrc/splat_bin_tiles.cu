@@ -809,15 +809,23 @@ __global__ void __launch_bounds__(kSortThreads, 3) tile_sort_kernel(int words, i
   }
 }
 
-// The colour quarter (rgb + view depth) is read HERE, by Gaussian id, not from the by-rank table: colours are the only
-// input of the binning that comes from the shade, so everything before this kernel can run beside the shade forward
-// (gb_bin_tiles_pack_ev waits for the caller's "colours ready" event just before this launch).
+// Late colours (gb_bin_tiles_pack_ev with an event): tile_scatter leaves the colour quarter of the by-rank records
+// empty and this kernel fills it once the colours exist — colours are the only input of the binning that comes from
+// the shade, so everything before it can run beside the shade forward.
+__global__ void __launch_bounds__(256) rec_colors_kernel(int G, const int* __restrict__ radii,
+                                                         const int* __restrict__ rank_of,
+                                                         const float* __restrict__ colors3,
+                                                         const float* __restrict__ depths, float4* __restrict__ rec_by_rank) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G || radii[g] <= 0) return;
+  rec_by_rank[3 * (size_t)rank_of[g] + 2] = make_float4(colors3[3 * (size_t)g], colors3[3 * (size_t)g + 1],
+                                                       colors3[3 * (size_t)g + 2], depths[g]);
+}
+
 __global__ void __launch_bounds__(256) gather_records_kernel(long long cap, const int* __restrict__ n_dev,
                                                              const int* __restrict__ ranks_sorted,
                                                              const int* __restrict__ rank_to_gid,
                                                              const float4* __restrict__ rec_by_rank,
-                                                             const float* __restrict__ colors3,
-                                                             const float* __restrict__ depths,
                                                              int* __restrict__ gids_sorted, float4* __restrict__ rec) {
   const long long n = min((long long)*n_dev, cap);
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index: record j / 3, part j % 3
@@ -825,11 +833,6 @@ __global__ void __launch_bounds__(256) gather_records_kernel(long long cap, cons
   const long long i = j / 3;
   const int part = (int)(j - 3 * i);
   const int r = ranks_sorted[i];
-  if (part == 2) {
-    const int g = rank_to_gid[r];
-    rec[j] = make_float4(colors3[3 * (size_t)g], colors3[3 * (size_t)g + 1], colors3[3 * (size_t)g + 2], depths[g]);
-    return;
-  }
   rec[j] = gb::ld_nc_f4(rec_by_rank + 3 * (size_t)r + part);
   if (part == 0) gids_sorted[i] = rank_to_gid[r];
 }
@@ -982,8 +985,9 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
 }
 
 // Same, with the colours allowed to arrive late: `colors_ready` (a cudaEvent_t recorded on the stream that produces
-// colors3, or NULL) is waited for on `stream` just before the first kernel that reads colors3 — the final record gather
-// with the split tile sort (default) — so depth ranks, tile buckets and the per-tile sort overlap the caller's shade.
+// colors3, or NULL) is waited for on `stream` just before the first kernel that reads colors3 — with the split tile
+// sort (default) a small kernel that fills the colour quarter of the by-rank records after the per-tile sort — so depth
+// ranks, tile buckets and the per-tile sort overlap the caller's shade.
 GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
                                 const float* colors3, const float* opacity, const float* compensation, int img_h,
                                 int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
@@ -1034,10 +1038,11 @@ GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, co
   const int e = tile_sched ? gb_tile_schedule(T, tile_bins, tile_order, stream)
                            : gb_tile_order(T, tile_bins, tile_order, stream);
   if (e) return e;
-  const bool split = tile_sort_mode() == 0;  // split: the colour quarter of the records is gathered by the last kernel
-  if (!split && colors_ready) GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
+  const bool split = tile_sort_mode() == 0;
+  const bool late = split && colors_ready;  // the colour quarter of the by-rank records is filled after the tile sort
+  if (!late && colors_ready) GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
   tile_scatter_kernel<<<gb::cdiv(G, kGaussBlock * kScatItems), kGaussBlock, (size_t)smem_tiles * 8, s>>>(
-      G, (const float2*)xys, radii, rank_of, conics, split ? nullptr : colors3, depths, opacity, compensation, tbx, tby,
+      G, (const float2*)xys, radii, rank_of, conics, late ? nullptr : colors3, depths, opacity, compensation, tbx, tby,
       block_width, (long long)cap, smem_tiles, cursor, tile_ranks, rec_by_rank);
   const int words = gb::cdiv(G, 32);
   const int chunk = gb::cdiv(words, kSortThreads) | 1;
@@ -1048,11 +1053,14 @@ GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, co
       if (e2) return e2;
     }
     tile_sort_kernel<<<T, kSortThreads, smem, s>>>(words, chunk, tile_order, (const int2*)tile_bins, tile_ranks);
-    if (colors_ready) GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
+    if (late) {
+      GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
+      rec_colors_kernel<<<gb::cdiv(G, 256), 256, 0, s>>>(G, radii, rank_of, colors3, depths, rec_by_rank);
+      gb::count_launches(1);
+    }
     if (cap > 0)
       gather_records_kernel<<<(unsigned)gb::cdiv64(3 * cap, 256), 256, 0, s>>>((long long)cap, n_total, tile_ranks, rank_to_gid,
-                                                                             rec_by_rank, colors3, depths, gids_sorted,
-                                                                             (float4*)records);
+                                                                             rec_by_rank, gids_sorted, (float4*)records);
     gb::count_launches(3);
     GB_CHECK_LAUNCH();
     return 0;

@@ -152,7 +152,22 @@ def shade_stream(device):
     dev = th.device(device)
     st = _SHADE_STREAMS.get(dev)
     if st is None:
-        st = _SHADE_STREAMS[dev] = th.cuda.Stream(device=dev)
+        # lowest priority: the shade fills the SMs the latency-bound binning kernels of a high-priority main stream
+        # (render_stream) leave idle instead of taking their slots
+        st = _SHADE_STREAMS[dev] = th.cuda.Stream(device=dev, priority=0)
+    return st
+
+
+_RENDER_STREAMS = {}
+
+
+def render_stream(device):
+    """A high-priority stream for the render itself (use it as the step's / the graph capture's stream when the shade
+    runs on shade_stream)."""
+    dev = th.device(device)
+    st = _RENDER_STREAMS.get(dev)
+    if st is None:
+        st = _RENDER_STREAMS[dev] = th.cuda.Stream(device=dev, priority=-1)
     return st
 
 

@@ -189,8 +189,8 @@ int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const int32_
                       int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
                       void* stream);
 /* Same, with colors3 allowed to arrive late: colors_ready (cudaEvent_t recorded on the stream that writes colors3, or
- * NULL) is waited for on `stream` just before the first kernel that reads colors3 (the final record gather with the
- * split tile sort), so ranks, buckets and the per-tile sort run beside the caller's shade (rgca.py:557-575 precedes
+ * NULL) is waited for on `stream` just before the first kernel that reads colors3 (with the split tile sort: a small
+ * kernel after the per-tile sort), so ranks, buckets and the per-tile sort run beside the caller's shade (rgca.py:557-575 precedes
  * render_gsplat.py:65 in the reference; only the colours depend on it). */
 int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
                          const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
