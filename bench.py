@@ -92,8 +92,15 @@ def unpack(flat, G=None):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-SHADE_STREAM = os.environ.get("GOLIATH_B200_SHADE_STREAM", "1") != "0"
-HIGH_PRIO = os.environ.get("GOLIATH_B200_RENDER_PRIO", "1") != "0"
+# measured (profiles/r02_bench_head_shade_stream.json): the side stream costs 9 us per step on this workload — the shade is
+# done before the latency-bound part of the binning starts, and the fork/join edges are not free; off by default
+SHADE_STREAM = os.environ.get("GOLIATH_B200_SHADE_STREAM", "0") != "0"
+HIGH_PRIO = os.environ.get("GOLIATH_B200_RENDER_PRIO", "0") != "0"
+
+
+def _fused_mod():
+    from goliath_b200.gsplat import fused
+    return fused
 
 
 def gpu_step(packed, cam, li, capacity=None):
@@ -231,7 +238,46 @@ def kernel_roofline(dev, packed, cam, flush, sm_mhz=None):
                                              gcol.data_ptr(), go.data_ptr(), st), "bwd")
 
     pack()
-    # the product path's binning (sync-free): depth ranks + tile buckets + bitmap sort + record packing, 9 launches
+    # the product path (goliath_b200.gsplat.fused, blend mode 3): records staged by depth rank from the per-Gaussian
+    # table, no sorted-record gather — time THOSE kernels and that binning when it is what the step runs
+    from goliath_b200.gsplat import fused as _fused
+    ranked = bool(_fused.RANKED and _fused.SPLIT and not sched and L.gb_get_blend_mode() == 3)
+    cap_r = int(n) + 1024
+    ranks_r = torch.empty(cap_r, dtype=torch.int32, device=dev)
+    rbr_r = torch.empty(G, 12, device=dev)
+    r2g_r = torch.empty(G, dtype=torch.int32, device=dev)
+    bins_r = torch.empty(T_, 2, dtype=torch.int32, device=dev)
+    order_r = torch.empty(T_, dtype=torch.int32, device=dev)
+    ovf_r = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_r = torch.empty(L.gb_bin_tiles_workspace_bytes(G, T_, cap_r), dtype=torch.uint8, device=dev)
+    col3_r, op1_r = u["diff_color"].contiguous(), u["opacity"].contiguous()
+
+    def bin_ranked():
+        _lib.check(L.gb_bin_tiles_ranked(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
+                                         col3_r.data_ptr(), op1_r.data_ptr(), comp.data_ptr(), H, W, BW, cap_r,
+                                         bins_r.data_ptr(), order_r.data_ptr(), 0, ranks_r.data_ptr(), rbr_r.data_ptr(),
+                                         r2g_r.data_ptr(), None, ovf_r.data_ptr(), ws_r.data_ptr(), None, st),
+                   "bin_tiles_ranked")
+
+    def fwd_ranked():
+        _lib.check(L.gb_rasterize_ranked_fwd(H, W, C, bins_r.data_ptr(), order_r.data_ptr(), ranks_r.data_ptr(),
+                                             rbr_r.data_ptr(), bg.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+                                             st), "ranked fwd")
+
+    def bwd_ranked():
+        _lib.check(L.gb_rasterize_ranked_bwd(H, W, C, r2g_r.data_ptr(), ranks_r.data_ptr(), bins_r.data_ptr(),
+                                             order_r.data_ptr(), rbr_r.data_ptr(), bg.data_ptr(), Ts.data_ptr(),
+                                             fi.data_ptr(), v_out.data_ptr(), v_a.data_ptr(), gx.data_ptr(), gc.data_ptr(),
+                                             gcol.data_ptr(), go.data_ptr(), st), "ranked bwd")
+
+    if ranked:
+        bin_ranked()
+        torch.cuda.synchronize()
+        assert torch.equal(bins_r, bins) and torch.equal(r2g_r[ranks_r[:n].long()], gids) and int(ovf_r) == 0, \
+            "ranked binning != key sort"
+        # same colours as the packed records of this function (diffuse + depth)
+        fwd_ranked()
+    # the packed path's binning (sync-free): depth ranks + tile buckets + bitmap sort + record gather
     cap_b = int(n) + 1024
     col3, op1 = u["diff_color"].contiguous(), u["opacity"].contiguous()
     ws_b = torch.empty(L.gb_bin_tiles_workspace_bytes(G, T_, cap_b), dtype=torch.uint8, device=dev)
@@ -266,6 +312,9 @@ def kernel_roofline(dev, packed, cam, flush, sm_mhz=None):
         return float(np.mean(ts))
 
     t_p, t_f, t_b, t_bin = timeit(pack), timeit(fwd), timeit(bwd), timeit(bin_tiles)
+    t_fr = t_br = t_binr = None
+    if ranked:
+        t_fr, t_br, t_binr = timeit(fwd_ranked), timeit(bwd_ranked), timeit(bin_ranked)
     P, T, I = H * W, tb[0] * tb[1], n
     # SURVEY.md §8d per-unit figures, with C = 4 colour channels (rgb + depth in one pass)
     bytes_f = I * (4 + 24 + 4 * C) + P * (4 * C + 4 + 4) + T * 8
@@ -282,18 +331,28 @@ def kernel_roofline(dev, packed, cam, flush, sm_mhz=None):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     which = "measured" if "hbm_gbs" in peaks else "fallback"
     mode = int(L.gb_get_blend_mode())
+    list_fwd = os.environ.get("GOLIATH_B200_BLEND_FWD", "list") != "rounds"
     fwd_name = ("blend_fwd_packed_kernel<4>", "blend_fwd_pipe_kernel<4>", "blend_fwd_pipe_kernel<4>",
-                "blend_fwd_ilp_kernel<4>", "blend_fwd_ilp_kernel<4>")[mode]
+                "blend_fwd_ilp_kernel<4, %d, 0>" % list_fwd, "blend_fwd_ilp_kernel<4, %d, 0>" % list_fwd)[mode]
     bwd_name = ("blend_bwd_packed_kernel<4>", "blend_bwd_pipe_kernel<4>", "blend_bwd_pipe_kernel<4>",
-                "blend_bwd_mom_kernel<4>", "blend_bwd_mom_kernel<4>")[mode]
+                "blend_bwd_mom_kernel<4, 0>", "blend_bwd_mom_kernel<4, 0>")[mode]
     ks = {
         fwd_name: {"ms": t_f, "alg_bytes": bytes_f, "gbs": bytes_f / t_f / 1e6},
         bwd_name: {"ms": t_b, "alg_bytes": bytes_b, "gbs": bytes_b / t_b / 1e6},
         "pack_records_kernel<4>": {"ms": t_p, "alg_bytes": bytes_p, "gbs": bytes_p / t_p / 1e6},
-        "bin_tiles_pack (9 launches: rank sort, buckets, bitmap sort + pack)": {
+        "bin_tiles_pack (rank sort, buckets, bitmap sort, record gather)": {
             "ms": t_bin, "alg_bytes": bytes_bin, "gbs": bytes_bin / t_bin / 1e6},
     }
-    dom = max((k for k in ks if k.startswith("blend")), key=lambda k: ks[k]["ms"])
+    if ranked:  # what the step runs; the packed kernels above stay as the comparison
+        # algorithmic bytes of the ranked formulation: 4 B rank + 48 B record per intersection read by the blend (the
+        # record comes from the 14.4 MB per-Gaussian table), no 48 B write + read of sorted records in the binning
+        bytes_binr = G * (4 * 16 + 2 * 16) + I * (8 + 8) + G * 48
+        ks["blend_fwd_ilp_kernel<4, 1, 1>"] = {"ms": t_fr, "alg_bytes": bytes_f, "gbs": bytes_f / t_fr / 1e6}
+        ks["blend_bwd_mom_kernel<4, 1>"] = {"ms": t_br, "alg_bytes": bytes_b, "gbs": bytes_b / t_br / 1e6}
+        ks["bin_tiles_ranked (rank sort, buckets, bitmap sort; no record gather)"] = {
+            "ms": t_binr, "alg_bytes": bytes_binr, "gbs": bytes_binr / t_binr / 1e6}
+    in_step = (lambda k: k.endswith(", 1, 1>") or k.endswith("<4, 1>")) if ranked else (lambda k: True)
+    dom = max((k for k in ks if k.startswith("blend") and in_step(k)), key=lambda k: ks[k]["ms"])
     # DRAM bytes and warp instructions per launch of the dominant kernel come from the committed `ncu --set full`
     # capture of the same scene (profiles/r02_traffic.json, written by scripts/ncu_summary.py traffic; neither is
     # measurable live).  The blend is not HBM-bound at this operating point: the second figure is
@@ -728,6 +787,11 @@ def run_ours(args):
                                       ("sync-free (capacity %d intersections)%s" % (cap, "" if args.no_graph else
                                                                                       ", step captured in a CUDA graph"))),
                         "binning": os.environ.get("GOLIATH_B200_BINNING", "buckets"),
+                        "records": ("staged by depth rank from the per-Gaussian table (no sorted-record gather)"
+                                    if (_fused_mod().RANKED and _fused_mod().SPLIT and int(lib.gb_get_blend_mode()) == 3)
+                                    else "sorted 48-byte records materialised by the binning"),
+                        "autograd_nodes": "projection | binning + blend" if _fused_mod().SPLIT else "one fused node",
+                        "shade_stream": bool(SHADE_STREAM),
                         "rank_sort": ["cooperative LSD (one launch, varying key bits only)", "4 radix passes",
                                       "2048 key buckets + in-bucket ranking (cooperative LSD fallback)"][int(lib.gb_get_rank_sort_mode())],
                         "tile_sort": ["bitmap sort per tile + grid-wide record gather", "one kernel per tile"][int(lib.gb_get_tile_sort_mode())],

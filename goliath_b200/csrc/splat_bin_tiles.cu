@@ -988,11 +988,43 @@ GB_API int gb_bin_tiles_pack(int G, const float* xys, const float* depths, const
 // colors3, or NULL) is waited for on `stream` just before the first kernel that reads colors3 — with the split tile
 // sort (default) a small kernel that fills the colour quarter of the by-rank records after the per-tile sort — so depth
 // ranks, tile buckets and the per-tile sort overlap the caller's shade.
+static int bin_tiles_impl(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                          const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
+                          int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int tile_sched,
+                          int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
+                          void* colors_ready, void* stream, int32_t* ext_ranks, float* ext_rec, int32_t* ext_r2g);
+
 GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
                                 const float* colors3, const float* opacity, const float* compensation, int img_h,
                                 int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
                                 int tile_sched, int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow,
                                 void* workspace, void* colors_ready, void* stream) {
+  return bin_tiles_impl(G, xys, depths, radii, conics, colors3, opacity, compensation, img_h, img_w, block_width, cap,
+                        tile_bins, tile_order, tile_sched, gids_sorted, records, n_out, overflow, workspace, colors_ready,
+                        stream, nullptr, nullptr, nullptr);
+}
+
+// Binning WITHOUT the sorted-record gather, for the blend kernels that stage records by rank (gb_rasterize_ranked_*):
+// ranks_sorted [cap] (per tile, the depth ranks in blend order), rec_by_rank [G,12] (one 48-byte record per Gaussian, at
+// its depth rank) and rank_to_gid [G] are written to the CALLER's arrays (they must outlive the backward; the shared
+// workspace does not).  Everything else as gb_bin_tiles_pack_ev.  Saves the 52 MB write + read of the sorted records
+// and holds 14.4 + 4 I bytes per view for the backward instead of 52 I.
+GB_API int gb_bin_tiles_ranked(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                               const float* colors3, const float* opacity, const float* compensation, int img_h,
+                               int img_w, int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order,
+                               int tile_sched, int32_t* ranks_sorted, float* rec_by_rank, int32_t* rank_to_gid,
+                               int32_t* n_out, int32_t* overflow, void* workspace, void* colors_ready, void* stream) {
+  if (!ranks_sorted || !rec_by_rank || !rank_to_gid) return (int)cudaErrorInvalidValue;
+  return bin_tiles_impl(G, xys, depths, radii, conics, colors3, opacity, compensation, img_h, img_w, block_width, cap,
+                        tile_bins, tile_order, tile_sched, nullptr, nullptr, n_out, overflow, workspace, colors_ready, stream,
+                        ranks_sorted, rec_by_rank, rank_to_gid);
+}
+
+static int bin_tiles_impl(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                          const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
+                          int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int tile_sched,
+                          int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
+                          void* colors_ready, void* stream, int32_t* ext_ranks, float* ext_rec, int32_t* ext_r2g) {
   if (!gb_bin_tiles_supported(G) || block_width < 1 || cap < 0) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   const int tbx = gb::cdiv(img_w, block_width), tby = gb::cdiv(img_h, block_width);
@@ -1007,11 +1039,12 @@ GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, co
   unsigned* keys_b = (unsigned*)(ws + l.keys_b);
   int* vals_a = (int*)(ws + l.vals_a);
   int* vals_b = (int*)(ws + l.vals_b);
-  int* rank_to_gid = (int*)(ws + l.rank_to_gid);
+  const bool ranked = ext_ranks != nullptr;  // outputs for the rank-staging blend: no sorted-record gather
+  int* rank_to_gid = ranked ? ext_r2g : (int*)(ws + l.rank_to_gid);
   unsigned* sync = (unsigned*)(ws + l.sync);
   int* rank_of = (int*)(ws + l.rank_of);
-  float4* rec_by_rank = (float4*)(ws + l.rec_by_rank);
-  int* tile_ranks = (int*)(ws + l.tile_ranks);
+  float4* rec_by_rank = ranked ? (float4*)ext_rec : (float4*)(ws + l.rec_by_rank);
+  int* tile_ranks = ranked ? ext_ranks : (int*)(ws + l.tile_ranks);
   const int items = rank_items(G);
   const int ctas = gb::cdiv(G, kRankBlock * items);
   const int smem_tiles = (T <= kMaxSmemTiles) ? T : 0;
@@ -1038,7 +1071,7 @@ GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, co
   const int e = tile_sched ? gb_tile_schedule(T, tile_bins, tile_order, stream)
                            : gb_tile_order(T, tile_bins, tile_order, stream);
   if (e) return e;
-  const bool split = tile_sort_mode() == 0;
+  const bool split = ranked || tile_sort_mode() == 0;
   const bool late = split && colors_ready;  // the colour quarter of the by-rank records is filled after the tile sort
   if (!late && colors_ready) GB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)colors_ready, 0));
   tile_scatter_kernel<<<gb::cdiv(G, kGaussBlock * kScatItems), kGaussBlock, (size_t)smem_tiles * 8, s>>>(
@@ -1058,7 +1091,7 @@ GB_API int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, co
       rec_colors_kernel<<<gb::cdiv(G, 256), 256, 0, s>>>(G, radii, rank_of, colors3, depths, rec_by_rank);
       gb::count_launches(1);
     }
-    if (cap > 0)
+    if (cap > 0 && !ranked)
       gather_records_kernel<<<(unsigned)gb::cdiv64(3 * cap, 256), 256, 0, s>>>((long long)cap, n_total, tile_ranks, rank_to_gid,
                                                                              rec_by_rank, gids_sorted, (float4*)records);
     gb::count_launches(3);

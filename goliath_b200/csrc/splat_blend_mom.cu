@@ -62,6 +62,36 @@ __device__ __forceinline__ float exp_neg(float s) {
   return r;
 }
 
+// RANKED staging: the tile's list is a list of sorted depth RANKS (4 B) into the by-rank record table [G,12] written
+// once per Gaussian by the binning; a stage is filled by 16-byte cp.async gathers (three per record) instead of one
+// bulk copy of materialised sorted records, which removes the binning's record gather (52 MB written + read per view).
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// arrival on `bar` once every cp.async this thread has issued so far has landed (the barrier's count includes it)
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// one warp stages `count` <= 128 records: stage slot i <- rec_by_rank[ranks[i]]
+__device__ __forceinline__ void stage_ranked(float4* stage, const float4* __restrict__ rec_by_rank,
+                                             const int* __restrict__ ranks, int count, int lane,
+                                             unsigned long long* bar) {
+  int r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r[k] = (lane + 32 * k < count) ? ranks[lane + 32 * k] : -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (r[k] >= 0) {
+      const float4* src = rec_by_rank + 3 * (size_t)r[k];
+      float4* dst = stage + 3 * (lane + 32 * k);
+      cp_async16(dst, src);
+      cp_async16(dst + 1, src + 1);
+      cp_async16(dst + 2, src + 2);
+    }
+  cp_async_arrive(bar);
+}
+
 // Does the record (centre (x, y), conic (A, B, Cc), opacity o) reach alpha >= 1/255 anywhere on the rectangle of pixel
 // centres [fx0, fx1] x [fy0, fy1]?  d = centre - pixel ranges over [x - fx1, x - fx0] x [y - fy1, y - fy0]; sigma(d) is
 // a positive-definite quadratic with its minimum at d = 0.  If 0 is outside the rectangle the minimiser lies on a face
@@ -101,11 +131,12 @@ __device__ __forceinline__ Tile make_tile(int tile_id, int tbx) {
 //               per-warp list of hit indices, then blends the list four entries per round (one LDS.128 fetches the four
 //               indices): rounds are full except the last one of a stage, and the mask walk (brev / flo / lop per hit
 //               on the uniform path) is gone.  Same per-pixel operations in the same order -> identical pixels.
-template <int C, bool LIST>
+template <int C, bool LIST, bool RANKED>
 __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
     int img_w, int img_h, int tbx, const int* order, int sched, const int2* __restrict__ tile_bins,
-    const float4* __restrict__ rec, const float* __restrict__ background, float* __restrict__ final_Ts,
-    int* __restrict__ final_idx, float* __restrict__ out_img) {
+    const float4* __restrict__ rec /* RANKED: the by-rank table */, const int* __restrict__ ranks /* RANKED only */,
+    const float* __restrict__ background, float* __restrict__ final_Ts, int* __restrict__ final_idx,
+    float* __restrict__ out_img) {
   __shared__ __align__(128) float4 s_rec[kFwdStages][kStageRecs * 3];
   __shared__ __align__(8) unsigned long long s_full[kFwdStages];
   __shared__ __align__(8) unsigned long long s_empty[kFwdStages];
@@ -118,7 +149,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
     s_tile = draw_tile(order, sched, tbx * ((img_h + 15) >> 4));
 #pragma unroll
     for (int s = 0; s < kFwdStages; ++s) {
-      mbar_init(&s_full[s], 1);
+      mbar_init(&s_full[s], RANKED ? 32 : 1);
       mbar_init(&s_empty[s], kPixelWarps);
     }
     s_ndone = 0;
@@ -130,6 +161,27 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
   const int2 range = tile_bins[tl.tile_id];
   const int num_batches = (range.y - range.x + kStageRecs - 1) / kStageRecs;
 
+  if (RANKED && warp == kPixelWarps) {  // --------------------- producer warp, all lanes: gathers by rank
+    volatile int* ndone = &s_ndone;
+    for (int b = 0; b < num_batches; ++b) {
+      const int s = b % kFwdStages;
+      if (b >= kFwdStages) {
+        int go = 1;
+        if (lane == 0) {
+          const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
+          while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
+          }
+          go = *ndone < kPixelWarps;
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        if (!go) break;
+      }
+      const int start = range.x + b * kStageRecs;
+      stage_ranked(&s_rec[s][0], rec, ranks + start, min(kStageRecs, range.y - start), lane, &s_full[s]);
+    }
+    cp_async_wait_all();  // every issued copy lands before the CTA retires
+    return;
+  }
   if (warp == kPixelWarps) {  // ------------------------------ producer warp (one lane)
     if (lane != 0) return;
     volatile int* ndone = &s_ndone;
@@ -317,9 +369,10 @@ constexpr int kSmM = kPixelWarps * kChunk * kMStride * 8;                   // 3
 constexpr int kSmVo = kPixelWarps * 32 * 16;                                // 4096
 constexpr int kBwdSmem = kSmRec + kSmEntries + kSmM + kSmVo;                // 74752
 
-template <int C>
+template <int C, bool RANKED>
 __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
-    int img_w, int img_h, int tbx, const int* order, int sched, const int* __restrict__ gids_sorted,
+    int img_w, int img_h, int tbx, const int* order, int sched,
+    const int* __restrict__ gids_sorted /* RANKED: rank_to_gid */, const int* __restrict__ ranks /* RANKED only */,
     const int2* __restrict__ tile_bins, const float4* __restrict__ rec, const float* __restrict__ background,
     const float* __restrict__ final_Ts, const int* __restrict__ final_idx, const float* __restrict__ v_output,
     const float* __restrict__ v_output_alpha, float* __restrict__ v_xy, float* __restrict__ v_conic,
@@ -373,7 +426,7 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
     s_cta_final = -1;
 #pragma unroll
     for (int s = 0; s < kBwdStages; ++s) {
-      mbar_init(&s_full[s], 1);
+      mbar_init(&s_full[s], RANKED ? 32 : 1);
       s_ticket[s] = 0;
     }
     fence_mbar_init();
@@ -393,8 +446,18 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
     mbar_expect_tx(&s_full[s], bytes);
     bulk_g2s(s_rec + s * kStageRecs * 3, rec + (size_t)lo * 3, bytes, &s_full[s]);
   };
-  if (tr == 0)
+  auto issue_ranked = [&](int k) {  // one whole warp
+    const int s = k % kBwdStages;
+    const int hi = last - k * kStageRecs;
+    const int lo = max(range.x, hi - kStageRecs + 1);
+    stage_ranked(s_rec + s * kStageRecs * 3, rec, ranks + lo, hi - lo + 1, lane, &s_full[s]);
+  };
+  if (RANKED) {
+    if (warp == 0)
+      for (int k = 0; k < min(kBwdStages, num_batches); ++k) issue_ranked(k);
+  } else if (tr == 0) {
     for (int k = 0; k < min(kBwdStages, num_batches); ++k) issue(k);
+  }
   // no CTA-wide barrier below this line
 
   // ---- one chunk of n <= 16 pending entries starting at entry `base`: phase A (lanes = pixels), phase B (lanes = hits)
@@ -443,7 +506,8 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
       const float4 a0 = E[(base + he) * 3], a1 = E[(base + he) * 3 + 1];
       // the Gaussian id is only needed by the REDs at the end: start its load now (padding entries: index 0)
       const int e_idx = __float_as_int(a1.z);
-      const int g_id = gids_sorted[e_idx == 0x7fffffff ? 0 : e_idx];
+      const int e_safe = e_idx == 0x7fffffff ? range.x : e_idx;
+      const int g_id = RANKED ? gids_sorted[ranks[e_safe]] : gids_sorted[e_safe];
       const float2* Mrow = M + hh * kMStride + half * 16;
       const float4* V = VO + half * 16;
       float g[4] = {0.f, 0.f, 0.f, 0.f};
@@ -558,17 +622,26 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
     }
     // this warp is finished with the stage: the last of the 8 through recycles it
     __syncwarp();
+    int refill = 0;
     if (lane == 0) {
       __threadfence_block();  // release this warp's reads of the stage
       const int ticket = atomicAdd(&s_ticket[s], 1);
       if (ticket == kPixelWarps - 1) {
         __threadfence_block();
         s_ticket[s] = 0;
-        if (k + kBwdStages < num_batches) issue(k + kBwdStages);
+        if (k + kBwdStages < num_batches) {
+          if (RANKED) refill = 1;
+          else issue(k + kBwdStages);
+        }
       }
+    }
+    if (RANKED) {
+      refill = __shfl_sync(0xffffffffu, refill, 0);
+      if (refill) issue_ranked(k + kBwdStages);
     }
   }
   if (cnt > 0) chunk(0, pad4(cnt));
+  if (RANKED) cp_async_wait_all();
 }
 
 // ================================================================== four lighting conditions per pass (OLAT)
@@ -590,6 +663,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
   __shared__ __align__(8) unsigned long long s_full[kFwdStages];
   __shared__ __align__(8) unsigned long long s_empty[kFwdStages];
   __shared__ int s_ndone;
+  __shared__ __align__(16) int s_hits[kPixelWarps][kStageRecs + 4];
   __shared__ int s_tile;
 
   const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
@@ -671,48 +745,57 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
     const float4* sr = s_rec[s];
     const int batch_start = range.x + b * kStageRecs;
     const int batch_size = min(kStageRecs, range.y - batch_start);
-    for (int c0 = 0; c0 < batch_size; c0 += 32) {
-      const int ti = c0 + lane;
-      bool hit = false;
-      if (ti < batch_size) hit = footprint_hit(sr[ti * kMRQ], &sr[ti * kMRQ + 1], fx0, fx1, fy0, fy1);
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        int t[2];
-        bool live[2];
+    {  // cull the whole stage into the warp's hit list, then blend the list two entries per round (see the single pass)
+      int* hl = s_hits[warp];
+      const unsigned lt = (1u << lane) - 1u;
+      int cnt = 0;
+#pragma unroll 4
+      for (int c0 = 0; c0 < batch_size; c0 += 32) {
+        const int ti = c0 + lane;
+        bool hit = false;
+        if (ti < batch_size) hit = footprint_hit(sr[ti * kMRQ], &sr[ti * kMRQ + 1], fx0, fx1, fy0, fy1);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (hit) hl[cnt + __popc(mask & lt)] = ti;
+        cnt += __popc(mask);
+      }
+      __syncwarp();
+      for (int i0 = 0; i0 < cnt; i0 += 16) {
+        const int i1 = min(i0 + 16, cnt);
+        for (int i = i0; i < i1; i += 2) {
+          const int2 e = *reinterpret_cast<const int2*>(hl + i);
+          bool live[2];
+          int t[2];
+          live[0] = true; live[1] = i + 1 < cnt;
+          t[0] = e.x; t[1] = live[1] ? e.y : e.x;
+          float alpha[2], sig[2];
+          float4 col[2][3];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {  // two hits per round: 2 x 12 colour registers
-          live[u] = mask != 0;
-          t[u] = live[u] ? c0 + __ffs(mask) - 1 : t[0];
-          mask &= mask - 1;
-        }
-        float alpha[2], sig[2];
-        float4 col[2][3];
+          for (int u = 0; u < 2; ++u) {
+            const float4 q0 = sr[t[u] * kMRQ], q1 = sr[t[u] * kMRQ + 1];
+            col[u][0] = sr[t[u] * kMRQ + 2]; col[u][1] = sr[t[u] * kMRQ + 3]; col[u][2] = sr[t[u] * kMRQ + 4];
+            const float dx = q0.x - px, dy = q0.y - py;
+            sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+            alpha[u] = fminf(kAlphaMaxFwd, q1.w * exp_neg(sig[u]));
+          }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float4 q0 = sr[t[u] * kMRQ], q1 = sr[t[u] * kMRQ + 1];
-          col[u][0] = sr[t[u] * kMRQ + 2]; col[u][1] = sr[t[u] * kMRQ + 3]; col[u][2] = sr[t[u] * kMRQ + 4];
-          const float dx = q0.x - px, dy = q0.y - py;
-          sig[u] = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
-          alpha[u] = fminf(kAlphaMaxFwd, q1.w * exp_neg(sig[u]));
-        }
+          for (int u = 0; u < 2; ++u) {
+            const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
+            const float next_T = T * (1.f - alpha[u]);
+            const bool stop = ok && (next_T <= kTEps);
+            const bool take = ok && !stop;
+            done = done || stop;
+            if (take) {
+              const float vis = alpha[u] * T;
+              const float cc[kMC] = {col[u][0].x, col[u][0].y, col[u][0].z, col[u][0].w, col[u][1].x, col[u][1].y,
+                                     col[u][1].z, col[u][1].w, col[u][2].x, col[u][2].y, col[u][2].z, col[u][2].w};
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const bool ok = live[u] && !done && !(sig[u] < 0.f) && !(alpha[u] < kAlphaMin);
-          const float next_T = T * (1.f - alpha[u]);
-          const bool stop = ok && (next_T <= kTEps);
-          const bool take = ok && !stop;
-          done = done || stop;
-          if (take) {
-            const float vis = alpha[u] * T;
-            const float cc[kMC] = {col[u][0].x, col[u][0].y, col[u][0].z, col[u][0].w, col[u][1].x, col[u][1].y,
-                                   col[u][1].z, col[u][1].w, col[u][2].x, col[u][2].y, col[u][2].z, col[u][2].w};
-#pragma unroll
-            for (int c = 0; c < kMC; ++c) acc[c] += cc[c] * vis;
-            T = next_T;
+              for (int c = 0; c < kMC; ++c) acc[c] += cc[c] * vis;
+              T = next_T;
+            }
           }
         }
+        if (__all_sync(0xffffffffu, done)) break;
       }
-      if (__all_sync(0xffffffffu, done)) break;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);
@@ -1039,20 +1122,23 @@ static bool fwd_list_variant() {
   return !(e && !strcmp(e, "rounds"));
 }
 
-int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
-                   const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
-                   cudaStream_t s) {
+// ranks == nullptr: `records` are the sorted 48-byte records; else `records` is the by-rank table and `ranks` the sorted ranks
+static int launch_fwd_any(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
+                          const float* records, const int32_t* ranks, const float* background, float* out_img,
+                          float* final_Ts, int32_t* final_idx, cudaStream_t s) {
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   if (sched && !tile_order) return (int)cudaErrorInvalidValue;
   static const bool list = fwd_list_variant();
-#define GB_FWD_MOM(CC, LL)                                                                                              \
-  blend_fwd_ilp_kernel<CC, LL><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched,                  \
-                                                                 (const int2*)tile_bins, (const float4*)records,        \
-                                                                 background, final_Ts, final_idx, out_img)
-  if (channels == 3) {
-    if (list) GB_FWD_MOM(3, true); else GB_FWD_MOM(3, false);
+#define GB_FWD_MOM(CC, LL, RR)                                                                                          \
+  blend_fwd_ilp_kernel<CC, LL, RR><<<tbx * tby, kFwdThreads, 0, s>>>(img_w, img_h, tbx, tile_order, sched,              \
+                                                                     (const int2*)tile_bins, (const float4*)records,    \
+                                                                     ranks, background, final_Ts, final_idx, out_img)
+  if (ranks) {
+    if (channels == 3) GB_FWD_MOM(3, true, true); else GB_FWD_MOM(4, true, true);
+  } else if (channels == 3) {
+    if (list) GB_FWD_MOM(3, true, false); else GB_FWD_MOM(3, false, false);
   } else {
-    if (list) GB_FWD_MOM(4, true); else GB_FWD_MOM(4, false);
+    if (list) GB_FWD_MOM(4, true, false); else GB_FWD_MOM(4, false, false);
   }
 #undef GB_FWD_MOM
   gb::count_launches(1);
@@ -1060,33 +1146,77 @@ int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins,
   return 0;
 }
 
-int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
-                   const int32_t* tile_order, int sched, const float* records, const float* background, const float* final_Ts,
-                   const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
-                   float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s) {
+static int launch_bwd_any(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* ranks,
+                          const int32_t* tile_bins, const int32_t* tile_order, int sched, const float* records,
+                          const float* background, const float* final_Ts, const int32_t* final_idx, const float* v_output,
+                          const float* v_output_alpha, float* v_xy, float* v_conic, float* v_colors, float* v_opacity,
+                          cudaStream_t s) {
   const int tbx = gb::cdiv(img_w, 16), tby = gb::cdiv(img_h, 16);
   if (sched && !tile_order) return (int)cudaErrorInvalidValue;
   int dev = 0;
   GB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !g_attr_set[dev]) {
-    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    GB_CUDA(cudaFuncSetAttribute(blend_bwd_mom_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     if (dev >= 0 && dev < 64) g_attr_set[dev] = true;
   }
-  if (channels == 3)
-    blend_bwd_mom_kernel<3><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(
-        img_w, img_h, tbx, tile_order, sched, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
-        final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
-  else
-    blend_bwd_mom_kernel<4><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(
-        img_w, img_h, tbx, tile_order, sched, gids_sorted, (const int2*)tile_bins, (const float4*)records, background, final_Ts,
-        final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity);
+#define GB_BWD_MOM(CC, RR)                                                                                              \
+  blend_bwd_mom_kernel<CC, RR><<<tbx * tby, kBwdThreads, kBwdSmem, s>>>(                                                \
+      img_w, img_h, tbx, tile_order, sched, gids_sorted, ranks, (const int2*)tile_bins, (const float4*)records, background, \
+      final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity)
+  if (ranks) {
+    if (channels == 3) GB_BWD_MOM(3, true); else GB_BWD_MOM(4, true);
+  } else {
+    if (channels == 3) GB_BWD_MOM(3, false); else GB_BWD_MOM(4, false);
+  }
+#undef GB_BWD_MOM
   gb::count_launches(1);
   GB_CHECK_LAUNCH();
   return 0;
 }
 
+int launch_fwd_mom(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order, int sched,
+                   const float* records, const float* background, float* out_img, float* final_Ts, int32_t* final_idx,
+                   cudaStream_t s) {
+  return launch_fwd_any(img_h, img_w, channels, tile_bins, tile_order, sched, records, nullptr, background, out_img, final_Ts,
+                        final_idx, s);
+}
+
+int launch_bwd_mom(int img_h, int img_w, int channels, const int32_t* gids_sorted, const int32_t* tile_bins,
+                   const int32_t* tile_order, int sched, const float* records, const float* background, const float* final_Ts,
+                   const int32_t* final_idx, const float* v_output, const float* v_output_alpha, float* v_xy,
+                   float* v_conic, float* v_colors, float* v_opacity, cudaStream_t s) {
+  return launch_bwd_any(img_h, img_w, channels, gids_sorted, nullptr, tile_bins, tile_order, sched, records, background,
+                        final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors, v_opacity, s);
+}
+
 }  // namespace gbblend
+
+// ---------------------------------------------------------------- blend straight from the by-rank record table, C ABI
+// ranks_sorted [cap] (per tile: depth ranks in blend order), rec_by_rank [G,12], rank_to_gid [G]: outputs of
+// gb_bin_tiles_ranked.  Same results as gb_rasterize_packed_fwd/bwd on the materialised records; final_idx indexes
+// ranks_sorted.  channels 3 or 4; tile_order as for the packed kernels (launch order, may be NULL).
+GB_API int gb_rasterize_ranked_fwd(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+                                   const int32_t* ranks_sorted, const float* rec_by_rank, const float* background,
+                                   float* out_img, float* final_Ts, int32_t* final_idx, void* stream) {
+  if (img_h <= 0 || img_w <= 0) return 0;
+  if ((channels != 3 && channels != 4) || !ranks_sorted) return (int)cudaErrorInvalidValue;
+  return gbblend::launch_fwd_any(img_h, img_w, channels, tile_bins, tile_order, 0, rec_by_rank, ranks_sorted, background,
+                                 out_img, final_Ts, final_idx, (cudaStream_t)stream);
+}
+GB_API int gb_rasterize_ranked_bwd(int img_h, int img_w, int channels, const int32_t* rank_to_gid,
+                                   const int32_t* ranks_sorted, const int32_t* tile_bins, const int32_t* tile_order,
+                                   const float* rec_by_rank, const float* background, const float* final_Ts,
+                                   const int32_t* final_idx, const float* v_output, const float* v_output_alpha,
+                                   float* v_xy, float* v_conic, float* v_colors, float* v_opacity, void* stream) {
+  if (img_h <= 0 || img_w <= 0) return 0;
+  if ((channels != 3 && channels != 4) || !ranks_sorted) return (int)cudaErrorInvalidValue;
+  return gbblend::launch_bwd_any(img_h, img_w, channels, rank_to_gid, ranks_sorted, tile_bins, tile_order, 0, rec_by_rank,
+                                 background, final_Ts, final_idx, v_output, v_output_alpha, v_xy, v_conic, v_colors,
+                                 v_opacity, (cudaStream_t)stream);
+}
 
 // ---------------------------------------------------------------- four lighting conditions per pass (OLAT), C ABI
 // wide records [cap, 20] fp32: geometry of the 48-byte records + 4 x rgb.

@@ -21,6 +21,9 @@ _OVERFLOW = {}
 BINNING = os.environ.get("GOLIATH_B200_BINNING", "buckets")
 # sync-free path as two autograd nodes (projection | binning + blend), see render_fused_split; "0" keeps the single node
 SPLIT = os.environ.get("GOLIATH_B200_RENDER_SPLIT", "1") != "0"
+# records of the two-node path: "ranked" (the blend stages records by depth rank from a per-Gaussian table, default) or
+# "packed" (sorted 48-byte records materialised by the binning's gather, as in the single-node path)
+RANKED = os.environ.get("GOLIATH_B200_RECORDS", "ranked") != "packed"
 
 
 def _overflow_flag(dev):
@@ -262,32 +265,49 @@ class _BinBlend(Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             sched = 1 if L.gb_get_blend_mode() in (2, 4) else 0
-            gids = torch.empty(cap, **i32)
             order = torch.empty(L.gb_tile_schedule_ints(T) if sched else T, **i32)
-            records = torch.empty(cap, 12, **f32)
             bins = torch.empty(T, 2, **i32)
             ws = _workspace(dev, L.gb_bin_tiles_workspace_bytes(G, T, cap))
             ev = None
             if colors_event is not None:
                 ev = colors_event.cuda_event
                 colors.record_stream(torch.cuda.current_stream(dev))
-            _lib.check(L.gb_bin_tiles_pack_ev(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
-                                              _lib.ptr(colors), _lib.ptr(opacity), _lib.ptr(comp), H, W, BW, cap,
-                                              _lib.ptr(bins), _lib.ptr(order), sched, _lib.ptr(gids), _lib.ptr(records),
-                                              None, _lib.ptr(_overflow_flag(dev)), _lib.ptr(ws), ev, st),
-                       "bin_tiles_pack_ev")
-            _lib.check((L.gb_rasterize_sched_fwd if sched else L.gb_rasterize_packed_fwd)(
-                H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4), _lib.ptr(out4),
-                _lib.ptr(final_Ts), _lib.ptr(final_idx), st), "rasterize_packed_forward")
-        ctx.save_for_backward(opacity, comp, bg4, gids, bins, order, records, final_Ts, final_idx)
-        ctx.meta = (G, H, W, sched)
+            # rank-staged records (default with the mom blend, launch-order tiles): the blend gathers each stage from the
+            # by-rank table, the sorted 48-byte records are never materialised (csrc/splat_blend_mom.cu, RANKED)
+            ranked = RANKED and not sched and L.gb_get_blend_mode() == 3
+            if ranked:
+                gids = torch.empty(G, **i32)            # rank -> Gaussian id
+                ranks = torch.empty(cap, **i32)         # per tile: depth ranks in blend order
+                records = torch.empty(G, 12, **f32)     # one record per Gaussian, by rank
+                _lib.check(L.gb_bin_tiles_ranked(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
+                                                 _lib.ptr(colors), _lib.ptr(opacity), _lib.ptr(comp), H, W, BW, cap,
+                                                 _lib.ptr(bins), _lib.ptr(order), sched, _lib.ptr(ranks),
+                                                 _lib.ptr(records), _lib.ptr(gids), None, _lib.ptr(_overflow_flag(dev)),
+                                                 _lib.ptr(ws), ev, st), "bin_tiles_ranked")
+                _lib.check(L.gb_rasterize_ranked_fwd(H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(ranks),
+                                                     _lib.ptr(records), _lib.ptr(bg4), _lib.ptr(out4), _lib.ptr(final_Ts),
+                                                     _lib.ptr(final_idx), st), "rasterize_ranked_forward")
+            else:
+                gids = torch.empty(cap, **i32)
+                ranks = gids  # unused
+                records = torch.empty(cap, 12, **f32)
+                _lib.check(L.gb_bin_tiles_pack_ev(G, _lib.ptr(xys), _lib.ptr(depths), _lib.ptr(radii), _lib.ptr(conics),
+                                                  _lib.ptr(colors), _lib.ptr(opacity), _lib.ptr(comp), H, W, BW, cap,
+                                                  _lib.ptr(bins), _lib.ptr(order), sched, _lib.ptr(gids),
+                                                  _lib.ptr(records), None, _lib.ptr(_overflow_flag(dev)), _lib.ptr(ws), ev,
+                                                  st), "bin_tiles_pack_ev")
+                _lib.check((L.gb_rasterize_sched_fwd if sched else L.gb_rasterize_packed_fwd)(
+                    H, W, 4, _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4), _lib.ptr(out4),
+                    _lib.ptr(final_Ts), _lib.ptr(final_idx), st), "rasterize_packed_forward")
+        ctx.save_for_backward(opacity, comp, bg4, gids, bins, order, records, final_Ts, final_idx, ranks)
+        ctx.meta = (G, H, W, sched, ranked)
         ctx.set_materialize_grads(False)
         return out4, 1 - final_Ts
 
     @staticmethod
     def backward(ctx, v_out4, v_alpha):
-        opacity, comp, bg4, gids, bins, order, records, final_Ts, final_idx = ctx.saved_tensors
-        G, H, W, sched = ctx.meta
+        opacity, comp, bg4, gids, bins, order, records, final_Ts, final_idx, ranks = ctx.saved_tensors
+        G, H, W, sched, ranked = ctx.meta
         dev = opacity.device
         L = _lib.lib()
         f32 = dict(device=dev, dtype=torch.float32)
@@ -300,10 +320,16 @@ class _BinBlend(Function):
         v_comp, v_depth = torch.empty(G, **f32), torch.empty(G, **f32)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            _lib.check((L.gb_rasterize_sched_bwd if sched else L.gb_rasterize_packed_bwd)(
-                H, W, 4, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4),
-                _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out4), _lib.ptr(v_alpha), _lib.ptr(v_xy),
-                _lib.ptr(v_conic), _lib.ptr(v_col4), _lib.ptr(v_opeff), st), "rasterize_packed_backward")
+            if ranked:
+                _lib.check(L.gb_rasterize_ranked_bwd(
+                    H, W, 4, _lib.ptr(gids), _lib.ptr(ranks), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records),
+                    _lib.ptr(bg4), _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out4), _lib.ptr(v_alpha),
+                    _lib.ptr(v_xy), _lib.ptr(v_conic), _lib.ptr(v_col4), _lib.ptr(v_opeff), st), "rasterize_ranked_backward")
+            else:
+                _lib.check((L.gb_rasterize_sched_bwd if sched else L.gb_rasterize_packed_bwd)(
+                    H, W, 4, _lib.ptr(gids), _lib.ptr(bins), _lib.ptr(order), _lib.ptr(records), _lib.ptr(bg4),
+                    _lib.ptr(final_Ts), _lib.ptr(final_idx), _lib.ptr(v_out4), _lib.ptr(v_alpha), _lib.ptr(v_xy),
+                    _lib.ptr(v_conic), _lib.ptr(v_col4), _lib.ptr(v_opeff), st), "rasterize_packed_backward")
             _lib.check(L.gb_splat_grad_unpack(G, _lib.ptr(v_col4), _lib.ptr(v_opeff), _lib.ptr(opacity), _lib.ptr(comp),
                                               _lib.ptr(v_colors), _lib.ptr(v_opacity), _lib.ptr(v_comp), _lib.ptr(v_depth),
                                               st), "splat_grad_unpack")

@@ -198,6 +198,27 @@ int gb_bin_tiles_pack_ev(int G, const float* xys, const float* depths, const int
                          int32_t* gids_sorted, float* records, int32_t* n_out, int32_t* overflow, void* workspace,
                          void* colors_ready, void* stream);
 
+/* Binning WITHOUT the sorted-record gather, for gb_rasterize_ranked_fwd/bwd: ranks_sorted [cap] (per tile, the depth ranks
+ * in blend order), rec_by_rank [G,12] (one 48-byte record per visible Gaussian, at its depth rank) and rank_to_gid [G] are
+ * written to the CALLER's arrays (they must live until the backward).  Everything else as gb_bin_tiles_pack_ev.  No
+ * counterpart in gsplat: it replaces the per-intersection sorted arrays of bin_and_sort_gaussians by per-Gaussian ones. */
+int gb_bin_tiles_ranked(int G, const float* xys, const float* depths, const int32_t* radii, const float* conics,
+                        const float* colors3, const float* opacity, const float* compensation, int img_h, int img_w,
+                        int block_width, int64_t cap, int32_t* tile_bins, int32_t* tile_order, int tile_sched,
+                        int32_t* ranks_sorted, float* rec_by_rank, int32_t* rank_to_gid, int32_t* n_out, int32_t* overflow,
+                        void* workspace, void* colors_ready, void* stream);
+/* Blend straight from the by-rank table (csrc/splat_blend_mom.cu, RANKED staging: 16-byte cp.async gathers by rank into
+ * the stage ring instead of bulk copies of materialised sorted records).  Same results as gb_rasterize_packed_fwd/bwd;
+ * final_idx indexes ranks_sorted.  channels 3 or 4; tile_order = launch order (gb_tile_order) or NULL. */
+int gb_rasterize_ranked_fwd(int img_h, int img_w, int channels, const int32_t* tile_bins, const int32_t* tile_order,
+                            const int32_t* ranks_sorted, const float* rec_by_rank, const float* background,
+                            float* out_img, float* final_Ts, int32_t* final_idx, void* stream);
+int gb_rasterize_ranked_bwd(int img_h, int img_w, int channels, const int32_t* rank_to_gid, const int32_t* ranks_sorted,
+                            const int32_t* tile_bins, const int32_t* tile_order, const float* rec_by_rank,
+                            const float* background, const float* final_Ts, const int32_t* final_idx,
+                            const float* v_output, const float* v_output_alpha, float* v_xy, float* v_conic,
+                            float* v_colors, float* v_opacity, void* stream);
+
 /* launch order of the tiles, longest list first: order [T] int32 */
 int gb_tile_order(int num_tiles, const int32_t* tile_bins, int32_t* order, void* stream);
 

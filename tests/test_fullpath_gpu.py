@@ -93,7 +93,7 @@ def test_benchmarked_binning_is_bit_exact_at_bench_size(orc, cuda):
     assert np.array_equal(t2n(gids[:n]), b["gaussian_ids_sorted"]), "gaussian_ids_sorted"
 
 
-def _step_variant(cuda, G, split, side_stream, graph=False):
+def _step_variant(cuda, G, split, side_stream, graph=False, ranked=True):
     """bench.gpu_step with the sync-free render as one autograd node or two, shade on the main or on the side stream."""
     import bench
     from goliath_b200 import synthetic
@@ -103,8 +103,8 @@ def _step_variant(cuda, G, split, side_stream, graph=False):
     c = synthetic.ring_camera(1, img_h=bench.H, img_w=bench.W)
     cam = dict(Rt=c["viewmat"][None].to(cuda), intr=(c["fx"], c["fy"], c["cx"], c["cy"]))
     leaves = {k: v.detach().requires_grad_() for k, v in bench.unpack(bench.packed_scene(G).to(cuda)).items()}
-    old = (fused.SPLIT, bench.SHADE_STREAM)
-    fused.SPLIT, bench.SHADE_STREAM = split, side_stream
+    old = (fused.SPLIT, bench.SHADE_STREAM, fused.RANKED)
+    fused.SPLIT, bench.SHADE_STREAM, fused.RANKED = split, side_stream, ranked
     try:
         cap = max(8 * G, 1 << 20)
         if graph:
@@ -126,7 +126,7 @@ def _step_variant(cuda, G, split, side_stream, graph=False):
             rgb, alpha, depth = bench.gpu_step(leaves, cam, li, capacity=cap)
         torch.cuda.synchronize()
     finally:
-        fused.SPLIT, bench.SHADE_STREAM = old
+        fused.SPLIT, bench.SHADE_STREAM, fused.RANKED = old
     return t2n(rgb), t2n(alpha), t2n(depth), {k: t2n(v.grad) for k, v in leaves.items()}
 
 
@@ -137,10 +137,11 @@ def test_split_nodes_and_side_stream_match_single_node(cuda, graph):
     images identical, gradients equal up to the order of the atomic adds.  Also under CUDA-graph capture (fork/join)."""
     G = 60_000
     ref = _step_variant(cuda, G, split=False, side_stream=False)
-    for split, side in ((True, False), (True, True), (False, True)):
-        got = _step_variant(cuda, G, split, side, graph=graph)
+    for split, side, ranked in ((True, False, True), (True, True, True), (True, True, False), (True, False, False),
+                                (False, True, False)):
+        got = _step_variant(cuda, G, split, side, graph=graph, ranked=ranked)
         for name, a, b in zip(("rgb", "alpha", "depth"), got[:3], ref[:3]):
-            assert np.array_equal(a, b), (name, split, side)
+            assert np.array_equal(a, b), (name, split, side, ranked)
         for k, want in ref[3].items():
             assert_close(got[3][k], want, rtol=1e-4, atol=1e-5 * float(np.abs(want).max()), frac=0.9999,
-                         what="grad %s split=%s side=%s" % (k, split, side))
+                         what="grad %s split=%s side=%s ranked=%s" % (k, split, side, ranked))

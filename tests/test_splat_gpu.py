@@ -615,3 +615,92 @@ def test_bin_tiles_matches_key_sort(cuda, case, rank_sort):
                 pos = {v: i for i, v in enumerate(ref_list.tolist())}
                 idx = [pos[v] for v in mine.tolist()]
                 assert idx == sorted(idx) and len(set(idx)) == len(idx)
+
+
+@pytest.mark.parametrize("case", ["dense96", "ragged", "ties", "big", "flat_depth_like"])
+@pytest.mark.parametrize("channels", [3, 4])
+def test_ranked_binning_and_blend_match_packed(cuda, case, channels):
+    """gb_bin_tiles_ranked + gb_rasterize_ranked_fwd/bwd (records staged by depth rank from the per-Gaussian table,
+    no sorted-record gather) against gb_bin_tiles_pack + gb_rasterize_packed_fwd/bwd: rank_to_gid[ranks_sorted] and
+    rec_by_rank[ranks_sorted] are the sorted ids / records bit for bit, images / final_T / final_idx identical, gradients
+    equal up to the order of the atomic adds."""
+    from goliath_b200 import _lib
+    from goliath_b200.gsplat import utils as gu
+
+    extra = {"big": (dict(G=150_000, img_h=512, img_w=384, seed=13), 16, 6.0),
+             "flat_depth_like": (dict(G=6000, img_h=96, img_w=80, seed=31, cam=0), 16, 10.0)}
+    kw, bw, mult = CASES[case] if case in CASES else extra[case]
+    if bw != 16:
+        pytest.skip("the blend kernels are block_width 16")
+    s = small_scene(**kw)
+    H, W = s["img_h"], s["img_w"]
+    xys, depths, radii, conics, comp, nth, cov3d = _project_gpu(s, cuda, bw, mult)
+    t = _dev(s, cuda)
+    colors, opacity = t["colors"].contiguous(), t["opacity"].contiguous()
+    G = xys.shape[0]
+    L = _lib.lib()
+    st = _lib.stream_ptr(cuda)
+    n, _ = gu.compute_cumulative_intersects(nth)
+    tb = gu._tile_bounds(H, W, bw)
+    T = tb[0] * tb[1]
+    cap = n + 33
+    i32 = dict(dtype=torch.int32, device=cuda)
+    ws = torch.empty(L.gb_bin_tiles_workspace_bytes(G, T, cap), dtype=torch.uint8, device=cuda)
+    ovf = torch.zeros(1, **i32)
+    # packed
+    bins, order = torch.empty(T, 2, **i32), torch.empty(T, **i32)
+    gids, rec = torch.empty(cap, **i32), torch.empty(cap, 12, device=cuda)
+    _lib.check(L.gb_bin_tiles_pack(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
+                                   colors.data_ptr(), opacity.data_ptr(), comp.data_ptr(), H, W, bw, cap, bins.data_ptr(),
+                                   order.data_ptr(), 0, gids.data_ptr(), rec.data_ptr(), None, ovf.data_ptr(),
+                                   ws.data_ptr(), st), "bin_tiles_pack")
+    # ranked (twice: the caller's arrays are rewritten, the shared workspace is reused)
+    for _ in range(2):
+        bins2, order2 = torch.empty(T, 2, **i32), torch.empty(T, **i32)
+        ranks = torch.full((cap,), -7, **i32)
+        rbr = torch.full((G, 12), float("nan"), device=cuda)
+        r2g = torch.full((G,), -7, **i32)
+        _lib.check(L.gb_bin_tiles_ranked(G, xys.data_ptr(), depths.data_ptr(), radii.data_ptr(), conics.data_ptr(),
+                                         colors.data_ptr(), opacity.data_ptr(), comp.data_ptr(), H, W, bw, cap,
+                                         bins2.data_ptr(), order2.data_ptr(), 0, ranks.data_ptr(), rbr.data_ptr(),
+                                         r2g.data_ptr(), None, ovf.data_ptr(), ws.data_ptr(), None, st), "bin_tiles_ranked")
+    torch.cuda.synchronize()
+    assert int(ovf) == 0 and torch.equal(bins, bins2) and torch.equal(order, order2)
+    rk = ranks[:n].long()
+    assert bool((rk >= 0).all()) and bool((ranks[n:] == -7).all())
+    assert torch.equal(r2g[rk], gids[:n])
+    assert torch.equal(rbr[rk].view(torch.int32), rec[:n].view(torch.int32))
+    # blend
+    C = channels
+    if C == 3:  # 3-channel records: the colour quarter's 4th float is ignored
+        pass
+    bg = torch.rand(C, device=cuda)
+    outs = []
+    v_out = torch.randn(H, W, C, device=cuda)
+    v_alpha = torch.randn(H, W, device=cuda)
+    for ranked in (False, True):
+        out = torch.empty(H, W, C, device=cuda)
+        Ts = torch.empty(H, W, device=cuda)
+        fi = torch.empty(H, W, **i32)
+        gx, gc, gcol, go = (torch.zeros(G, 2, device=cuda), torch.zeros(G, 3, device=cuda),
+                            torch.zeros(G, C, device=cuda), torch.zeros(G, 1, device=cuda))
+        if ranked:
+            _lib.check(L.gb_rasterize_ranked_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), ranks.data_ptr(), rbr.data_ptr(),
+                                                 bg.data_ptr(), out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "ranked fwd")
+            _lib.check(L.gb_rasterize_ranked_bwd(H, W, C, r2g.data_ptr(), ranks.data_ptr(), bins.data_ptr(), order.data_ptr(),
+                                                 rbr.data_ptr(), bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(),
+                                                 v_out.data_ptr(), v_alpha.data_ptr(), gx.data_ptr(), gc.data_ptr(),
+                                                 gcol.data_ptr(), go.data_ptr(), st), "ranked bwd")
+        else:
+            _lib.check(L.gb_rasterize_packed_fwd(H, W, C, bins.data_ptr(), order.data_ptr(), rec.data_ptr(), bg.data_ptr(),
+                                                 out.data_ptr(), Ts.data_ptr(), fi.data_ptr(), st), "packed fwd")
+            _lib.check(L.gb_rasterize_packed_bwd(H, W, C, gids.data_ptr(), bins.data_ptr(), order.data_ptr(), rec.data_ptr(),
+                                                 bg.data_ptr(), Ts.data_ptr(), fi.data_ptr(), v_out.data_ptr(),
+                                                 v_alpha.data_ptr(), gx.data_ptr(), gc.data_ptr(), gcol.data_ptr(),
+                                                 go.data_ptr(), st), "packed bwd")
+        torch.cuda.synchronize()
+        outs.append((t2n(out), t2n(Ts), t2n(fi), [t2n(g) for g in (gx, gc, gcol, go)]))
+    (o0, T0, f0, g0), (o1, T1, f1, g1) = outs
+    assert np.array_equal(o0, o1) and np.array_equal(T0, T1) and np.array_equal(f0, f1)
+    for a, b, name in zip(g1, g0, ("v_xy", "v_conic", "v_colors", "v_opacity")):
+        assert_close(a, b, rtol=1e-4, atol=1e-5 * float(np.abs(b).max()), frac=0.9999, what=name)
