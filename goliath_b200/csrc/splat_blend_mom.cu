@@ -163,6 +163,16 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
 
   if (RANKED && warp == kPixelWarps) {  // --------------------- producer warp, all lanes: gathers by rank
     volatile int* ndone = &s_ndone;
+    // the ranks of stage b + 1 are loaded while the producer waits for stage b's slot: the per-stage chain is then one
+    // L2 round trip (the gathers), not two
+    int r[4];
+    auto load_ranks = [&](int b) {
+      const int start = range.x + b * kStageRecs;
+      const int count = min(kStageRecs, range.y - start);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = (b < num_batches && lane + 32 * k < count) ? ranks[start + lane + 32 * k] : -1;
+    };
+    load_ranks(0);
     for (int b = 0; b < num_batches; ++b) {
       const int s = b % kFwdStages;
       if (b >= kFwdStages) {
@@ -176,8 +186,17 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
         go = __shfl_sync(0xffffffffu, go, 0);
         if (!go) break;
       }
-      const int start = range.x + b * kStageRecs;
-      stage_ranked(&s_rec[s][0], rec, ranks + start, min(kStageRecs, range.y - start), lane, &s_full[s]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r[k] >= 0) {
+          const float4* src = rec + 3 * (size_t)r[k];
+          float4* dst = &s_rec[s][3 * (lane + 32 * k)];
+          cp_async16(dst, src);
+          cp_async16(dst + 1, src + 1);
+          cp_async16(dst + 2, src + 2);
+        }
+      cp_async_arrive(&s_full[s]);
+      load_ranks(b + 1);
     }
     cp_async_wait_all();  // every issued copy lands before the CTA retires
     return;
