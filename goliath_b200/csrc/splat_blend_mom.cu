@@ -47,6 +47,8 @@ constexpr int kChunk = 16;            // hits per transposed-reduction chunk
 constexpr int kEntryCap = 48;         // pending entries per warp: < kChunk left over + up to 32 new
 constexpr int kMStride = 33;          // float2 row stride of the (hit, pixel) matrix: odd -> conflict-free both ways
 constexpr float kCullMargin = 2e-3f;  // slack of the exact cull test (ex2.approx / lg2.approx / rounding)
+constexpr unsigned kSpinNs = 32;      // forward: pause between barrier probes of a warp that waits for data / a free slot
+constexpr unsigned kParkNs = 200;     // forward: pause of a saturated warp (it only keeps the barrier phases aligned)
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -73,25 +75,9 @@ __device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// one warp stages `count` <= 128 records: stage slot i <- rec_by_rank[ranks[i]]
-__device__ __forceinline__ void stage_ranked(float4* stage, const float4* __restrict__ rec_by_rank,
-                                             const int* __restrict__ ranks, int count, int lane,
-                                             unsigned long long* bar) {
-  int r[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) r[k] = (lane + 32 * k < count) ? ranks[lane + 32 * k] : -1;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (r[k] >= 0) {
-      const float4* src = rec_by_rank + 3 * (size_t)r[k];
-      float4* dst = stage + 3 * (lane + 32 * k);
-      cp_async16(dst, src);
-      cp_async16(dst + 1, src + 1);
-      cp_async16(dst + 2, src + 2);
-    }
-  cp_async_arrive(bar);
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-
 // Does the record (centre (x, y), conic (A, B, Cc), opacity o) reach alpha >= 1/255 anywhere on the rectangle of pixel
 // centres [fx0, fx1] x [fy0, fy1]?  d = centre - pixel ranges over [x - fx1, x - fx0] x [y - fy1, y - fy0]; sigma(d) is
 // a positive-definite quadratic with its minimum at d = 0.  If 0 is outside the rectangle the minimiser lies on a face
@@ -179,8 +165,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
         int go = 1;
         if (lane == 0) {
           const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
-          while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
-          }
+          while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) __nanosleep(kSpinNs);
           go = *ndone < kPixelWarps;
         }
         go = __shfl_sync(0xffffffffu, go, 0);
@@ -209,8 +194,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
       const int s = b % kFwdStages;
       if (b >= kFwdStages) {
         const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
-        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
-        }
+        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) __nanosleep(kSpinNs);
         if (*ndone >= kPixelWarps) break;  // every pixel of the tile is saturated: nothing more to fetch
       }
       const int start = range.x + b * kStageRecs;
@@ -250,6 +234,10 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
       for (;;) {
         if (mbar_try(&s_full[s], par)) { st = 1; break; }
         if (all_done && *ndone >= kPixelWarps) { st = 2; break; }
+        // park between probes: ncu (profiles/r02_fwd_spin.txt) counted 25 % of this kernel's executed instructions in
+        // these single-lane probe loops, most of them saturated warps waiting at the producer's frontier — issue slots
+        // the blending warps of the SM need
+        __nanosleep(all_done ? kParkNs : kSpinNs);
       }
     }
     st = __shfl_sync(0xffffffffu, st, 0);
@@ -402,6 +390,7 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
   __shared__ int s_ticket[kBwdStages];  // warps that have finished culling the stage's current batch
   __shared__ int s_cta_final;
   __shared__ int s_tile;
+  __shared__ int s_rk[RANKED ? kBwdStages : 1][RANKED ? kStageRecs : 1];  // RANKED: ranks of each slot's NEXT batch
 
   const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
   if (tr == 0) s_tile = draw_tile(order, sched, tbx * ((img_h + 15) >> 4));
@@ -465,11 +454,41 @@ __global__ void __launch_bounds__(kBwdThreads, 3) blend_bwd_mom_kernel(
     mbar_expect_tx(&s_full[s], bytes);
     bulk_g2s(s_rec + s * kStageRecs * 3, rec + (size_t)lo * 3, bytes, &s_full[s]);
   };
-  auto issue_ranked = [&](int k) {  // one whole warp
+  // One whole warp.  The ranks of batch k were copied into s_rk[slot] by the issue of batch k - kBwdStages (same slot;
+  // its arrival on the stage's barrier covers that copy, and this warp has since waited on that phase), so the warp
+  // that recycles a stage pays one L2 round trip (the gathers), not two.
+  auto issue_ranked = [&](int k) {
     const int s = k % kBwdStages;
     const int hi = last - k * kStageRecs;
     const int lo = max(range.x, hi - kStageRecs + 1);
-    stage_ranked(s_rec + s * kStageRecs * 3, rec, ranks + lo, hi - lo + 1, lane, &s_full[s]);
+    const int count = hi - lo + 1;
+    int r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = lane + 32 * i;
+      r[i] = (j < count) ? (k >= kBwdStages ? s_rk[s][j] : ranks[lo + j]) : -1;
+    }
+    float4* stage = s_rec + s * kStageRecs * 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (r[i] >= 0) {
+        const float4* src = rec + 3 * (size_t)r[i];
+        float4* dst = stage + 3 * (lane + 32 * i);
+        cp_async16(dst, src);
+        cp_async16(dst + 1, src + 1);
+        cp_async16(dst + 2, src + 2);
+      }
+    const int k2 = k + kBwdStages;
+    if (k2 < num_batches) {
+      const int hi2 = last - k2 * kStageRecs;
+      const int lo2 = max(range.x, hi2 - kStageRecs + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = lane + 32 * i;
+        if (j < hi2 - lo2 + 1) cp_async4(&s_rk[s][j], ranks + lo2 + j);
+      }
+    }
+    cp_async_arrive(&s_full[s]);
   };
   if (RANKED) {
     if (warp == 0)
@@ -710,8 +729,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
       const int s = b % kFwdStages;
       if (b >= kFwdStages) {
         const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
-        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
-        }
+        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) __nanosleep(kSpinNs);
         if (*ndone >= kPixelWarps) break;
       }
       const int start = range.x + b * kStageRecs;
@@ -752,6 +770,10 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
       for (;;) {
         if (mbar_try(&s_full[s], par)) { st = 1; break; }
         if (all_done && *ndone >= kPixelWarps) { st = 2; break; }
+        // park between probes: ncu (profiles/r02_fwd_spin.txt) counted 25 % of this kernel's executed instructions in
+        // these single-lane probe loops, most of them saturated warps waiting at the producer's frontier — issue slots
+        // the blending warps of the SM need
+        __nanosleep(all_done ? kParkNs : kSpinNs);
       }
     }
     st = __shfl_sync(0xffffffffu, st, 0);
