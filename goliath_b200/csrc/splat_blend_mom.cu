@@ -47,8 +47,6 @@ constexpr int kChunk = 16;            // hits per transposed-reduction chunk
 constexpr int kEntryCap = 48;         // pending entries per warp: < kChunk left over + up to 32 new
 constexpr int kMStride = 33;          // float2 row stride of the (hit, pixel) matrix: odd -> conflict-free both ways
 constexpr float kCullMargin = 2e-3f;  // slack of the exact cull test (ex2.approx / lg2.approx / rounding)
-constexpr unsigned kSpinNs = 32;      // forward: pause between barrier probes of a warp that waits for data / a free slot
-constexpr unsigned kParkNs = 200;     // forward: pause of a saturated warp (it only keeps the barrier phases aligned)
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -165,7 +163,8 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
         int go = 1;
         if (lane == 0) {
           const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
-          while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) __nanosleep(kSpinNs);
+          while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
+        }
           go = *ndone < kPixelWarps;
         }
         go = __shfl_sync(0xffffffffu, go, 0);
@@ -194,7 +193,8 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
       const int s = b % kFwdStages;
       if (b >= kFwdStages) {
         const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
-        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) __nanosleep(kSpinNs);
+        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
+        }
         if (*ndone >= kPixelWarps) break;  // every pixel of the tile is saturated: nothing more to fetch
       }
       const int start = range.x + b * kStageRecs;
@@ -234,10 +234,9 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_ilp_kernel(
       for (;;) {
         if (mbar_try(&s_full[s], par)) { st = 1; break; }
         if (all_done && *ndone >= kPixelWarps) { st = 2; break; }
-        // park between probes: ncu (profiles/r02_fwd_spin.txt) counted 25 % of this kernel's executed instructions in
-        // these single-lane probe loops, most of them saturated warps waiting at the producer's frontier — issue slots
-        // the blending warps of the SM need
-        __nanosleep(all_done ? kParkNs : kSpinNs);
+        // (ncu, profiles/r02_fwd_spin.txt: 25 % of this kernel's executed instructions are these single-lane probes, most
+        // of them saturated warps waiting at the producer's frontier.  Parking them with __nanosleep(32 / 200 ns) was
+        // measured SLOWER, 79.5 vs 74 us: the probes use issue slots nobody else wants, the wake-up latency is real.)
       }
     }
     st = __shfl_sync(0xffffffffu, st, 0);
@@ -729,7 +728,8 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
       const int s = b % kFwdStages;
       if (b >= kFwdStages) {
         const unsigned par = (unsigned)(((b / kFwdStages) - 1) & 1);
-        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) __nanosleep(kSpinNs);
+        while (!mbar_try(&s_empty[s], par) && *ndone < kPixelWarps) {
+        }
         if (*ndone >= kPixelWarps) break;
       }
       const int start = range.x + b * kStageRecs;
@@ -770,10 +770,9 @@ __global__ void __launch_bounds__(kFwdThreads) blend_fwd_multi_kernel(
       for (;;) {
         if (mbar_try(&s_full[s], par)) { st = 1; break; }
         if (all_done && *ndone >= kPixelWarps) { st = 2; break; }
-        // park between probes: ncu (profiles/r02_fwd_spin.txt) counted 25 % of this kernel's executed instructions in
-        // these single-lane probe loops, most of them saturated warps waiting at the producer's frontier — issue slots
-        // the blending warps of the SM need
-        __nanosleep(all_done ? kParkNs : kSpinNs);
+        // (ncu, profiles/r02_fwd_spin.txt: 25 % of this kernel's executed instructions are these single-lane probes, most
+        // of them saturated warps waiting at the producer's frontier.  Parking them with __nanosleep(32 / 200 ns) was
+        // measured SLOWER, 79.5 vs 74 us: the probes use issue slots nobody else wants, the wake-up latency is real.)
       }
     }
     st = __shfl_sync(0xffffffffu, st, 0);
