@@ -419,11 +419,13 @@ class HeadWorkload:
     def intersections(self, packed):
         return _count_intersections(packed, [self.cam["Rt"][0]], [self.cam["intr"]])
 
-    def compute(self, packed):
-        """forward + backward of one view from the flat decoded buffer; returns ([rgb, alpha, depth], flat grad)."""
+    def compute(self, packed, grad_out=None):
+        """forward + backward of one view from the flat decoded buffer; returns ([rgb, alpha, depth], flat grad).
+        grad_out: write the flat gradient there (the exchange's reduction buffer) instead of a new tensor."""
         leaves = {k: v.detach().requires_grad_() for k, v in unpack(packed).items()}
         rgb, alpha, depth = gpu_step(leaves, self.cam, self.li, capacity=self.cap)
-        grad = torch.cat([leaves[k].grad.reshape(-1) for k, _ in FIELDS])  # flat dL/d(decoded), same layout
+        parts = [leaves[k].grad.reshape(-1) for k, _ in FIELDS]  # flat dL/d(decoded), same layout
+        grad = torch.cat(parts) if grad_out is None else torch.cat(parts, out=grad_out)
         return [rgb, alpha, depth], grad
 
 
@@ -460,7 +462,7 @@ class OlatWorkload:
     def intersections(self, packed):
         return _count_intersections(packed, list(self.Rt), self.intr)
 
-    def compute(self, packed):
+    def compute(self, packed, grad_out=None):
         from goliath_b200.gsplat.olat import render_views_shared
         from goliath_b200.rgca_heads import shade_compose
 
@@ -473,7 +475,8 @@ class OlatWorkload:
         rgb, alpha, depth = render_views_shared(W, H, self.Rt, geom, colors[None].expand(V, *colors.shape), self.intr,
                                                 capacity=self.cap)
         torch.autograd.backward([rgb, depth], [torch.ones_like(rgb), torch.ones_like(depth)])
-        grad = torch.cat([u[k].grad.reshape(-1) for k, _ in FIELDS])
+        parts = [u[k].grad.reshape(-1) for k, _ in FIELDS]
+        grad = torch.cat(parts) if grad_out is None else torch.cat(parts, out=grad_out)
         return [rgb, alpha, depth], grad
 
 
@@ -500,6 +503,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # The two 22.8 MB collectives of a step run UNDER the neighbouring renders; what they cost the step is the SMs
+        # NCCL's CTAs take from the blend, not their own duration.  Measured at N = 4 (profiles/r02_nccl_ctas_n4.txt):
+        # 8 CTAs lengthen them to 0.15 + 0.20 ms (still hidden under the 0.4 ms render) and shorten the step by 5 %.
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
     from goliath_b200 import _lib
     from goliath_b200.dist import FrameExchange
@@ -521,21 +528,23 @@ def run_ours(args):
     static_in = torch.empty_like(resident)                    # the graph's input buffer (field-major decoded Gaussians)
     state = {"graph": None, "outs": None}
 
-    def build_graph():
-        """Capture compute(static_in) once (sync-free path), after side-stream warm-up as torch requires."""
+    def capture(inp, grad_out=None):
+        """Capture compute(inp) once (sync-free path), after side-stream warm-up as torch requires."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
-                wl.compute(static_in)
+                wl.compute(inp, grad_out)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         from goliath_b200.render import render_stream
-        # captured on a high-priority stream: the shade's side stream (lowest priority) then only takes what the binning
-        # kernels leave idle; kernel nodes keep the priority of the stream they were captured on
+        # (optionally) captured on a high-priority stream: see SHADE_STREAM / HIGH_PRIO above
         with torch.cuda.graph(g, stream=render_stream(dev) if HIGH_PRIO else None):
-            outs = wl.compute(static_in)
-        state["graph"], state["outs"] = g, outs
+            outs = wl.compute(inp, grad_out)
+        return g, outs
+
+    def build_graph():
+        state["graph"], state["outs"] = capture(static_in)
 
     def run_step():
         if state["graph"] is not None:
@@ -594,6 +603,21 @@ def run_ours(args):
         src = (host_packed if e2e else resident) if rank == 0 else None
         s_out = torch.cuda.Stream()
         main = torch.cuda.current_stream()
+        # one captured graph per buffer parity: the step reads the exchange's input buffer and writes its flat gradient
+        # into the exchange's reduction buffer, no device-to-device copy of either 22.8 MB table (GOLIATH_B200_EXCHANGE=copy
+        # keeps the round-1 protocol: copy in, copy out)
+        zero_copy = state["graph"] is not None and os.environ.get("GOLIATH_B200_EXCHANGE", "inplace") != "copy"
+        pg = None
+        if zero_copy:
+            if "pgraphs" not in state:
+                for k in range(2):
+                    ex.inputs[k].copy_(resident)
+                state["pgraphs"] = [capture(ex.inputs[k], ex.grads[k]) for k in range(2)]
+                state["pgraphs_ex"] = ex
+            else:  # graphs are bound to the first exchange's buffers: reuse it
+                ex = state["pgraphs_ex"]
+                ex.bytes_h2d = 0
+            pg = state["pgraphs"]
         stage_out = [[torch.empty_like(t) for t in state["outs"][0]] for _ in range(2)] if e2e else None
         hosts = [host_out, host_out2]
         out_ready = [torch.cuda.Event() for _ in range(2)]
@@ -606,11 +630,20 @@ def run_ours(args):
                 flush()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                ex.take_input(i, static_in)
-                if i + 1 < n:
-                    ex.post_input(i + 1, src)
-                imgs, grad = run_step()
-                ex.post_grad(i, grad)
+                if zero_copy:
+                    ex.wait_input(i)
+                    if i + 1 < n:
+                        ex.post_input(i + 1, src)
+                    pg[k][0].replay()
+                    imgs = pg[k][1][0]
+                    ex.release_input(i)
+                    ex.post_grad_inplace(i)
+                else:
+                    ex.take_input(i, static_in)
+                    if i + 1 < n:
+                        ex.post_input(i + 1, src)
+                    imgs, grad = run_step()
+                    ex.post_grad(i, grad)
                 if e2e:
                     if i >= 2:
                         main.wait_event(out_free[k])
@@ -780,6 +813,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict({"workload": wl.workload, "name": wl.key, "gaussians": G, "block_width": BW,
                         "l2": "flushed between timed steps (256 MiB write)", "parallelism": "view-shard x%d" % world,
+                        "nccl_max_ctas": None if world == 1 else os.environ.get("NCCL_MAX_CTAS"),
+                        "exchange": None if world == 1 else os.environ.get("GOLIATH_B200_EXCHANGE", "inplace"),
                         "collectives": (None if world == 1 else "goliath_b200.dist.FrameExchange: NCCL broadcast of frame "
                                         "i+1's decoded table from its owner and all-reduce of frame i's gradient on a "
                                         "communication stream under the neighbouring renders; only the owner reads its source"),
@@ -1534,6 +1569,17 @@ def run_decoder_library(args):
         ws[-1].grad = bs[-1].grad = h5g.grad = None
 
     res["last_layer_fwd_bwd_ms_library"] = timeit(last_fwd_bwd)
+    # the same with TF32 disallowed: cuDNN's fp32 kernels, the precision class of this repo's SIMT backward (the TF32
+    # numbers above are the precision class of the 3xTF32 tcgen05 forward only up to the 3x split)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            res["tower_vnocond_ms_library_fp32"] = timeit(lambda: tower(x))
+        res["tower_vnocond_fwd_bwd_ms_library_fp32"] = timeit(fwd_bwd)
+        res["last_layer_fwd_bwd_ms_library_fp32"] = timeit(last_fwd_bwd)
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
     print(json.dumps({"decoder_library": res}))
 
 

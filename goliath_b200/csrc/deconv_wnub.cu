@@ -13,6 +13,9 @@
 // 8x16 weights of the current input channel come from shared memory (weights as broadcast float4).  The tcgen05
 // phase-GEMM version (TF32x3, TMA-fed) is the planned successor; the last layers are bound by the
 // untied-bias + output traffic (1.07 GB for 16->125 @1024^2), not by FLOPs.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -499,9 +502,244 @@ __global__ void __launch_bounds__(256) deconv4x4s2_bwd_weight_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide backward kernels for the high-resolution layers (Cin <= 32, the same layers as the wide forward).  The two
+// kernels above move one shared-memory operand per 2.7 (data) / 3.2 (weight) FMAs and re-stage the gz tile with scalar
+// loads; at 16->125 @1024^2 the layer's backward is 8.4 G FMA each way over a 524 MB gradient.  Here:
+//  data:   a thread owns TWO horizontally adjacent input positions x 16 input channels in FFMA2 pairs (32 sums in 16
+//          64-bit registers); per output channel it reads its 4x6 window of gz (3 loads per row) once, and every 16-byte
+//          weight load (two channel pairs of one tap) feeds 4 FFMA2.  gz tiles (4 output channels x 34 x 66, 16-byte
+//          cp.async for the interior, zero-filled halo) and the weights are double-buffered.
+//  weight: lane = (4 input channels, 1 output channel, 16 taps) as above, but a step covers TWO adjacent positions: the
+//          6-wide gz rows are shared between them (12 loads + 4 x-pair loads for 128 FMAs), tiles are staged with
+//          cp.async and double-buffered.
+constexpr int DW_Y = 16, DW_X = 32;                 // input positions per CTA (256 threads x 2 positions)
+constexpr int DW_CO = 4, DW_CI = 16;
+constexpr int DW_GY = 2 * DW_Y + 2, DW_GS = 72;     // gz tile rows, row stride in floats (global column 2*tx0 at index 4)
+constexpr int DW_GBYTES = DW_CO * DW_GY * DW_GS * 4;   // 39168
+constexpr int DW_WBYTES = DW_CO * 16 * DW_CI * 4;      // 4096, layout [co][tap][ci]
+constexpr int DW_SMEM = 2 * (DW_GBYTES + DW_WBYTES);   // 86528
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// stage the gz tile of `nco` output channels starting at co0 into s_g [nco][rows][DW_GS]: rows 2*ty0-1 .. 2*ty0+rows-2,
+// global columns 2*tx0-1 .. 2*tx0+64 at indices 3 .. 68.  Requires Wo % 4 == 0 (16-byte chunks are inside or outside).
+template <int NCO, int ROWS>
+__device__ __forceinline__ void stage_gz_tile(float* s_g, const float* __restrict__ gzb, int co0, int Cout, int Ho, int Wo,
+                                              int ty0, int tx0, int tid) {
+  constexpr int kChunks = 16;  // 64 interior floats per row
+  for (int i = tid; i < NCO * ROWS * (kChunks + 2); i += 256) {
+    const int co = i / (ROWS * (kChunks + 2)), r = (i / (kChunks + 2)) % ROWS, c = i % (kChunks + 2);
+    const int Y = 2 * ty0 - 1 + r;
+    const bool rok = co0 + co < Cout && Y >= 0 && Y < Ho;
+    float* row = s_g + ((size_t)co * ROWS + r) * DW_GS;
+    const float* grow = gzb + ((size_t)(co0 + co) * Ho + (rok ? Y : 0)) * Wo;
+    if (c < kChunks) {
+      const int X = 2 * tx0 + 4 * c;
+      const bool ok = rok && X < Wo;
+      cp_async16_zfill(row + 4 + 4 * c, ok ? grow + X : gzb, ok);
+    } else {
+      const int X = (c == kChunks) ? 2 * tx0 - 1 : 2 * tx0 + 64;
+      const bool ok = rok && X >= 0 && X < Wo;
+      cp_async4_zfill(row + (c == kChunks ? 3 : 68), ok ? grow + X : gzb, ok);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) deconv4x4s2_bwd_data_wide_kernel(
+    int Cin, int Cout, int Hi, int Wi, const float* __restrict__ gz /* [B,Cout,2Hi,2Wi] */, const float* __restrict__ v,
+    const float* __restrict__ scale, float* __restrict__ gx /* [B,Cin,Hi,Wi] */) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int tiles_x = (Wi + DW_X - 1) / DW_X;
+  const int ty0 = (blockIdx.x / tiles_x) * DW_Y, tx0 = (blockIdx.x % tiles_x) * DW_X;
+  const int ci0 = blockIdx.y * DW_CI;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x, qy = tid >> 4, qx = tid & 15;
+  const int m = ty0 + qy, n = tx0 + 2 * qx;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const float* gzb = gz + (size_t)b * Cout * Ho * Wo;
+  auto g_buf = [&](int k) { return reinterpret_cast<float*>(dsm + (size_t)k * (DW_GBYTES + DW_WBYTES)); };
+  auto w_buf = [&](int k) { return reinterpret_cast<float*>(dsm + (size_t)k * (DW_GBYTES + DW_WBYTES) + DW_GBYTES); };
+  auto stage = [&](int k, int co0) {
+    stage_gz_tile<DW_CO, DW_GY>(g_buf(k), gzb, co0, Cout, Ho, Wo, ty0, tx0, tid);
+    float* sw = w_buf(k);
+    for (int i = tid; i < DW_CO * 16 * DW_CI; i += 256) {
+      const int ci = i / (DW_CO * 16), co = (i / 16) % DW_CO, t = i % 16;  // consecutive lanes read consecutive taps
+      const bool ok = ci0 + ci < Cin && co0 + co < Cout;
+      cp_async4_zfill(sw + (co * 16 + t) * DW_CI + ci, ok ? v + ((size_t)(ci0 + ci) * Cout + co0 + co) * 16 + t : v, ok);
+    }
+  };
+  unsigned long long acc[2][DW_CI / 2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int c = 0; c < DW_CI / 2; ++c) acc[p][c] = 0ull;
+
+  const int nblk = (Cout + DW_CO - 1) / DW_CO;
+  stage(0, 0);
+  gb::cp_async_commit();
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int k = blk & 1;
+    gb::cp_async_wait<0>();
+    __syncthreads();  // this block's tile has landed for everybody; everybody has left the previous block's FMA loop
+    if (blk + 1 < nblk) {
+      stage(k ^ 1, (blk + 1) * DW_CO);
+      gb::cp_async_commit();
+    }
+    const float* sg = g_buf(k);
+    const float* sw = w_buf(k);
+#pragma unroll 1
+    for (int co = 0; co < DW_CO; ++co) {
+      if (blk * DW_CO + co >= Cout) break;
+      const float sc = scale[blk * DW_CO + co];
+      unsigned long long G[4][6];  // rows 2m-1 .. 2m+2, columns 2n-1 .. 2n+4, scaled and duplicated
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float* rp = sg + ((size_t)co * DW_GY + 2 * qy + r) * DW_GS + 4 * qx + 3;
+        const float g0 = rp[0];
+        const float4 g14 = *reinterpret_cast<const float4*>(rp + 1);
+        const float g5 = rp[5];
+        const float gs[6] = {g0 * sc, g14.x * sc, g14.y * sc, g14.z * sc, g14.w * sc, g5 * sc};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) G[r][c] = pack2(gs[c], gs[c]);
+      }
+      const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(sw + (size_t)co * 16 * DW_CI);
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+#pragma unroll
+          for (int q = 0; q < DW_CI / 4; ++q) {
+            const ulonglong2 w2 = wp[(ky * 4 + kx) * (DW_CI / 4) + q];  // channel pairs 2q, 2q+1 of this tap
+            acc[0][2 * q] = ffma2(G[ky][kx], w2.x, acc[0][2 * q]);
+            acc[0][2 * q + 1] = ffma2(G[ky][kx], w2.y, acc[0][2 * q + 1]);
+            acc[1][2 * q] = ffma2(G[ky][kx + 2], w2.x, acc[1][2 * q]);
+            acc[1][2 * q + 1] = ffma2(G[ky][kx + 2], w2.y, acc[1][2 * q + 1]);
+          }
+        }
+    }
+  }
+  if (m >= Hi || n >= Wi) return;  // Wi and n are even: both positions are inside together
+  float* gxb = gx + (size_t)b * Cin * Hi * Wi;
+#pragma unroll
+  for (int c = 0; c < DW_CI / 2; ++c) {
+    const float2 a0 = unpack2(acc[0][c]), a1 = unpack2(acc[1][c]);
+    if (ci0 + 2 * c < Cin) *reinterpret_cast<float2*>(gxb + ((size_t)(ci0 + 2 * c) * Hi + m) * Wi + n) = make_float2(a0.x, a1.x);
+    if (ci0 + 2 * c + 1 < Cin)
+      *reinterpret_cast<float2*>(gxb + ((size_t)(ci0 + 2 * c + 1) * Hi + m) * Wi + n) = make_float2(a0.y, a1.y);
+  }
+}
+
+constexpr int WW_Y = 8, WW_X = 32;                 // input positions per staged tile
+constexpr int WW_CO = 8, WW_CI = 16;
+constexpr int WW_GY = 2 * WW_Y + 2;                // 18 gz rows
+constexpr int WW_XS = 36;                          // x row stride in floats (32 + pad, rows 16-byte aligned)
+constexpr int WW_XBYTES = WW_CI * WW_Y * WW_XS * 4;       // 18432
+constexpr int WW_GBYTES = WW_CO * WW_GY * DW_GS * 4;      // 41472
+constexpr int WW_SMEM = 2 * (WW_XBYTES + WW_GBYTES);      // 119808
+
+__global__ void __launch_bounds__(256, 1) deconv4x4s2_bwd_weight_wide_kernel(
+    int B, int Cin, int Cout, int Hi, int Wi, const float* __restrict__ x, const float* __restrict__ gz,
+    float* __restrict__ gw /* [Cin,Cout,4,4], accumulated */) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int ci0 = blockIdx.y * WW_CI, co0 = blockIdx.z * WW_CO;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cig = lane >> 3, col = lane & 7;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const int tiles_x = (Wi + WW_X - 1) / WW_X, tiles_y = (Hi + WW_Y - 1) / WW_Y;
+  const int total = B * tiles_x * tiles_y;
+  auto x_buf = [&](int k) { return reinterpret_cast<float*>(dsm + (size_t)k * (WW_XBYTES + WW_GBYTES)); };
+  auto g_buf = [&](int k) { return reinterpret_cast<float*>(dsm + (size_t)k * (WW_XBYTES + WW_GBYTES) + WW_XBYTES); };
+  auto stage = [&](int k, int t) {
+    const int b = t / (tiles_x * tiles_y), tt = t % (tiles_x * tiles_y);
+    const int ty0 = (tt / tiles_x) * WW_Y, tx0 = (tt % tiles_x) * WW_X;
+    float* sx = x_buf(k);
+    for (int i = tid; i < WW_CI * WW_Y * (WW_X / 4); i += 256) {  // 16-byte chunks: Wi % 4 == 0, tx0 % 32 == 0
+      const int ci = i / (WW_Y * (WW_X / 4)), r = (i / (WW_X / 4)) % WW_Y, c = i % (WW_X / 4);
+      const int yy = ty0 + r, xx = tx0 + 4 * c;
+      const bool ok = ci0 + ci < Cin && yy < Hi && xx < Wi;
+      cp_async16_zfill(sx + ((size_t)ci * WW_Y + r) * WW_XS + 4 * c,
+                       ok ? x + (((size_t)b * Cin + ci0 + ci) * Hi + yy) * Wi + xx : x, ok);
+    }
+    stage_gz_tile<WW_CO, WW_GY>(g_buf(k), gz + (size_t)b * Cout * Ho * Wo, co0, Cout, Ho, Wo, ty0, tx0, tid);
+  };
+  float acc[4][16];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc[a][t] = 0.f;
+
+  int it = 0;
+  if ((int)blockIdx.x < total) {
+    stage(0, blockIdx.x);
+    gb::cp_async_commit();
+  }
+  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int k = it & 1;
+    gb::cp_async_wait<0>();
+    __syncthreads();
+    if (t + (int)gridDim.x < total) {
+      stage(k ^ 1, t + gridDim.x);
+      gb::cp_async_commit();
+    }
+    const float* sx = x_buf(k);
+    const float* sg = g_buf(k) + (size_t)col * WW_GY * DW_GS;
+    // warp w: tile row w, 16 pairs of adjacent positions
+#pragma unroll 2
+    for (int pp = 0; pp < WW_X / 2; ++pp) {
+      const int py = warp, px = 2 * pp;
+      float2 xv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xv[a] = *reinterpret_cast<const float2*>(sx + ((size_t)(cig * 4 + a) * WW_Y + py) * WW_XS + px);
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const float* rp = sg + (size_t)(2 * py + ky) * DW_GS + 2 * px + 3;  // global column 2*(tx0+px) - 1
+        // 2*px + 3 = 4*pp + 3: one scalar, one aligned float4, one scalar
+        const float g0 = rp[0];
+        const float4 g14 = *reinterpret_cast<const float4*>(rp + 1);
+        const float g5 = rp[5];
+        const float g[6] = {g0, g14.x, g14.y, g14.z, g14.w, g5};
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[a][ky * 4 + kx] += xv[a].x * g[kx] + xv[a].y * g[kx + 2];
+      }
+    }
+  }
+  const int co = co0 + col;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int ci = ci0 + cig * 4 + a;
+    if (ci < Cin && co < Cout) {
+#pragma unroll
+      for (int t = 0; t < 16; t += 4)
+        gb::red_add_v4(gw + ((size_t)ci * Cout + co) * 16 + t, acc[a][t], acc[a][t + 1], acc[a][t + 2], acc[a][t + 3]);
+    }
+  }
+}
+
 }  // namespace
 
-// Backward of gb_deconv4x4s2_wnub_fwd.  gz [B,Cout,2Hi,2Wi] is scratch (pre-activation gradient), g_bias
+// GOLIATH_B200_DECONV_BWD=narrow keeps the round-1 backward kernels on every layer (A/B timing, tests)
+static bool wide_bwd_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GOLIATH_B200_DECONV_BWD");
+    v = (e && !strcmp(e, "narrow")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Backward of gb_deconv4x4s2_wnub_fwd.  gz [B,Cout,2Hi,2Wi] is scratch (pre-activation gradient; may be gout itself when
+// apply_act == 0 and g_bias == NULL: nothing is copied), g_bias
 // [Cout,2Hi,2Wi] or NULL, gx [B,Cin,Hi,Wi] or NULL, gw [Cin,Cout,4,4] is ACCUMULATED into (caller zeroes it) and is the
 // gradient w.r.t. the un-normalised direction tensor v at unit scale (d out / d (scale*v) contracted with v's slot):
 // gw[ci,co,k] = sum x * gz; the caller applies the weight-norm chain rule.
@@ -511,8 +749,42 @@ GB_API int gb_deconv4x4s2_wnub_bwd(int B, int Cin, int Cout, int Hi, int Wi, con
   if (B <= 0 || Cin <= 0 || Cout <= 0 || Hi <= 0 || Wi <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const long long per_item = (long long)Cout * 4 * Hi * Wi;
-  deconv_act_bwd_kernel<<<(unsigned)gb::cdiv64(per_item, 256), 256, 0, s>>>(B, per_item, gout, out, slope, apply_act, gz, g_bias);
-  int launches = 1;
+  // gz == gout with no activation and no separate bias gradient: the pre-activation gradient IS gout (the caller
+  // aliases the untied-bias gradient to it when B == 1) — no 3 x 524 MB copy pass at the 16->125 @1024^2 layer
+  const bool alias = (gz == gout) && !apply_act && !g_bias;
+  int launches = 0;
+  if (!alias) {
+    deconv_act_bwd_kernel<<<(unsigned)gb::cdiv64(per_item, 256), 256, 0, s>>>(B, per_item, gout, out, slope, apply_act,
+                                                                              gz, g_bias);
+    launches = 1;
+  }
+  // high-resolution layers (the wide forward's condition, plus 16-byte staging: Wi % 4 == 0): wide backward kernels
+  const bool wide = Cin <= 32 && Wi % 4 == 0 && Wi >= 32 && Hi >= 16 && wide_bwd_enabled();
+  if (wide) {
+    static bool configured = false;
+    if (!configured) {
+      GB_CUDA(cudaFuncSetAttribute(deconv4x4s2_bwd_data_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+      GB_CUDA(cudaFuncSetAttribute(deconv4x4s2_bwd_weight_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM));
+      configured = true;
+    }
+    if (gx) {
+      dim3 grid(gb::cdiv(Hi, DW_Y) * gb::cdiv(Wi, DW_X), gb::cdiv(Cin, DW_CI), B);
+      deconv4x4s2_bwd_data_wide_kernel<<<grid, 256, DW_SMEM, s>>>(Cin, Cout, Hi, Wi, gz, v, scale, gx);
+      ++launches;
+    }
+    if (gw) {
+      const int total = B * gb::cdiv(Hi, WW_Y) * gb::cdiv(Wi, WW_X);
+      const int pairs = gb::cdiv(Cin, WW_CI) * gb::cdiv(Cout, WW_CO);
+      int split = gb::cdiv(gb::kNumSMs * 2, pairs);  // one CTA per SM at a time (120 KB of shared memory), two waves
+      split = max(1, min(split, total));
+      dim3 grid(split, gb::cdiv(Cin, WW_CI), gb::cdiv(Cout, WW_CO));
+      deconv4x4s2_bwd_weight_wide_kernel<<<grid, 256, WW_SMEM, s>>>(B, Cin, Cout, Hi, Wi, x, gz, gw);
+      ++launches;
+    }
+    gb::count_launches(launches);
+    GB_CHECK_LAUNCH();
+    return 0;
+  }
   if (gx) {
     dim3 grid(gb::cdiv(Hi, BD_T) * gb::cdiv(Wi, BD_T), gb::cdiv(Cin, BD_CI), B);
     deconv4x4s2_bwd_data_kernel<<<grid, BD_T * BD_T, 0, s>>>(Cin, Cout, Hi, Wi, gz, v, scale, gx);

@@ -61,8 +61,10 @@ class FrameExchange:
         self.grads = [torch.empty(numel, dtype=dtype, device=self.device) for _ in range(2)]
         if self.cuda:
             self.comm = torch.cuda.Stream(device=self.device)
+            self.h2d = torch.cuda.Stream(device=self.device)  # owner: host table -> device, beside the collectives
             ev = lambda: [torch.cuda.Event() for _ in range(2)]
             self.in_ready, self.in_free, self.g_ready, self.g_free = ev(), ev(), ev(), ev()
+            self.h2d_done = ev()
         self.bytes_h2d = 0  # host bytes this rank copied in (owner only)
 
     def post_input(self, i: int, source: Optional[torch.Tensor], ready: Optional["torch.cuda.Event"] = None):
@@ -77,15 +79,25 @@ class FrameExchange:
                 self.inputs[k].copy_(source)
             owner_broadcast(self.inputs[k], self.owner)
             return
+        if is_owner and source.device.type != "cuda":
+            # a host table goes in on its own stream: the 22.8 MB PCIe copy of frame i+1 then runs beside the previous
+            # frame's collectives instead of in front of them on the communication stream
+            self.bytes_h2d += source.numel() * source.element_size()
+            with torch.cuda.stream(self.h2d):
+                if i >= 2:
+                    self.h2d.wait_event(self.in_free[k])
+                self.inputs[k].copy_(source, non_blocking=True)
+                self.h2d_done[k].record(self.h2d)
         with torch.cuda.stream(self.comm):
             if i >= 2:
                 self.comm.wait_event(self.in_free[k])
             if is_owner:  # only the owner reads its source; non-owners receive over NVLink
-                if ready is not None:
-                    self.comm.wait_event(ready)
                 if source.device.type != "cuda":
-                    self.bytes_h2d += source.numel() * source.element_size()
-                self.inputs[k].copy_(source, non_blocking=True)
+                    self.comm.wait_event(self.h2d_done[k])
+                else:
+                    if ready is not None:
+                        self.comm.wait_event(ready)
+                    self.inputs[k].copy_(source, non_blocking=True)
             owner_broadcast(self.inputs[k], self.owner)
             self.in_ready[k].record(self.comm)
 
@@ -118,6 +130,43 @@ class FrameExchange:
     def grad(self, i: int) -> torch.Tensor:
         return self.grads[i & 1]
 
+    # ---- zero-copy variant: the step reads inputs[i & 1] and writes its gradient into grads[i & 1] directly (one
+    # captured graph per buffer parity), so neither table is copied on the device:
+    #     ex.post_input(0, source)
+    #     for i in range(n):
+    #         ex.wait_input(i)                      # main stream: frame i's table has arrived in ex.inputs[i & 1]
+    #         if i + 1 < n: ex.post_input(i + 1, source)
+    #         ... step reading ex.inputs[i & 1], writing ex.grads[i & 1] ...
+    #         ex.release_input(i)
+    #         ex.post_grad_inplace(i)               # all-reduce of ex.grads[i & 1] on the communication stream
+    #     ex.finish()
+    def wait_input(self, i: int):
+        """Main stream waits for frame i's table in inputs[i & 1] and for the reduction that last used grads[i & 1]."""
+        if not self.cuda:
+            return
+        k = i & 1
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self.in_ready[k])
+        if i >= 2:
+            main.wait_event(self.g_free[k])
+
+    def release_input(self, i: int):
+        if self.cuda:
+            self.in_free[i & 1].record(torch.cuda.current_stream(self.device))
+
+    def post_grad_inplace(self, i: int):
+        k = i & 1
+        if not self.cuda:
+            reduce_grads(self.grads[k])
+            return
+        main = torch.cuda.current_stream(self.device)
+        self.g_ready[k].record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.g_ready[k])
+            reduce_grads(self.grads[k])
+            self.g_free[k].record(self.comm)
+
     def finish(self):
         if self.cuda:
             torch.cuda.current_stream(self.device).wait_stream(self.comm)
+            torch.cuda.current_stream(self.device).wait_stream(self.h2d)

@@ -52,8 +52,16 @@ class _Deconv4x4s2WNUB(Function):
         gout = gout.contiguous()
         vnorm = v.norm()
         scale = (g.reshape(-1) / vnorm).contiguous()
-        gz = torch.empty_like(out)                       # scratch: gradient w.r.t. the pre-activation
-        gb = torch.empty(Cout, 2 * Hi, 2 * Wi, device=dev, dtype=torch.float32) if ctx.has_bias else None
+        # the untied bias has one entry per output element, so with B == 1 its gradient IS the pre-activation gradient:
+        # alias instead of writing it a second time; without an activation the pre-activation gradient is gout itself
+        alias_bias = ctx.has_bias and B == 1
+        if B == 1 and ctx.slope is None:
+            gz = gout                                    # nothing to compute, nothing to copy
+        else:
+            gz = torch.empty_like(out)                   # scratch: gradient w.r.t. the pre-activation
+        gb = None
+        if ctx.has_bias and not alias_bias:
+            gb = torch.empty(Cout, 2 * Hi, 2 * Wi, device=dev, dtype=torch.float32)
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gw = torch.zeros_like(v)                         # d L / d (effective weight), accumulated by the kernel
         with torch.cuda.device(dev):
@@ -61,6 +69,8 @@ class _Deconv4x4s2WNUB(Function):
                 B, Cin, Cout, Hi, Wi, _lib.ptr(x), _lib.ptr(v), _lib.ptr(scale), _lib.ptr(out), _lib.ptr(gout),
                 float(ctx.slope if ctx.slope is not None else 1.0), int(ctx.slope is not None), _lib.ptr(gz), _lib.ptr(gb),
                 _lib.ptr(gx), _lib.ptr(gw), _lib.stream_ptr(dev)), "deconv4x4s2_wnub_bwd")
+        if alias_bias:
+            gb = gz.view(Cout, 2 * Hi, 2 * Wi)
         # weight-norm chain rule on the small [Cin,Cout,4,4] tensors:  w = g * v / n,  n = ||v||_F
         w = g * v / vnorm
         gg = (gw * v).sum(dim=(0, 2, 3), keepdim=True) / vnorm

@@ -110,6 +110,21 @@ def _exchange_worker(rank, world, port, q):
         ex.post_grad(i, static_in * (rank + 1))        # rank r contributes (r+1) * table
         sums.append(float(ex.grad(i)[0]))
     ex.finish()
+    # zero-copy variant: the step reads ex.inputs[i & 1] and writes ex.grads[i & 1] in place
+    ex2 = FrameExchange(n, "cpu", owner=0)
+    seen2, sums2 = [], []
+    ex2.post_input(0, frames[0])
+    for i in range(3):
+        ex2.wait_input(i)
+        if i + 1 < 3:
+            ex2.post_input(i + 1, frames[i + 1])
+        seen2.append(float(ex2.inputs[i & 1][0]))
+        ex2.grads[i & 1].copy_(ex2.inputs[i & 1] * (rank + 1))
+        ex2.release_input(i)
+        ex2.post_grad_inplace(i)
+        sums2.append(float(ex2.grad(i)[0]))
+    ex2.finish()
+    assert seen2 == seen and sums2 == sums, (seen2, sums2)
     bad = None
     if rank != 0:
         try:

@@ -56,6 +56,46 @@ def test_deconv_kernel_vs_torch(cuda, shape):
     assert_close(t2n(y), ref.detach().numpy(), rtol=1e-4, atol=1e-5 * float(ref.abs().max()), what="deconv %s" % (shape,))
 
 
+@pytest.mark.parametrize("shape,slope", [((1, 16, 125, 64, 48), None), ((1, 16, 125, 64, 48), 0.2), ((2, 32, 16, 32, 64), 0.2),
+                                         ((1, 8, 12, 24, 36), 0.2), ((1, 20, 6, 16, 32), None), ((1, 3, 5, 17, 33), 0.2),
+                                         ((2, 264, 40, 8, 8), 0.2)])
+def test_deconv_backward_vs_torch(cuda, shape, slope):
+    """Every gradient of the fused layer (input, weight_v, weight_g, untied bias) against torch autograd of the reference
+    formula in fp64 (layers.py:200-204,380-396): the wide backward kernels (Cin <= 32, Wi % 4 == 0, >= 32 x 16: full and
+    partial tiles, one and two channel blocks, batch 2, with and without the fused LeakyReLU, incl. the B == 1 aliasing of
+    the bias gradient) and the narrow ones."""
+    from goliath_b200 import nn as gnn
+
+    B, Cin, Cout, Hi, Wi = shape
+    gen = torch.Generator().manual_seed(Cin * 11 + Cout + Wi)
+    layer = gnn.ConvTranspose2dWNUB(Cin, Cout, 2 * Hi, 2 * Wi)
+    with torch.no_grad():
+        layer.weight_v.copy_(torch.randn(layer.weight_v.shape, generator=gen) * 0.1)
+        layer.weight_g.copy_(torch.rand(layer.weight_g.shape, generator=gen) + 0.5)
+        layer.bias.copy_(torch.randn(layer.bias.shape, generator=gen))
+    x = torch.randn(B, Cin, Hi, Wi, generator=gen)
+    go = torch.randn(B, Cout, 2 * Hi, 2 * Wi, generator=gen)
+    # reference
+    v = layer.weight_v.detach().double().requires_grad_()
+    g = layer.weight_g.detach().double().requires_grad_()
+    bias = layer.bias.detach().double().requires_grad_()
+    xr = x.double().requires_grad_()
+    y = torch.nn.functional.conv_transpose2d(xr, g * v / v.norm(), None, 2, 1) + bias[None]
+    if slope is not None:
+        y = torch.nn.functional.leaky_relu(y, slope)
+    y.backward(go.double())
+    # ours
+    layer = layer.to(cuda)
+    xc = x.to(cuda).requires_grad_()
+    yc = layer(xc, slope=slope)
+    yc.backward(go.to(cuda))
+    assert_close(t2n(yc), y.detach().numpy(), rtol=1e-4, atol=1e-5 * float(y.abs().max()), what="forward")
+    for name, got, want in (("x", xc.grad, xr.grad), ("weight_v", layer.weight_v.grad, v.grad),
+                            ("weight_g", layer.weight_g.grad, g.grad), ("bias", layer.bias.grad, bias.grad)):
+        want = want.numpy()
+        assert_close(t2n(got), want, rtol=2e-4, atol=2e-5 * float(np.abs(want).max()), what="grad %s %s" % (name, shape))
+
+
 def test_linear_wn_vs_reference(cuda):
     from goliath_b200 import nn as gnn
 
