@@ -532,7 +532,7 @@ __device__ __forceinline__ unsigned long long pack2(float a, float b) {
 
 // stage the gz tile of `nco` output channels starting at co0 into s_g [nco][rows][DW_GS]: rows 2*ty0-1 .. 2*ty0+rows-2,
 // global columns 2*tx0-1 .. 2*tx0+64 at indices 3 .. 68.  Requires Wo % 4 == 0 (16-byte chunks are inside or outside).
-template <int NCO, int ROWS>
+template <int NCO, int ROWS, int PLANE>
 __device__ __forceinline__ void stage_gz_tile(float* s_g, const float* __restrict__ gzb, int co0, int Cout, int Ho, int Wo,
                                               int ty0, int tx0, int tid) {
   constexpr int kChunks = 16;  // 64 interior floats per row
@@ -540,7 +540,7 @@ __device__ __forceinline__ void stage_gz_tile(float* s_g, const float* __restric
     const int co = i / (ROWS * (kChunks + 2)), r = (i / (kChunks + 2)) % ROWS, c = i % (kChunks + 2);
     const int Y = 2 * ty0 - 1 + r;
     const bool rok = co0 + co < Cout && Y >= 0 && Y < Ho;
-    float* row = s_g + ((size_t)co * ROWS + r) * DW_GS;
+    float* row = s_g + (size_t)co * PLANE + (size_t)r * DW_GS;
     const float* grow = gzb + ((size_t)(co0 + co) * Ho + (rok ? Y : 0)) * Wo;
     if (c < kChunks) {
       const int X = 2 * tx0 + 4 * c;
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(256, 2) deconv4x4s2_bwd_data_wide_kernel(
   auto g_buf = [&](int k) { return reinterpret_cast<float*>(dsm + (size_t)k * (DW_GBYTES + DW_WBYTES)); };
   auto w_buf = [&](int k) { return reinterpret_cast<float*>(dsm + (size_t)k * (DW_GBYTES + DW_WBYTES) + DW_GBYTES); };
   auto stage = [&](int k, int co0) {
-    stage_gz_tile<DW_CO, DW_GY>(g_buf(k), gzb, co0, Cout, Ho, Wo, ty0, tx0, tid);
+    stage_gz_tile<DW_CO, DW_GY, DW_GY * DW_GS>(g_buf(k), gzb, co0, Cout, Ho, Wo, ty0, tx0, tid);
     float* sw = w_buf(k);
     for (int i = tid; i < DW_CO * 16 * DW_CI; i += 256) {
       const int ci = i / (DW_CO * 16), co = (i / 16) % DW_CO, t = i % 16;  // consecutive lanes read consecutive taps
@@ -642,9 +642,14 @@ constexpr int WW_Y = 8, WW_X = 32;                 // input positions per staged
 constexpr int WW_CO = 8, WW_CI = 16;
 constexpr int WW_GY = 2 * WW_Y + 2;                // 18 gz rows
 constexpr int WW_XS = 36;                          // x row stride in floats (32 + pad, rows 16-byte aligned)
-constexpr int WW_XBYTES = WW_CI * WW_Y * WW_XS * 4;       // 18432
-constexpr int WW_GBYTES = WW_CO * WW_GY * DW_GS * 4;      // 41472
-constexpr int WW_SMEM = 2 * (WW_XBYTES + WW_GBYTES);      // 119808
+// plane strides = 16 bytes mod 128: the 4 channel groups (x, 8-byte loads) and the 8 output channels (gz, 16-byte loads)
+// that the lanes of a warp address in one instruction then fall into distinct banks.  (First version: strides of 0 / 64
+// bytes mod 128, 4-way conflicts on every operand load, 1.35 ms for the two wide layers.)
+constexpr int WW_XP = WW_Y * WW_XS + 4;            // 292 floats
+constexpr int WW_GP = WW_GY * DW_GS + 20;          // 1316 floats
+constexpr int WW_XBYTES = WW_CI * WW_XP * 4;              // 18688
+constexpr int WW_GBYTES = WW_CO * WW_GP * 4;              // 42112
+constexpr int WW_SMEM = 2 * (WW_XBYTES + WW_GBYTES);      // 121600
 
 __global__ void __launch_bounds__(256, 1) deconv4x4s2_bwd_weight_wide_kernel(
     int B, int Cin, int Cout, int Hi, int Wi, const float* __restrict__ x, const float* __restrict__ gz,
@@ -666,10 +671,10 @@ __global__ void __launch_bounds__(256, 1) deconv4x4s2_bwd_weight_wide_kernel(
       const int ci = i / (WW_Y * (WW_X / 4)), r = (i / (WW_X / 4)) % WW_Y, c = i % (WW_X / 4);
       const int yy = ty0 + r, xx = tx0 + 4 * c;
       const bool ok = ci0 + ci < Cin && yy < Hi && xx < Wi;
-      cp_async16_zfill(sx + ((size_t)ci * WW_Y + r) * WW_XS + 4 * c,
+      cp_async16_zfill(sx + (size_t)ci * WW_XP + (size_t)r * WW_XS + 4 * c,
                        ok ? x + (((size_t)b * Cin + ci0 + ci) * Hi + yy) * Wi + xx : x, ok);
     }
-    stage_gz_tile<WW_CO, WW_GY>(g_buf(k), gz + (size_t)b * Cout * Ho * Wo, co0, Cout, Ho, Wo, ty0, tx0, tid);
+    stage_gz_tile<WW_CO, WW_GY, WW_GP>(g_buf(k), gz + (size_t)b * Cout * Ho * Wo, co0, Cout, Ho, Wo, ty0, tx0, tid);
   };
   float acc[4][16];
 #pragma unroll
@@ -691,14 +696,15 @@ __global__ void __launch_bounds__(256, 1) deconv4x4s2_bwd_weight_wide_kernel(
       gb::cp_async_commit();
     }
     const float* sx = x_buf(k);
-    const float* sg = g_buf(k) + (size_t)col * WW_GY * DW_GS;
+    const float* sg = g_buf(k) + (size_t)col * WW_GP;
     // warp w: tile row w, 16 pairs of adjacent positions
 #pragma unroll 2
     for (int pp = 0; pp < WW_X / 2; ++pp) {
       const int py = warp, px = 2 * pp;
       float2 xv[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) xv[a] = *reinterpret_cast<const float2*>(sx + ((size_t)(cig * 4 + a) * WW_Y + py) * WW_XS + px);
+      for (int a = 0; a < 4; ++a)  // lane's channels: a * 4 + cig (adjacent planes across the channel groups)
+        xv[a] = *reinterpret_cast<const float2*>(sx + (size_t)(a * 4 + cig) * WW_XP + (size_t)py * WW_XS + px);
 #pragma unroll
       for (int ky = 0; ky < 4; ++ky) {
         const float* rp = sg + (size_t)(2 * py + ky) * DW_GS + 2 * px + 3;  // global column 2*(tx0+px) - 1
@@ -717,7 +723,7 @@ __global__ void __launch_bounds__(256, 1) deconv4x4s2_bwd_weight_wide_kernel(
   const int co = co0 + col;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int ci = ci0 + cig * 4 + a;
+    const int ci = ci0 + a * 4 + cig;
     if (ci < Cin && co < Cout) {
 #pragma unroll
       for (int t = 0; t < 16; t += 4)
@@ -775,7 +781,7 @@ GB_API int gb_deconv4x4s2_wnub_bwd(int B, int Cin, int Cout, int Hi, int Wi, con
     if (gw) {
       const int total = B * gb::cdiv(Hi, WW_Y) * gb::cdiv(Wi, WW_X);
       const int pairs = gb::cdiv(Cin, WW_CI) * gb::cdiv(Cout, WW_CO);
-      int split = gb::cdiv(gb::kNumSMs * 2, pairs);  // one CTA per SM at a time (120 KB of shared memory), two waves
+      int split = (gb::kNumSMs * 2) / pairs;  // one CTA per SM at a time (120 KB of shared memory): two FULL waves
       split = max(1, min(split, total));
       dim3 grid(split, gb::cdiv(Cin, WW_CI), gb::cdiv(Cout, WW_CO));
       deconv4x4s2_bwd_weight_wide_kernel<<<grid, 256, WW_SMEM, s>>>(B, Cin, Cout, Hi, Wi, x, gz, gw);
