@@ -506,7 +506,9 @@ def run_ours(args):
         # The two 22.8 MB collectives of a step run UNDER the neighbouring renders; what they cost the step is the SMs
         # NCCL's CTAs take from the blend, not their own duration.  Measured at N = 4 (profiles/r02_nccl_ctas_n4.txt):
         # 8 CTAs lengthen them to 0.15 + 0.20 ms (still hidden under the 0.4 ms render) and shorten the step by 5 %.
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # At N = 2 the library default is better by 2 % (profiles/r02_exchange_n2.txt): the cap applies from N = 4.
+        if world >= 4:
+            os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
     from goliath_b200 import _lib
     from goliath_b200.dist import FrameExchange
