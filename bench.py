@@ -506,9 +506,10 @@ def run_ours(args):
         # The two 22.8 MB collectives of a step run UNDER the neighbouring renders; what they cost the step is the SMs
         # NCCL's CTAs take from the blend, not their own duration.  Measured at N = 4 (profiles/r02_nccl_ctas_n4.txt):
         # 8 CTAs lengthen them to 0.15 + 0.20 ms (still hidden under the 0.4 ms render) and shorten the step by 5 %.
-        # At N = 2 the library default is better by 2 % (profiles/r02_exchange_n2.txt): the cap applies from N = 4.
+        # At N = 2 the library default is better by 2 % (profiles/r02_exchange_n2.txt); at N = 8 a cap of 16 gives 11 107
+        # MP/s, 8 gives 9 797 and 4 gives 7 390 (profiles/r02_nccl_ctas_n8.txt): two CTAs per peer from N = 4.
         if world >= 4:
-            os.environ.setdefault("NCCL_MAX_CTAS", "8")
+            os.environ.setdefault("NCCL_MAX_CTAS", str(2 * world))
         dist.init_process_group("nccl", device_id=dev)
     from goliath_b200 import _lib
     from goliath_b200.dist import FrameExchange
