@@ -468,8 +468,11 @@ __global__ void __launch_bounds__(kRankBlock) rank_sort_coop_kernel(
   }
 }
 
-// ------------------------------------------------------------------ 2c. depth ranks by buckets (default)
-// The cooperative LSD sort above is latency-bound: 147 CTAs of 8 warps walk 3 passes of dependent L2 round trips and
+// ------------------------------------------------------------------ 2c. depth ranks by buckets (option, measured slower)
+// MEASURED (profiles/r02_launches_head_buckets.txt): steps (1)-(3) below take 8 + 5 + 12 us, but step (4), the n^2 in-bucket
+// ranking, executes 25.6 M warp instructions and takes 65 us at 300 k keys -- the cooperative sort stays the default; the
+// code is kept for GOLIATH_B200_RANKSORT=buckets and as the tested fallback protocol (device flag -> cooperative sort).
+// The idea: the cooperative LSD sort above is latency-bound: 147 CTAs of 8 warps walk 3 passes of dependent L2 round trips and
 // grid barriers (ncu: 6 % issue-active, 44 us for 300 k keys).  The ranks only have to order the VISIBLE Gaussians
 // by (depth bits, id), so: (1) the visible keys are dealt into 2048 buckets that split [min key, max key] evenly
 // (monotone in the key: bucket order == depth order), counts privatised per CTA; (2) one CTA scans the counts;

@@ -518,9 +518,9 @@ def test_render_views_fused_matches_reference_sequence(cuda):
 
 @pytest.fixture(params=["buckets+split", "coop+split", "passes+fused", "buckets+fused"])
 def rank_sort(request):
-    """variants of the bucket binning: depth ranks by 2048 key buckets + in-bucket ranking (default, cooperative LSD
-    fallback for degenerate depth distributions), as one cooperative LSD kernel over the varying key bits, or as the
-    four radix passes of round 1; per-tile ordering as bitmap sort + grid-wide record gather (default) or as the
+    """variants of the bucket binning: depth ranks by 2048 key buckets + in-bucket ranking (cooperative LSD fallback for
+    degenerate depth distributions), as one cooperative LSD kernel over the varying key bits (default), or as the four
+    radix passes of round 1; per-tile ordering as bitmap sort + grid-wide record gather (default) or as the
     single per-tile kernel of round 1"""
     from goliath_b200 import _lib
 
