@@ -10,10 +10,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "goliath_b200", "build")
-WATCH = ("UTCHMMA", "UTCQMMA", "UTCMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "REDG", "RED.", "ATOMS", "ATOMG",
+WATCH = ("FFMA2", "UTCHMMA", "UTCQMMA", "UTCMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "REDG", "RED.", "ATOMS", "ATOMG",
          "MUFU", "SHFL", "HMMA", "LDGSTS", "BAR.SYNC", "MATCH", "VOTE")
 TARGETS = {
-    "splat_blend_mom": ("blend_bwd_mom_kernelILi4", "profiles/r02_sass_splat_blend_mom.txt"),
+    "splat_blend_mom": ("blend_fwd_ilp_kernelILi4ELb1ELb0", "profiles/r02_sass_splat_blend_mom.txt"),
+    "deconv_wnub": ("deconv4x4s2_bwd_data_wide_kernel", "profiles/r02_sass_deconv_wnub.txt"),
     "deconv_tc": ("deconv_tc_kernel", "profiles/r02_sass_deconv_tc.txt"),
     "mvp_raymarch": ("raymarch_fwd_kernelILb0ELb0", "profiles/r02_sass_mvp_raymarch.txt"),
     "splat_bin_tiles": ("rank_sort_coop_kernelILi8", "profiles/r02_sass_splat_bin_tiles.txt"),
