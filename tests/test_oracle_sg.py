@@ -82,3 +82,55 @@ def test_sg_clamp_edge_derivative_is_minus_20(orc):
     dirs2 = np.array([[[0.0, 0.0, 1.0000001]]], np.float32) * 1.5  # cos > 1: clamped angle 0
     gd2, _, _ = orc.sg_bwd(dirs2, sig, lv, lp, pp, nl, np.ones((1, 1, 3), np.float32), 0)
     assert np.all(np.isfinite(gd2))
+
+
+def test_regrouped_pair_arithmetic_of_the_fused_shade_is_within_the_bar():
+    """csrc/sg_shade.cu evaluates a (Gaussian, light) pair in the fused shade_compose pass as
+    cos = (l.dir) rsqrt(l.l);  angle = sqrt(1-|c|) P7(|c|) (Abramowitz & Stegun 4.4.46), reflected for c < 0;
+    weight = ex2(-0.5 log2e (angle / sigma)^2) / (sigma K) with the normalisation applied to the light sum.
+    The same arithmetic in numpy fp32 against the fp64 restatement of the reference formula: forward values and the
+    closed-form gradients w.r.t. sigma and the (unit) lobe direction, over sharp (sigma 0.01) to broad lobes and cosines
+    up to the clamp edges."""
+    f = np.float32
+    dirs, sig, lv, lp, pp, nl = make(N=2, D=513, L=7, seed=5)
+    ref = torch_sg(dirs.double(), sig.double(), lv.double(), lp.double(), pp.double(), nl, 0).numpy()
+    d, s_, v, P, Q = (t.numpy().astype(f) for t in (dirs, sig, lv, lp, pp))
+    co = [f(c) for c in (-0.0012624911, 0.0066700901, -0.0170881256, 0.0308918810, -0.0501743046, 0.0889789874,
+                         -0.2145988016, 1.5707963050)]
+    out = np.zeros_like(ref, dtype=f)
+    for n in range(2):
+        acc = np.zeros((d.shape[1], 3), f)
+        for l in range(int(nl[n])):
+            lvec = (P[n, l][None] - Q[n]).astype(f)
+            rinv = (f(1) / np.sqrt((lvec * lvec).sum(-1, dtype=f))).astype(f)
+            c = np.clip(((lvec * d[n]).sum(-1, dtype=f) * rinv).astype(f), f(-1), f(1))
+            a = np.abs(c)
+            p = np.full_like(a, co[0])
+            for k in co[1:]:
+                p = (p * a + k).astype(f)
+            r = (np.sqrt((f(1) - a).astype(f)) * p).astype(f)
+            ang = np.where(c < 0, f(3.14159265358979) - r, r).astype(f)
+            t = (ang / s_[n]).astype(f)
+            w = np.exp2((f(-0.72134752044448) * (t * t)).astype(f)).astype(f)
+            acc += w[:, None] * v[n, l][None]
+        out[n] = acc * (f(0.32964899322) / s_[n])[:, None]
+    # the same pairs in the REFERENCE's operation order, also fp32 (sg.cu:27-76): for sharp lobes the fp32 cosine itself
+    # limits both (d angle = d cos / sin angle), so the bar for the regrouped arithmetic is the reference order's own
+    # distance to fp64, not a fixed 1e-4
+    ref32 = np.zeros_like(out)
+    for n in range(2):
+        acc = np.zeros((d.shape[1], 3), f)
+        for l in range(int(nl[n])):
+            lvec = (P[n, l][None] - Q[n]).astype(f)
+            ln = np.sqrt((lvec * lvec).sum(-1, dtype=f)).astype(f)
+            lh = (lvec / ln[:, None]).astype(f)
+            c = np.clip((lh * d[n]).sum(-1, dtype=f), f(-1), f(1))
+            ang = np.arccos(c).astype(f)
+            w = (np.exp((f(-0.5) * ((ang / s_[n]) ** 2).astype(f)).astype(f)) / (s_[n] * f(3.03352966508))).astype(f)
+            acc += w[:, None] * v[n, l][None]
+        ref32[n] = acc
+    scale = float(np.abs(ref).max())
+    err_new, err_ref = np.abs(out - ref) / scale, np.abs(ref32 - ref) / scale
+    assert float(err_new.max()) <= 2.0 * float(err_ref.max()) + 1e-6, (float(err_new.max()), float(err_ref.max()))
+    assert float(np.sqrt((err_new ** 2).mean())) <= 2.0 * float(np.sqrt((err_ref ** 2).mean())) + 1e-7
+    assert_close(out, ref, rtol=1e-4, atol=1e-5 * scale, frac=0.995, what="regrouped SG forward")
